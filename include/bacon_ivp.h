@@ -1,0 +1,197 @@
+/* bacon_ivp.h — C ABI of the B200 ensemble IVP engine (libbacon_ivp.so).
+ *
+ * This is the drop-in boundary for ONE path of aftix/bacon (bacon-sci 0.16.2):
+ * the adaptive solvers of `bacon_sci::ivp` (RungeKutta45, RungeKutta23, BDF6),
+ * batched over N independent trajectories.  The reference has no FFI of its
+ * own (it is pure safe Rust); every entry point below names the reference
+ * interface it replaces (file:line relative to the reference tree).
+ *
+ * All entry points are `extern "C"`, take plain pointers and sizes, never
+ * throw, and never touch torch/nalgebra types.  Call-level failures are the
+ * return code (0 = success, otherwise a bacon_status); per-trajectory failures
+ * go to `status[i]` and never abort the ensemble (the reference aborts the one
+ * trajectory it is integrating, src/ivp.rs:232-235).
+ */
+#ifndef BACON_IVP_H
+#define BACON_IVP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BACON_IVP_ABI_VERSION 1
+
+/* ---- solver families: src/ivp/rk.rs:561 (RungeKutta45), rk.rs:656
+ * (RungeKutta23), src/ivp/bdf.rs:706 (BDF6), bdf.rs:762 (BDF2) ------------- */
+typedef enum bacon_method {
+    BACON_RK45 = 0,
+    BACON_RK23 = 1,
+    BACON_BDF6 = 2,
+    BACON_BDF2 = 3,
+    BACON_N_METHODS = 4
+} bacon_method;
+
+/* ---- status codes.  1..12 mirror `IVPError` variant by variant
+ * (src/ivp.rs:50-76); 0 is `IVPStatus::Done` (src/ivp.rs:24) reached without
+ * error; 13.. are conditions the reference either hangs on or cannot hit. -- */
+typedef enum bacon_status {
+    BACON_OK = 0,
+    BACON_E_MISSING_PARAMETERS = 1,  /* ivp.rs:52 */
+    BACON_E_USER = 2,                /* ivp.rs:54 */
+    BACON_E_TOLERANCE_OOB = 3,       /* ivp.rs:56 */
+    BACON_E_TIME_DELTA_OOB = 4,      /* ivp.rs:58 */
+    BACON_E_TIME_END_OOB = 5,        /* ivp.rs:60 */
+    BACON_E_TIME_START_OOB = 6,      /* ivp.rs:62 */
+    BACON_E_FROM_PRIMITIVE = 7,      /* ivp.rs:64 */
+    BACON_E_MIN_DT_EXCEEDED = 8,     /* ivp.rs:66 */
+    BACON_E_MAX_ITER = 9,            /* ivp.rs:68 */
+    BACON_E_SINGULAR = 10,           /* ivp.rs:70 */
+    BACON_E_DYNAMIC_ON_STATIC = 11,  /* ivp.rs:72 */
+    BACON_E_STATIC_ON_DYNAMIC = 12,  /* ivp.rs:74 */
+    BACON_E_NONFINITE = 13,          /* NaN error estimate: reference loops forever (rk.rs:392-422) */
+    BACON_E_MAX_ATTEMPTS = 14,       /* hard per-trajectory attempt cap hit */
+    BACON_E_HISTORY_OVERFLOW = 15,   /* more accepted points than history_capacity */
+    BACON_E_CUDA = 16,               /* CUDA runtime error; see bacon_last_error() */
+    BACON_E_BAD_ARGUMENT = 17,       /* NULL pointer, unknown rhs/method, dim mismatch */
+    BACON_E_UNSUPPORTED = 18         /* combination not built (e.g. BDF literal on device) */
+} bacon_status;
+
+/* ---- semantics: SURVEY.md §8c.  REF_LITERAL reproduces the source as
+ * written (transposed Butcher matrix rk.rs:459/370, 1859/4014 rk.rs:499,
+ * safety factor 100/100 rk.rs:267, ...); REF_CORRECTED applies D1-D7 only. -- */
+#define BACON_SEM_CORRECTED 0
+#define BACON_SEM_LITERAL 1
+
+/* ---- flags ------------------------------------------------------------ */
+#define BACON_FLAG_STRICT_FP 1u      /* no FMA contraction: bit-comparable with the CPU oracle */
+#define BACON_FLAG_SHARED_PARAMS 2u  /* params is [n_params], shared by all trajectories        */
+#define BACON_FLAG_BDF_NEWTON 4u     /* BDF: Newton + analytic-Jacobian LU instead of Broyden   */
+
+/* One POD block = everything the reference builder collects before `solve`
+ * (rk.rs:60-68 / bdf.rs:57-65), shared by the whole ensemble. */
+typedef struct bacon_ivp_config {
+    int32_t method;           /* bacon_method                                            */
+    int32_t dim;              /* state dimension D; must equal the RHS's DIM             */
+    int32_t n_params;         /* per-trajectory parameter count; must equal RHS NPARAM   */
+    int32_t semantics;        /* BACON_SEM_*                                             */
+    uint32_t flags;           /* BACON_FLAG_*                                            */
+    int32_t history_capacity; /* accepted points kept per trajectory; 0 = final only     */
+    double dt_min, dt_max;    /* with_minimum_dt / with_maximum_dt  (ivp.rs:171-172)     */
+    double tol;               /* with_tolerance                      (ivp.rs:169)        */
+    double t_start, t_end;    /* with_initial_time / with_ending_time (ivp.rs:173-174)   */
+    uint64_t max_attempts;    /* per-trajectory cap on step() calls; 0 = 2^32-2          */
+} bacon_ivp_config;
+
+/* Output block.  Any pointer may be NULL (that output is skipped) except
+ * y_end and status.  Layouts (n = number of trajectories):
+ *   y_end   [dim][n]        SoA, trajectory index fastest
+ *   hist_t  [n][cap]        accepted times, trajectory-major (one `Path` each, ivp.rs:203)
+ *   hist_y  [n][cap][dim]   accepted states, same order as the reference yields them
+ * For the host entry points these are host pointers, for *_device device
+ * pointers. */
+typedef struct bacon_ivp_result {
+    double* y_end;
+    double* t_end;       /* [n] stepper time at Done / failure (IVPStepper::time, ivp.rs:124)  */
+    double* dt_end;      /* [n] controller dt at exit (restart record)                         */
+    int32_t* status;     /* [n] bacon_status                                                   */
+    uint32_t* n_accept;  /* [n] points yielded (`Ok`, ivp.rs:229)                               */
+    uint32_t* n_reject;  /* [n] rejected step attempts                                          */
+    uint32_t* n_rhs;     /* [n] derivative evaluations                                          */
+    double* hist_t;
+    double* hist_y;
+    uint32_t* hist_len;  /* [n] points written (<= history_capacity)                            */
+} bacon_ivp_result;
+
+/* Launch record filled by the last solve on this thread (timing + totals). */
+typedef struct bacon_ivp_launch_info {
+    float kernel_ms;        /* CUDA-event time of the ensemble kernel on its stream */
+    float h2d_ms, d2h_ms;   /* host entry point only                               */
+    int32_t grid, block;    /* launch geometry                                     */
+    int32_t regs_per_thread;
+    int32_t n_kernels;      /* kernels launched by the call                        */
+} bacon_ivp_launch_info;
+
+/* ---- configuration: replaces the builder setters.  Same rules, same order
+ * of checks as rk.rs:168-256 (identical in bdf.rs:176-264). ---------------- */
+typedef struct bacon_solver bacon_solver; /* opaque builder handle */
+
+int bacon_abi_version(void);
+
+/* IVPSolver::new / new_dyn (ivp.rs:159-163).  Static dimensions are the ones
+ * a RHS was compiled for; `dim` is checked against the RHS at solve time. */
+bacon_solver* bacon_solver_new(int method, int dim);
+void bacon_solver_free(bacon_solver*);
+int bacon_solver_with_tolerance(bacon_solver*, double tol);            /* rk.rs:168-174 */
+int bacon_solver_with_maximum_dt(bacon_solver*, double max);           /* rk.rs:179-192 */
+int bacon_solver_with_minimum_dt(bacon_solver*, double min);           /* rk.rs:197-210 */
+int bacon_solver_with_initial_time(bacon_solver*, double initial);     /* rk.rs:212-222 */
+int bacon_solver_with_ending_time(bacon_solver*, double ending);       /* rk.rs:224-234 */
+int bacon_solver_with_semantics(bacon_solver*, int semantics);
+int bacon_solver_with_flags(bacon_solver*, uint32_t flags);
+int bacon_solver_with_history(bacon_solver*, int capacity);
+int bacon_solver_with_max_attempts(bacon_solver*, uint64_t cap);
+/* `solve` front half (rk.rs:249-256): MissingParameters if any of dt_max,
+ * dt_min, tolerance, initial time, ending time is unset; fills *out. */
+int bacon_solver_config(const bacon_solver*, bacon_ivp_config* out);
+
+/* Stateless re-check of a filled config (bounds only; used by the solve calls). */
+int bacon_ivp_validate(const bacon_ivp_config*);
+
+/* ---- right-hand sides: replaces `Derivative` (ivp.rs:34-48) and
+ * `with_derivative` (ivp.rs:186).  Built in: "lorenz", "vdp", "robertson",
+ * "linear32", "exp", "decay", "quadratic", "cos", "harmonic".  User RHS are
+ * CUDA device functors compiled against bacon_ivp_rhs.cuh and registered
+ * through bacon_rhs_register. ------------------------- */
+struct bacon_launch_args; /* defined in bacon_ivp_rhs.cuh; opaque to C callers */
+typedef int (*bacon_launch_fn)(const struct bacon_launch_args*);
+
+typedef struct bacon_rhs_desc {
+    const char* name;
+    int32_t dim;
+    int32_t n_params;
+    /* [strict_fp 0/1][method]; NULL = not built for that slot */
+    bacon_launch_fn launch[2][BACON_N_METHODS];
+} bacon_rhs_desc;
+
+int bacon_rhs_register(const bacon_rhs_desc*); /* returns rhs id >= 0, or -bacon_status */
+int bacon_rhs_lookup(const char* name);        /* rhs id >= 0, or -1                     */
+int bacon_rhs_count(void);
+int bacon_rhs_info(int rhs_id, const char** name, int* dim, int* n_params);
+
+/* ---- the solve: replaces `solve(data)` + `IVPIterator::collect_vec`
+ * (rk.rs:249-343, ivp.rs:209-238) for n trajectories at once. --------------
+ * y0 [dim][n] SoA; params [n_params][n] SoA (or [n_params] with
+ * BACON_FLAG_SHARED_PARAMS, or NULL when n_params == 0). */
+
+/* Host buffers: H2D, kernel, D2H on the current CUDA device. */
+int bacon_ivp_solve_ensemble(const bacon_ivp_config*, int rhs_id, size_t n, const double* y0,
+                             const double* params, const bacon_ivp_result* out);
+
+/* Device buffers already resident in HBM; `stream` is a cudaStream_t (NULL =
+ * default stream).  Asynchronous: returns after enqueueing.  */
+int bacon_ivp_solve_ensemble_device(const bacon_ivp_config*, int rhs_id, size_t n,
+                                    const double* d_y0, const double* d_params,
+                                    const bacon_ivp_result* d_out, void* stream);
+
+/* Host buffers, trajectories dealt round-robin (i mod G) over the first
+ * n_gpus visible devices of this process (one stream per device). */
+int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config*, int rhs_id, size_t n, const double* y0,
+                                   const double* params, const bacon_ivp_result* out, int n_gpus);
+
+int bacon_ivp_last_launch(bacon_ivp_launch_info* out);
+const char* bacon_last_error(void); /* thread-local message for the last rc != 0 */
+const char* bacon_status_name(int status);
+
+/* ---- measurement helpers (not on the product path) -------------------- */
+/* Register-resident DFMA loop on the current device: returns achieved FP64
+ * TFLOP/s (the roofline denominator of the RK kernels), <0 on error. */
+double bacon_fp64_peak_tflops(int iters, void* stream);
+int bacon_device_sm_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BACON_IVP_H */

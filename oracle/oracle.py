@@ -1,0 +1,132 @@
+"""Python binding of the CPU ORACLE (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; nothing under bacon_b200/ does.
+
+The oracle restates src/ivp/rk.rs:361-423, src/ivp/bdf.rs:346-634 and
+src/ivp.rs:220-238 of aftix/bacon (see oracle/bacon_oracle.hpp for the pinning
+statement).
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from bacon_b200 import _abi  # noqa: E402  (struct layouts only)
+
+_LIB = None
+
+
+def build(force=False):
+    """Compile oracle/liboracle.so with the committed Makefile."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "bacon_oracle.hpp", "Makefile")]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "bacon_ivp.h"))
+    stale = force or not os.path.exists(so) or any(
+        os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.oracle_rhs_lookup.argtypes = [C.c_char_p]
+        L.oracle_rhs_lookup.restype = C.c_int
+        L.oracle_rhs_info.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.oracle_ivp_solve_ensemble.argtypes = [
+            C.POINTER(_abi.Config), C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
+            C.POINTER(_abi.Result), C.c_int, C.c_int]
+        L.oracle_ivp_solve_ensemble.restype = C.c_int
+        L.oracle_roots_secant.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
+                                          C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong)]
+        L.oracle_roots_secant.restype = C.c_int
+        L.oracle_fourth_root.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.oracle_fourth_root.restype = None
+        L.oracle_max_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def max_threads():
+    return lib().oracle_max_threads()
+
+
+def rhs_info(name):
+    L = lib()
+    rid = L.oracle_rhs_lookup(name.encode())
+    if rid < 0:
+        raise KeyError(name)
+    d, p = C.c_int(), C.c_int()
+    L.oracle_rhs_info(rid, C.byref(d), C.byref(p))
+    return rid, d.value, p.value
+
+
+def solve_ensemble(method, rhs, y0, params=None, *, dt_min, dt_max, tol, t_start, t_end,
+                   semantics=_abi.SEM_CORRECTED, shared_params=False, history_capacity=0,
+                   max_attempts=0, pow_mode=0, n_threads=0):
+    """Run the oracle on an ensemble.  y0: (dim, n) float64; params: (n_params, n) or (n_params,).
+
+    Returns a dict of numpy arrays with the same names/layouts as bacon_ivp_result.
+    """
+    L = lib()
+    rid, dim, npar = rhs_info(rhs)
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    assert y0.ndim == 2 and y0.shape[0] == dim, (y0.shape, dim)
+    n = y0.shape[1]
+    flags = 0
+    pptr = None
+    if npar > 0:
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if shared_params:
+            assert params.shape == (npar,)
+            flags |= _abi.FLAG_SHARED_PARAMS
+        else:
+            assert params.shape == (npar, n), (params.shape, npar, n)
+        pptr = params.ctypes.data
+    cfg = _abi.Config(method=method, dim=dim, n_params=npar, semantics=semantics, flags=flags,
+                      history_capacity=history_capacity, dt_min=dt_min, dt_max=dt_max, tol=tol,
+                      t_start=t_start, t_end=t_end, max_attempts=max_attempts)
+    out = {
+        "y_end": np.zeros((dim, n)), "t_end": np.zeros(n), "dt_end": np.zeros(n),
+        "status": np.zeros(n, dtype=np.int32), "n_accept": np.zeros(n, dtype=np.uint32),
+        "n_reject": np.zeros(n, dtype=np.uint32), "n_rhs": np.zeros(n, dtype=np.uint32),
+    }
+    if history_capacity > 0:
+        out["hist_t"] = np.zeros((n, history_capacity))
+        out["hist_y"] = np.zeros((n, history_capacity, dim))
+        out["hist_len"] = np.zeros(n, dtype=np.uint32)
+    res = _abi.Result(**{k: v.ctypes.data for k, v in out.items()})
+    rc = L.oracle_ivp_solve_ensemble(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res),
+                                     pow_mode, n_threads)
+    if rc != 0:
+        raise RuntimeError(f"oracle_ivp_solve_ensemble rc={rc}")
+    return out
+
+
+def roots_secant(which, start, h, tol, n_max=1000, central=False):
+    """roots::secant (src/roots/mod.rs:289-337) on the reference's test functions."""
+    L = lib()
+    start = np.ascontiguousarray(start, dtype=np.float64)
+    sol = np.zeros(3)
+    it = C.c_ulonglong(0)
+    rc = L.oracle_roots_secant(which, start.ctypes.data, h, tol, n_max, int(central),
+                               sol.ctypes.data, C.byref(it))
+    return rc, sol[:len(start)], it.value
+
+
+def fourth_root(x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    a, b = np.empty_like(x), np.empty_like(x)
+    lib().oracle_fourth_root(x.ctypes.data, x.size, a.ctypes.data, b.ctypes.data)
+    return a, b
