@@ -38,7 +38,7 @@ STATUS_NAMES = {
 }
 
 SEM_CORRECTED, SEM_LITERAL = 0, 1
-FLAG_STRICT_FP, FLAG_SHARED_PARAMS, FLAG_BDF_NEWTON = 1, 2, 4
+FLAG_STRICT_FP, FLAG_SHARED_PARAMS, FLAG_BDF_NEWTON, FLAG_PARAMS_AOS = 1, 2, 4, 8
 
 
 class Config(C.Structure):

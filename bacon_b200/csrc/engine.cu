@@ -1,0 +1,680 @@
+// engine.cu — the C ABI of libbacon_ivp.so (include/bacon_ivp.h): builder handle,
+// RHS registry, and the three solve entry points (device-resident, host buffers,
+// host buffers sharded over the GPUs of one box).  No torch, no CPU fallback:
+// every solve ends in a CUDA kernel launch or an error code.
+//
+// Reference interfaces replaced (file:line relative to aftix/bacon):
+//   builder setters + validation        src/ivp/rk.rs:168-256 (same in bdf.rs:176-264)
+//   `solve(data)` + collect_vec         src/ivp/rk.rs:249-343, src/ivp.rs:209-238
+//   `Derivative` / with_derivative      src/ivp.rs:34-48, :186
+//   IVPError / IVPStatus                src/ivp.rs:20-28, :50-76
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bacon_ivp.h"
+#include "ivp_common.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+thread_local bacon_ivp_launch_info g_last_launch = {};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(BACON_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),   \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+// ---------------------------------------------------------------- RHS registry
+struct RhsEntry {
+    std::string name;
+    int dim, n_params;
+    bacon_launch_fn launch[2][BACON_N_METHODS];
+};
+struct Registry {
+    std::mutex mu;
+    std::vector<RhsEntry> entries;
+};
+Registry& registry() {
+    static Registry* r = new Registry();  // leaked on purpose: RHS translation units register during static init
+    return *r;
+}
+
+// ---------------------------------------------------------------- per-device context
+constexpr int kCounterSlots = 256;
+struct DeviceCtx {
+    bool ready = false;
+    int sm_count = 0;
+    unsigned long long* counters = nullptr;  // ring of work counters, one per in-flight launch
+    int next_counter = 0;
+    cudaStream_t stream = nullptr;           // used by the host-buffer entry points
+    cudaEvent_t ev[4] = {};
+    // grow-only device staging for the host-buffer entry points
+    void* d_buf = nullptr;
+    size_t d_cap = 0;
+    // pinned host staging for the multi-GPU entry point
+    void* h_buf = nullptr;
+    size_t h_cap = 0;
+};
+std::mutex g_ctx_mu;
+DeviceCtx g_ctx[64];
+
+int get_ctx(int dev, DeviceCtx** out) {
+    if (dev < 0 || dev >= 64) return fail(BACON_E_BAD_ARGUMENT, "device index %d out of range", dev);
+    DeviceCtx& c = g_ctx[dev];
+    if (!c.ready) {
+        CUDA_TRY(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaMalloc(&c.counters, sizeof(unsigned long long) * kCounterSlots));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        for (auto& e : c.ev) CUDA_TRY(cudaEventCreate(&e));
+        c.ready = true;
+    }
+    *out = &c;
+    return 0;
+}
+
+int ensure_device_buf(DeviceCtx& c, size_t bytes) {
+    if (bytes <= c.d_cap) return 0;
+    if (c.d_buf) CUDA_TRY(cudaFree(c.d_buf));
+    c.d_buf = nullptr;
+    c.d_cap = 0;
+    CUDA_TRY(cudaMalloc(&c.d_buf, bytes));
+    c.d_cap = bytes;
+    return 0;
+}
+int ensure_host_buf(DeviceCtx& c, size_t bytes) {
+    if (bytes <= c.h_cap) return 0;
+    if (c.h_buf) CUDA_TRY(cudaFreeHost(c.h_buf));
+    c.h_buf = nullptr;
+    c.h_cap = 0;
+    CUDA_TRY(cudaMallocHost(&c.h_buf, bytes));
+    c.h_cap = bytes;
+    return 0;
+}
+
+// thread-local timing events of the device entry point (one pair per device)
+struct TlEvents {
+    cudaEvent_t start[64] = {}, stop[64] = {};
+    int last_dev = -1;
+    bool pending = false;
+};
+thread_local TlEvents g_tl;
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// carve the outputs (and optionally inputs) of one shard out of a device buffer
+struct Carve {
+    unsigned char* base;
+    size_t off = 0;
+    explicit Carve(void* b) : base((unsigned char*)b) {}
+    template <class T> T* take(size_t count) {
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += align_up(count * sizeof(T), 256);
+        return p;
+    }
+};
+
+struct ShardLayout {
+    double* y0;
+    double* params;
+    bacon_ivp_result out;
+    size_t bytes;
+};
+
+// which outputs the caller asked for decides what is allocated and copied back
+ShardLayout layout_shard(void* base, const bacon_ivp_config& cfg, size_t n, bool shared_params,
+                         const bacon_ivp_result& want) {
+    Carve c(base);
+    ShardLayout L{};
+    L.y0 = c.take<double>((size_t)cfg.dim * n);
+    L.params = cfg.n_params > 0 ? c.take<double>(shared_params ? (size_t)cfg.n_params : (size_t)cfg.n_params * n) : nullptr;
+    L.out.y_end = c.take<double>((size_t)cfg.dim * n);
+    L.out.t_end = want.t_end ? c.take<double>(n) : nullptr;
+    L.out.dt_end = want.dt_end ? c.take<double>(n) : nullptr;
+    L.out.status = c.take<int32_t>(n);
+    L.out.n_accept = want.n_accept ? c.take<uint32_t>(n) : nullptr;
+    L.out.n_reject = want.n_reject ? c.take<uint32_t>(n) : nullptr;
+    L.out.n_rhs = want.n_rhs ? c.take<uint32_t>(n) : nullptr;
+    const size_t cap = cfg.history_capacity > 0 ? (size_t)cfg.history_capacity : 0;
+    L.out.hist_t = cap ? c.take<double>(n * cap) : nullptr;
+    L.out.hist_y = cap ? c.take<double>(n * cap * (size_t)cfg.dim) : nullptr;
+    L.out.hist_len = (cap && want.hist_len) ? c.take<uint32_t>(n) : nullptr;
+    L.bytes = c.off;
+    return L;
+}
+
+int check_common(const bacon_ivp_config* cfg, int rhs_id, const double* y0, const double* params,
+                 const bacon_ivp_result* out, RhsEntry* entry, bacon_launch_fn* fn) {
+    if (!cfg || !out) return fail(BACON_E_BAD_ARGUMENT, "cfg and out must not be NULL");
+    const int v = bacon_ivp_validate(cfg);
+    if (v != 0) return v;
+    {
+        Registry& r = registry();
+        std::lock_guard<std::mutex> lk(r.mu);
+        if (rhs_id < 0 || rhs_id >= (int)r.entries.size()) return fail(BACON_E_BAD_ARGUMENT, "unknown rhs id %d", rhs_id);
+        *entry = r.entries[rhs_id];
+    }
+    if (cfg->dim != entry->dim)
+        return fail(BACON_E_BAD_ARGUMENT, "cfg.dim=%d but rhs '%s' has DIM=%d", cfg->dim, entry->name.c_str(), entry->dim);
+    if (cfg->n_params != entry->n_params)
+        return fail(BACON_E_BAD_ARGUMENT, "cfg.n_params=%d but rhs '%s' has NPARAM=%d", cfg->n_params,
+                    entry->name.c_str(), entry->n_params);
+    if (!y0 || !out->y_end || !out->status) return fail(BACON_E_BAD_ARGUMENT, "y0, out.y_end and out.status are required");
+    if (entry->n_params > 0 && !params) return fail(BACON_E_BAD_ARGUMENT, "rhs '%s' needs params", entry->name.c_str());
+    if (cfg->history_capacity > 0 && (!out->hist_t || !out->hist_y))
+        return fail(BACON_E_BAD_ARGUMENT, "history_capacity > 0 needs out.hist_t and out.hist_y");
+    // REF_LITERAL is the source as written, operation order included: only the strict kernels implement it
+    const int strict = ((cfg->flags & BACON_FLAG_STRICT_FP) || cfg->semantics == BACON_SEM_LITERAL) ? 1 : 0;
+    *fn = entry->launch[strict][cfg->method];
+    if (!*fn)
+        return fail(BACON_E_UNSUPPORTED, "rhs '%s' was not built for method %d (%s)", entry->name.c_str(), cfg->method,
+                    strict ? "strict" : "fast");
+    return 0;
+}
+
+int launch_on_device(const bacon_ivp_config* cfg, bacon_launch_fn fn, size_t n, const double* d_y0,
+                     const double* d_params, const bacon_ivp_result* d_out, cudaStream_t stream, int dev,
+                     DeviceCtx& ctx, cudaEvent_t ev_start, cudaEvent_t ev_stop, bacon_launch_args* filled) {
+    bacon_launch_args a{};
+    a.cfg = *cfg;
+    a.n = n;
+    a.y0 = d_y0;
+    a.params = d_params;
+    a.out = *d_out;
+    a.stream = stream;
+    a.sm_count = ctx.sm_count;
+    a.grid_override = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        a.work_counter = ctx.counters + ctx.next_counter;
+        ctx.next_counter = (ctx.next_counter + 1) % kCounterSlots;
+    }
+    (void)dev;
+    CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
+    if (ev_start) CUDA_TRY(cudaEventRecord(ev_start, stream));
+    const int rc = fn(&a);
+    if (rc != 0) return fail(rc, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (ev_stop) CUDA_TRY(cudaEventRecord(ev_stop, stream));
+    if (filled) *filled = a;
+    return 0;
+}
+
+}  // namespace
+
+// ===================================================================== C ABI
+extern "C" {
+
+int bacon_abi_version(void) { return BACON_IVP_ABI_VERSION; }
+
+const char* bacon_last_error(void) { return g_last_error.c_str(); }
+
+const char* bacon_status_name(int s) {
+    static const char* names[] = {"Ok", "MissingParameters", "UserError", "ToleranceOOB", "TimeDeltaOOB", "TimeEndOOB",
+                                  "TimeStartOOB", "FromPrimitiveFailure", "MinimumTimeDeltaExceeded",
+                                  "MaximumIterationsExceeded", "SingularMatrix", "DynamicOnStatic", "StaticOnDynamic",
+                                  "NonFinite", "MaxAttempts", "HistoryOverflow", "CudaError", "BadArgument", "Unsupported"};
+    if (s < 0 || s > BACON_E_UNSUPPORTED) return "Unknown";
+    return names[s];
+}
+
+// ---------------------------------------------------------------- builder (rk.rs:118-256)
+struct bacon_solver {
+    int method, dim;
+    bool has_tol, has_max, has_min, has_t0, has_t1;
+    double tol, dt_max, dt_min, t0, t1;
+    int semantics;
+    uint32_t flags;
+    int history;
+    uint64_t max_attempts;
+};
+
+bacon_solver* bacon_solver_new(int method, int dim) {
+    if (method < 0 || method >= BACON_N_METHODS) {
+        fail(BACON_E_BAD_ARGUMENT, "unknown method %d", method);
+        return nullptr;
+    }
+    if (dim < 1) {  // Dimension::dim_dyn of a zero-sized system is meaningless here (lib.rs:53-76)
+        fail(BACON_E_BAD_ARGUMENT, "dim must be >= 1");
+        return nullptr;
+    }
+    bacon_solver* s = new bacon_solver();
+    std::memset(s, 0, sizeof(*s));
+    s->method = method;
+    s->dim = dim;
+    return s;
+}
+void bacon_solver_free(bacon_solver* s) { delete s; }
+
+int bacon_solver_with_tolerance(bacon_solver* s, double tol) {
+    if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
+    if (tol <= 0.0) return fail(BACON_E_TOLERANCE_OOB, "tolerance must be > 0");  // rk.rs:169-171
+    s->tol = tol;
+    s->has_tol = true;
+    return 0;
+}
+int bacon_solver_with_maximum_dt(bacon_solver* s, double max) {
+    if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
+    if (max <= 0.0) return fail(BACON_E_TIME_DELTA_OOB, "maximum dt must be > 0");  // rk.rs:180-182
+    s->dt_max = max;
+    s->has_max = true;
+    if (s->has_min && s->dt_min > max) s->dt_min = max;  // rk.rs:185-189
+    return 0;
+}
+int bacon_solver_with_minimum_dt(bacon_solver* s, double min) {
+    if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
+    if (min <= 0.0) return fail(BACON_E_TIME_DELTA_OOB, "minimum dt must be > 0");  // rk.rs:198-200
+    s->dt_min = min;
+    s->has_min = true;
+    if (s->has_max && s->dt_max < min) s->dt_max = min;  // rk.rs:203-207
+    return 0;
+}
+int bacon_solver_with_initial_time(bacon_solver* s, double initial) {
+    if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
+    s->t0 = initial;  // stored first, then checked (rk.rs:213-219)
+    s->has_t0 = true;
+    if (s->has_t1 && s->t1 <= initial) return fail(BACON_E_TIME_START_OOB, "initial time must be before the ending time");
+    return 0;
+}
+int bacon_solver_with_ending_time(bacon_solver* s, double ending) {
+    if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
+    s->t1 = ending;  // rk.rs:225-231
+    s->has_t1 = true;
+    if (s->has_t0 && s->t0 >= ending) return fail(BACON_E_TIME_END_OOB, "ending time must be after the initial time");
+    return 0;
+}
+int bacon_solver_with_semantics(bacon_solver* s, int semantics) {
+    if (!s || (semantics != BACON_SEM_CORRECTED && semantics != BACON_SEM_LITERAL))
+        return fail(BACON_E_BAD_ARGUMENT, "bad semantics");
+    s->semantics = semantics;
+    return 0;
+}
+int bacon_solver_with_flags(bacon_solver* s, uint32_t flags) {
+    if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
+    s->flags = flags;
+    return 0;
+}
+int bacon_solver_with_history(bacon_solver* s, int capacity) {
+    if (!s || capacity < 0) return fail(BACON_E_BAD_ARGUMENT, "history capacity must be >= 0");
+    s->history = capacity;
+    return 0;
+}
+int bacon_solver_with_max_attempts(bacon_solver* s, uint64_t cap) {
+    if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
+    s->max_attempts = cap;
+    return 0;
+}
+int bacon_solver_config(const bacon_solver* s, bacon_ivp_config* out) {
+    if (!s || !out) return fail(BACON_E_BAD_ARGUMENT, "NULL argument");
+    // rk.rs:250-254, in the reference's order
+    if (!s->has_max || !s->has_min || !s->has_tol || !s->has_t0 || !s->has_t1)
+        return fail(BACON_E_MISSING_PARAMETERS, "dt_max, dt_min, tolerance, initial time and ending time are all required");
+    std::memset(out, 0, sizeof(*out));
+    out->method = s->method;
+    out->dim = s->dim;
+    out->n_params = 0;  // filled from the RHS by the caller
+    out->semantics = s->semantics;
+    out->flags = s->flags;
+    out->history_capacity = s->history;
+    out->dt_min = s->dt_min;
+    out->dt_max = s->dt_max;
+    out->tol = s->tol;
+    out->t_start = s->t0;
+    out->t_end = s->t1;
+    out->max_attempts = s->max_attempts;
+    return 0;
+}
+
+int bacon_ivp_validate(const bacon_ivp_config* c) {
+    if (!c) return fail(BACON_E_BAD_ARGUMENT, "NULL config");
+    if (c->method < 0 || c->method >= BACON_N_METHODS) return fail(BACON_E_BAD_ARGUMENT, "unknown method %d", c->method);
+    if (c->dim < 1) return fail(BACON_E_BAD_ARGUMENT, "dim must be >= 1");
+    if (c->n_params < 0 || c->history_capacity < 0) return fail(BACON_E_BAD_ARGUMENT, "negative size");
+    if (c->semantics != BACON_SEM_CORRECTED && c->semantics != BACON_SEM_LITERAL)
+        return fail(BACON_E_BAD_ARGUMENT, "bad semantics %d", c->semantics);
+    if (c->tol <= 0.0) return fail(BACON_E_TOLERANCE_OOB, "tolerance must be > 0");
+    if (c->dt_max <= 0.0 || c->dt_min <= 0.0) return fail(BACON_E_TIME_DELTA_OOB, "dt bounds must be > 0");
+    if (c->dt_min > c->dt_max) return fail(BACON_E_TIME_DELTA_OOB, "dt_min > dt_max");
+    if (c->t_end <= c->t_start) return fail(BACON_E_TIME_END_OOB, "t_end must be after t_start");
+    return 0;
+}
+
+// ---------------------------------------------------------------- registry
+int bacon_rhs_register(const bacon_rhs_desc* d) {
+    if (!d || !d->name || d->dim < 1 || d->n_params < 0) return -BACON_E_BAD_ARGUMENT;
+    Registry& r = registry();
+    std::lock_guard<std::mutex> lk(r.mu);
+    for (size_t i = 0; i < r.entries.size(); ++i) {
+        RhsEntry& e = r.entries[i];
+        if (e.name == d->name) {  // a second translation unit (e.g. the strict build) adds its launchers
+            if (e.dim != d->dim || e.n_params != d->n_params) return -BACON_E_BAD_ARGUMENT;
+            for (int s = 0; s < 2; ++s)
+                for (int m = 0; m < BACON_N_METHODS; ++m)
+                    if (d->launch[s][m]) e.launch[s][m] = d->launch[s][m];
+            return (int)i;
+        }
+    }
+    RhsEntry e;
+    e.name = d->name;
+    e.dim = d->dim;
+    e.n_params = d->n_params;
+    std::memcpy(e.launch, d->launch, sizeof(e.launch));
+    r.entries.push_back(e);
+    return (int)r.entries.size() - 1;
+}
+int bacon_rhs_lookup(const char* name) {
+    if (!name) return -1;
+    Registry& r = registry();
+    std::lock_guard<std::mutex> lk(r.mu);
+    for (size_t i = 0; i < r.entries.size(); ++i)
+        if (r.entries[i].name == name) return (int)i;
+    return -1;
+}
+int bacon_rhs_count(void) {
+    Registry& r = registry();
+    std::lock_guard<std::mutex> lk(r.mu);
+    return (int)r.entries.size();
+}
+int bacon_rhs_info(int id, const char** name, int* dim, int* n_params) {
+    Registry& r = registry();
+    std::lock_guard<std::mutex> lk(r.mu);
+    if (id < 0 || id >= (int)r.entries.size()) return fail(BACON_E_BAD_ARGUMENT, "unknown rhs id %d", id);
+    if (name) *name = r.entries[id].name.c_str();
+    if (dim) *dim = r.entries[id].dim;
+    if (n_params) *n_params = r.entries[id].n_params;
+    return 0;
+}
+
+// ---------------------------------------------------------------- solves
+int bacon_ivp_solve_ensemble_device(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* d_y0,
+                                    const double* d_params, const bacon_ivp_result* d_out, void* stream) {
+    RhsEntry entry;
+    bacon_launch_fn fn = nullptr;
+    int rc = check_common(cfg, rhs_id, d_y0, d_params, d_out, &entry, &fn);
+    if (rc != 0) return rc;
+    g_last_launch = bacon_ivp_launch_info{};
+    if (n == 0) return 0;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DeviceCtx* ctx = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        rc = get_ctx(dev, &ctx);
+    }
+    if (rc != 0) return rc;
+    if (!g_tl.start[dev]) {
+        CUDA_TRY(cudaEventCreate(&g_tl.start[dev]));
+        CUDA_TRY(cudaEventCreate(&g_tl.stop[dev]));
+    }
+    bacon_launch_args filled{};
+    rc = launch_on_device(cfg, fn, n, d_y0, d_params, d_out, (cudaStream_t)stream, dev, *ctx, g_tl.start[dev],
+                          g_tl.stop[dev], &filled);
+    if (rc != 0) return rc;
+    g_tl.last_dev = dev;
+    g_tl.pending = true;
+    g_last_launch.grid = filled.grid;
+    g_last_launch.block = filled.block;
+    g_last_launch.regs_per_thread = filled.regs_per_thread;
+    g_last_launch.n_kernels = filled.n_kernels;
+    return 0;
+}
+
+int bacon_ivp_solve_ensemble(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0, const double* params,
+                             const bacon_ivp_result* out) {
+    return bacon_ivp_solve_ensemble_multi(cfg, rhs_id, n, y0, params, out, 1);
+}
+
+// Round-robin sharding (trajectory i -> GPU i mod G): parameter
+// sweeps stay balanced, no data-path collective.  With G == 1 the shard IS the
+// caller's buffer and no repacking happens.
+int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0,
+                                   const double* params, const bacon_ivp_result* out, int n_gpus) {
+    RhsEntry entry;
+    bacon_launch_fn fn = nullptr;
+    int rc = check_common(cfg, rhs_id, y0, params, out, &entry, &fn);
+    if (rc != 0) return rc;
+    g_last_launch = bacon_ivp_launch_info{};
+    g_tl.pending = false;
+    if (n == 0) return 0;
+    int have = 0;
+    CUDA_TRY(cudaGetDeviceCount(&have));
+    if (n_gpus < 1 || n_gpus > have) return fail(BACON_E_BAD_ARGUMENT, "n_gpus=%d but %d device(s) visible", n_gpus, have);
+    int dev0 = 0;
+    CUDA_TRY(cudaGetDevice(&dev0));
+    const int G = n_gpus;
+    const bool shared = (cfg->flags & BACON_FLAG_SHARED_PARAMS) != 0;
+    const int D = cfg->dim, P = cfg->n_params;
+    const size_t cap = cfg->history_capacity > 0 ? (size_t)cfg->history_capacity : 0;
+
+    struct Shard {
+        int dev;
+        size_t n;
+        DeviceCtx* ctx;
+        ShardLayout dl, hl;  // device / pinned-host layouts
+        bacon_launch_args filled;
+    };
+    std::vector<Shard> shards(G);
+    std::lock_guard<std::mutex> lk_all(g_ctx_mu);  // host-buffer solves are serialised per process
+
+    for (int g = 0; g < G; ++g) {
+        Shard& s = shards[g];
+        s.dev = (G == 1) ? dev0 : g;
+        s.n = (n + G - 1 - g) / G;  // indices g, g+G, ...
+        if (s.n == 0) continue;
+        CUDA_TRY(cudaSetDevice(s.dev));
+        rc = get_ctx(s.dev, &s.ctx);
+        if (rc != 0) return rc;
+        s.dl = layout_shard(nullptr, *cfg, s.n, shared, *out);
+        rc = ensure_device_buf(*s.ctx, s.dl.bytes);
+        if (rc != 0) return rc;
+        s.dl = layout_shard(s.ctx->d_buf, *cfg, s.n, shared, *out);
+        if (G > 1) {
+            rc = ensure_host_buf(*s.ctx, s.dl.bytes);
+            if (rc != 0) return rc;
+            s.hl = layout_shard(s.ctx->h_buf, *cfg, s.n, shared, *out);
+            // pack the strided shard (i = g + k*G) into pinned memory
+            for (int d = 0; d < D; ++d)
+                for (size_t k = 0; k < s.n; ++k) s.hl.y0[(size_t)d * s.n + k] = y0[(size_t)d * n + g + k * G];
+            if (P > 0) {
+                if (shared) std::memcpy(s.hl.params, params, sizeof(double) * P);
+                else
+                    for (int p = 0; p < P; ++p)
+                        for (size_t k = 0; k < s.n; ++k) s.hl.params[(size_t)p * s.n + k] = params[(size_t)p * n + g + k * G];
+            }
+        }
+    }
+
+    // enqueue H2D -> kernel -> D2H on every device's own stream, then wait for all
+    for (int g = 0; g < G; ++g) {
+        Shard& s = shards[g];
+        if (s.n == 0) continue;
+        CUDA_TRY(cudaSetDevice(s.dev));
+        cudaStream_t st = s.ctx->stream;
+        const double* src_y0 = (G == 1) ? y0 : s.hl.y0;
+        const double* src_p = (G == 1) ? params : s.hl.params;
+        CUDA_TRY(cudaEventRecord(s.ctx->ev[0], st));
+        CUDA_TRY(cudaMemcpyAsync(s.dl.y0, src_y0, sizeof(double) * D * s.n, cudaMemcpyHostToDevice, st));
+        if (P > 0)
+            CUDA_TRY(cudaMemcpyAsync(s.dl.params, src_p, sizeof(double) * (shared ? (size_t)P : (size_t)P * s.n),
+                                     cudaMemcpyHostToDevice, st));
+        {
+            // launch_on_device takes g_ctx_mu for the counter ring; we already hold it -> inline the ring step
+            bacon_launch_args a{};
+            a.cfg = *cfg;
+            a.n = s.n;
+            a.y0 = s.dl.y0;
+            a.params = s.dl.params;
+            a.out = s.dl.out;
+            a.stream = st;
+            a.sm_count = s.ctx->sm_count;
+            a.work_counter = s.ctx->counters + s.ctx->next_counter;
+            s.ctx->next_counter = (s.ctx->next_counter + 1) % kCounterSlots;
+            CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+            CUDA_TRY(cudaEventRecord(s.ctx->ev[1], st));
+            rc = fn(&a);
+            if (rc != 0) return fail(rc, "kernel launch failed on device %d: %s", s.dev, cudaGetErrorString(cudaGetLastError()));
+            CUDA_TRY(cudaEventRecord(s.ctx->ev[2], st));
+            s.filled = a;
+        }
+        const bacon_ivp_result& dst = (G == 1) ? *out : s.hl.out;
+        const bacon_ivp_result& src = s.dl.out;
+#define D2H(field, type, count)                                                                       \
+    if (dst.field && src.field)                                                                       \
+    CUDA_TRY(cudaMemcpyAsync(dst.field, src.field, sizeof(type) * (count), cudaMemcpyDeviceToHost, st))
+        D2H(y_end, double, (size_t)D * s.n);
+        D2H(t_end, double, s.n);
+        D2H(dt_end, double, s.n);
+        D2H(status, int32_t, s.n);
+        D2H(n_accept, uint32_t, s.n);
+        D2H(n_reject, uint32_t, s.n);
+        D2H(n_rhs, uint32_t, s.n);
+        if (cap) {
+            D2H(hist_t, double, s.n * cap);
+            D2H(hist_y, double, s.n * cap * D);
+            D2H(hist_len, uint32_t, s.n);
+        }
+#undef D2H
+        CUDA_TRY(cudaEventRecord(s.ctx->ev[3], st));
+    }
+
+    float k_ms = 0.f, h2d_ms = 0.f, d2h_ms = 0.f;
+    for (int g = 0; g < G; ++g) {
+        Shard& s = shards[g];
+        if (s.n == 0) continue;
+        CUDA_TRY(cudaSetDevice(s.dev));
+        CUDA_TRY(cudaStreamSynchronize(s.ctx->stream));
+        float a = 0, b = 0, c = 0;
+        CUDA_TRY(cudaEventElapsedTime(&a, s.ctx->ev[0], s.ctx->ev[1]));
+        CUDA_TRY(cudaEventElapsedTime(&b, s.ctx->ev[1], s.ctx->ev[2]));
+        CUDA_TRY(cudaEventElapsedTime(&c, s.ctx->ev[2], s.ctx->ev[3]));
+        h2d_ms = a > h2d_ms ? a : h2d_ms;
+        k_ms = b > k_ms ? b : k_ms;  // max over devices
+        d2h_ms = c > d2h_ms ? c : d2h_ms;
+        if (G > 1) {  // scatter the shard back into the caller's arrays
+            const bacon_ivp_result& h = s.hl.out;
+            for (int d = 0; d < D; ++d)
+                for (size_t k = 0; k < s.n; ++k) out->y_end[(size_t)d * n + g + k * G] = h.y_end[(size_t)d * s.n + k];
+#define SCATTER(field)                                                       \
+    if (out->field && h.field)                                               \
+        for (size_t k = 0; k < s.n; ++k) out->field[g + k * G] = h.field[k]
+            SCATTER(t_end);
+            SCATTER(dt_end);
+            SCATTER(status);
+            SCATTER(n_accept);
+            SCATTER(n_reject);
+            SCATTER(n_rhs);
+            if (cap) {
+                SCATTER(hist_len);
+                for (size_t k = 0; k < s.n; ++k) {
+                    std::memcpy(out->hist_t + (g + k * G) * cap, h.hist_t + k * cap, sizeof(double) * cap);
+                    std::memcpy(out->hist_y + (g + k * G) * cap * D, h.hist_y + k * cap * D, sizeof(double) * cap * D);
+                }
+            }
+#undef SCATTER
+        }
+    }
+    CUDA_TRY(cudaSetDevice(dev0));
+    g_last_launch.kernel_ms = k_ms;
+    g_last_launch.h2d_ms = h2d_ms;
+    g_last_launch.d2h_ms = d2h_ms;
+    g_last_launch.grid = shards[0].filled.grid;
+    g_last_launch.block = shards[0].filled.block;
+    g_last_launch.regs_per_thread = shards[0].filled.regs_per_thread;
+    g_last_launch.n_kernels = G * shards[0].filled.n_kernels;
+    return 0;
+}
+
+int bacon_ivp_last_launch(bacon_ivp_launch_info* out) {
+    if (!out) return fail(BACON_E_BAD_ARGUMENT, "NULL argument");
+    if (g_tl.pending && g_tl.last_dev >= 0) {  // device entry point: resolve the event pair lazily
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaSetDevice(g_tl.last_dev));
+        CUDA_TRY(cudaEventSynchronize(g_tl.stop[g_tl.last_dev]));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g_tl.start[g_tl.last_dev], g_tl.stop[g_tl.last_dev]));
+        CUDA_TRY(cudaSetDevice(dev));
+        g_last_launch.kernel_ms = ms;
+        g_tl.pending = false;
+    }
+    *out = g_last_launch;
+    return 0;
+}
+
+int bacon_device_sm_count(void) {
+    int dev = 0, sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return sm;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- FP64 peak probe
+// Register-resident DFMA chains: the denominator of the RK kernels' roofline
+// (MEASURED_PEAKS.json has HBM and bf16 only).  16 independent chains per thread,
+// 8 resident warps per SM sub-partition: the FP64 pipe is the only limiter.
+namespace {
+constexpr int kPeakChains = 16;
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double a, double b) {
+    double x[kPeakChains];
+#pragma unroll
+    for (int k = 0; k < kPeakChains; ++k) x[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < kPeakChains; ++k) x[k] = fma(x[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPeakChains; ++k) s += x[k];
+    if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
+}
+}  // namespace
+
+extern "C" double bacon_fp64_peak_tflops(int iters, void* stream) {
+    if (iters < 1) iters = 4096;
+    int dev = 0, sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1.0;
+    double* sink = nullptr;
+    if (cudaMalloc(&sink, 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = sm * 4, block = 256;
+    fp64_peak_kernel<<<grid, block, 0, st>>>(sink, 64, 0.999999, 1e-9);  // warm-up
+    double best = -1.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, st);
+        fp64_peak_kernel<<<grid, block, 0, st>>>(sink, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * kPeakChains * (double)iters * (double)grid * block;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return best;
+}

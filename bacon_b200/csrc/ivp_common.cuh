@@ -1,0 +1,96 @@
+// ivp_common.cuh — shared device-side plumbing of the ensemble IVP kernels.
+//
+// One trajectory = one `solve(data)` + `IVPIterator::collect_vec` of the
+// reference (src/ivp.rs:209-238).  A kernel owns a grid of persistent lanes; a
+// lane integrates one trajectory at a time with its whole stepper state in
+// registers, and when the trajectory retires (Done / Failure) the warp ballots,
+// stores the results and pulls the next trajectory indices from a global work
+// counter with ONE atomicAdd per warp (warp-aggregated fetch).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bacon_ivp.h"
+
+// Everything a launcher needs.  Plain C layout: it crosses the C ABI inside
+// bacon_rhs_desc::launch (user RHS translation units fill it the same way).
+struct bacon_launch_args {
+    bacon_ivp_config cfg;
+    unsigned long long n;              // trajectories in this launch
+    const double* y0;                  // [dim][n] device
+    const double* params;              // [n_params][n] or [n_params] device (or NULL)
+    bacon_ivp_result out;              // device pointers
+    unsigned long long* work_counter;  // device scratch, zeroed by the engine before the launch
+    void* stream;                      // cudaStream_t
+    int32_t sm_count;                  // SMs of the current device
+    int32_t grid_override;             // >0: force this grid (tests)
+    // filled by the launcher
+    int32_t grid, block, regs_per_thread, n_kernels;
+};
+
+namespace bacon {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// compile-time loop with a constexpr index (tableau zeros vanish at compile time)
+template <int I> struct IC { static constexpr int value = I; constexpr operator int() const { return I; } };
+template <int B, int E, class F> __host__ __device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(IC<B>{});
+        static_for<B + 1, E>(static_cast<F&&>(f));
+    }
+}
+
+__device__ __forceinline__ unsigned lane_id() {
+    unsigned l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Warp-aggregated work fetch: lanes with `want` set receive consecutive
+// trajectory indices; one atomicAdd per warp.  Must be called by all 32 lanes.
+__device__ __forceinline__ unsigned long long warp_fetch(unsigned long long* counter, bool want) {
+    const unsigned m = __ballot_sync(FULL_MASK, want);
+    if (m == 0) return ~0ull;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    return base + (unsigned long long)__popc(m & lanemask_lt());
+}
+
+// Per-trajectory record written at retirement.  Scattered 4/8-byte stores: a few
+// dozen bytes per trajectory against thousands of steps of register-only work.
+template <int D>
+__device__ __forceinline__ void store_result(const bacon_ivp_result& o, unsigned long long n,
+                                             unsigned long long i, const double (&y)[D], double t,
+                                             double dt, int status, uint32_t n_acc, uint32_t n_rej,
+                                             uint32_t n_rhs) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) o.y_end[(size_t)d * n + i] = y[d];
+    if (o.t_end) o.t_end[i] = t;
+    if (o.dt_end) o.dt_end[i] = dt;
+    o.status[i] = status;
+    if (o.n_accept) o.n_accept[i] = n_acc;
+    if (o.n_reject) o.n_reject[i] = n_rej;
+    if (o.n_rhs) o.n_rhs[i] = n_rhs;
+}
+
+template <int D, int P>
+__device__ __forceinline__ void load_problem(const bacon_launch_args& a, unsigned long long i,
+                                             double (&y)[D], double (&p)[(P > 0 ? P : 1)]) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) y[d] = a.y0[(size_t)d * a.n + i];
+    if constexpr (P > 0) {
+        const bool shared = (a.cfg.flags & BACON_FLAG_SHARED_PARAMS) != 0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) p[k] = shared ? a.params[k] : a.params[(size_t)k * a.n + i];
+    }
+}
+
+}  // namespace bacon

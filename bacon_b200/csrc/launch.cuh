@@ -1,0 +1,89 @@
+// launch.cuh — host-side launchers, instantiated in the translation unit that
+// defines the RHS functor (built-ins: rhs_builtin_*.cu; user RHS: their own .cu,
+// see INTEGRATION.md).  A launcher picks the kernel variant (final state only /
+// dense output), sizes a PERSISTENT grid (resident CTAs per SM x SM count: every
+// lane stays on the machine and pulls trajectories from the work counter) and
+// enqueues it on the caller's stream.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "drive.cuh"
+#include "rk_fast.cuh"
+#include "rk_strict.cuh"
+
+namespace bacon {
+
+template <class K> inline int launch_persistent(K kernel, bacon_launch_args* a, size_t smem) {
+    cudaError_t e;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return BACON_E_CUDA;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ENSEMBLE_BLOCK, smem);
+    if (e != cudaSuccess || per_sm < 1) return BACON_E_CUDA;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return BACON_E_CUDA;
+    long long grid = (long long)per_sm * a->sm_count;
+    const long long need = (long long)((a->n + ENSEMBLE_BLOCK - 1) / ENSEMBLE_BLOCK);
+    if (grid > need) grid = need;
+    if (a->grid_override > 0) grid = a->grid_override;
+    if (grid < 1) grid = 1;
+    a->grid = (int)grid;
+    a->block = ENSEMBLE_BLOCK;
+    a->regs_per_thread = fa.numRegs;
+    a->n_kernels = 1;
+    kernel<<<(unsigned)grid, ENSEMBLE_BLOCK, smem, (cudaStream_t)a->stream>>>(*a);
+    return cudaGetLastError() == cudaSuccess ? 0 : BACON_E_CUDA;
+}
+
+template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* a) {
+    constexpr int D = Stepper::D;
+    if (a->cfg.history_capacity > 0 && a->out.hist_t && a->out.hist_y) {
+        const size_t smem = HistStage<D, true>::smem_bytes(ENSEMBLE_BLOCK / 32);
+        return launch_persistent(ensemble_kernel<Stepper, true, MINB>, a, smem);
+    }
+    return launch_persistent(ensemble_kernel<Stepper, false, MINB>, a, 0);
+}
+
+// ---- fast (FMA, compile-time tableau), REF_CORRECTED only
+template <class Rhs, class Tab, int MINB = 4> int launch_rk_fast(bacon_launch_args* a) {
+    if (a->cfg.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;
+    return launch_stepper<RkFastStepper<Rhs, Tab>, MINB>(a);
+}
+
+// ---- strict (oracle operation order, runtime tableau in __constant__), either semantics
+template <class Rhs, class Tab, int MINB = 1> int launch_rk_strict(bacon_launch_args* a) {
+    RkTableauRt T;
+    fill_runtime_tableau<Tab>(T, a->cfg.semantics == BACON_SEM_LITERAL);
+    if (cudaMemcpyToSymbolAsync(c_rk_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, (cudaStream_t)a->stream) != cudaSuccess)
+        return BACON_E_CUDA;
+    return launch_stepper<RkStrictStepper<Rhs, Tab::O>, MINB>(a);
+}
+
+// ---- registration: fills the launcher table of one RHS for THIS translation unit's build
+// flavour (fast, or strict when compiled with -DBACON_STRICT_FP -fmad=false) and hands it
+// to the engine through the C ABI (bacon_rhs_register merges the two flavours by name).
+template <class Rhs> int register_rhs(const char* name) {
+    bacon_rhs_desc d{};
+    d.name = name;
+    d.dim = Rhs::DIM;
+    d.n_params = Rhs::NPARAM;
+#ifdef BACON_STRICT_FP
+    d.launch[1][BACON_RK45] = &launch_rk_strict<Rhs, TabRKF45>;
+    d.launch[1][BACON_RK23] = &launch_rk_strict<Rhs, TabBS23>;
+#else
+    d.launch[0][BACON_RK45] = &launch_rk_fast<Rhs, TabRKF45>;
+    d.launch[0][BACON_RK23] = &launch_rk_fast<Rhs, TabBS23>;
+#endif
+    return bacon_rhs_register(&d);
+}
+
+}  // namespace bacon
+
+#define BACON_CAT2(a, b) a##b
+#define BACON_CAT(a, b) BACON_CAT2(a, b)
+// BACON_REGISTER_RHS(MyRhs, "my_rhs"); at namespace scope of a .cu file
+#define BACON_REGISTER_RHS(RhsType, name) \
+    static const int BACON_CAT(bacon_rhs_id_, __LINE__) = ::bacon::register_rhs<RhsType>(name)

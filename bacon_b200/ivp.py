@@ -1,0 +1,323 @@
+"""Host-side mirror of `bacon_sci::ivp`'s solver front end over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference's `IVPSolver`
+builder trait (src/ivp.rs:134-190) as implemented by `RungeKutta`
+(src/ivp/rk.rs:118-343) and `BDF` (src/ivp/bdf.rs:124-332); the README's older
+names (README.md:24-40: RK45, with_dt_min, with_dt_max, with_start, with_end,
+build, solve_ivp) are kept as aliases.  New: `solve_ivp_ensemble`.
+
+Every setter returns `self` or raises `IVPError` (the reference returns
+`Result<Self, IVPError>`).  Validation itself runs inside the C library
+(bacon_solver_with_*), so any other binding gets identical behaviour.
+
+The right-hand side is a CUDA device functor registered in the library
+("lorenz", "vdp", "robertson", ... or a user RHS); the
+per-trajectory parameter block plays the role of the reference's `UserData`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._lib import lib, last_error
+
+
+class IVPError(Exception):
+    """Mirror of `IVPError` (src/ivp.rs:50-76) plus the engine's own call-level codes."""
+
+    def __init__(self, code, message=""):
+        self.code = int(code)
+        self.variant = _abi.STATUS_NAMES.get(self.code, f"Unknown({code})")
+        super().__init__(f"{self.variant}: {message}" if message else self.variant)
+
+
+def _check(rc):
+    if rc != 0:
+        raise IVPError(rc, last_error())
+
+
+class EnsembleResult:
+    """Per-trajectory records of one ensemble solve (layouts of bacon_ivp_result)."""
+
+    def __init__(self, arrays, launch):
+        self.y_end = arrays["y_end"]          # (dim, n)
+        self.t_end = arrays["t_end"]          # (n,)
+        self.dt_end = arrays["dt_end"]
+        self.status = arrays["status"]        # bacon_status per trajectory
+        self.n_accept = arrays["n_accept"]
+        self.n_reject = arrays["n_reject"]
+        self.n_rhs = arrays["n_rhs"]
+        self.hist_t = arrays.get("hist_t")    # (n, cap)
+        self.hist_y = arrays.get("hist_y")    # (n, cap, dim)
+        self.hist_len = arrays.get("hist_len")
+        self.launch = launch                  # dict: kernel_ms, h2d_ms, d2h_ms, grid, block, regs_per_thread
+
+    def path(self, i):
+        """The `Path` of trajectory i (src/ivp.rs:203): [(t, y)] of accepted points."""
+        m = int(self.hist_len[i])
+        return [(float(self.hist_t[i, k]), np.array(self.hist_y[i, k])) for k in range(m)]
+
+
+class _Solver:
+    METHOD = None
+    _ORDER = None
+
+    def __init__(self, dim):
+        self._h = lib().bacon_solver_new(self.METHOD, int(dim))
+        if not self._h:
+            raise IVPError(_abi.E_BAD_ARGUMENT, last_error())
+        self._dim = int(dim)
+        self._y0 = None
+        self._rhs = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().bacon_solver_free(h)
+            except Exception:
+                pass
+
+    # ---- IVPSolver::new / new_dyn (ivp.rs:159-163).  Python has no static dimensions:
+    # `new(dim)` == `new_dyn(dim)`.
+    @classmethod
+    def new(cls, dim=1):
+        return cls(dim)
+
+    @classmethod
+    def new_dyn(cls, size):
+        return cls(size)
+
+    def dim(self):
+        return self._dim
+
+    # ---- setters (rk.rs:168-247)
+    def with_tolerance(self, tol):
+        _check(lib().bacon_solver_with_tolerance(self._h, float(tol)))
+        return self
+
+    def with_maximum_dt(self, max_dt):
+        _check(lib().bacon_solver_with_maximum_dt(self._h, float(max_dt)))
+        return self
+
+    def with_minimum_dt(self, min_dt):
+        _check(lib().bacon_solver_with_minimum_dt(self._h, float(min_dt)))
+        return self
+
+    def with_initial_time(self, initial):
+        _check(lib().bacon_solver_with_initial_time(self._h, float(initial)))
+        return self
+
+    def with_ending_time(self, ending):
+        _check(lib().bacon_solver_with_ending_time(self._h, float(ending)))
+        return self
+
+    def with_initial_conditions_slice(self, start):
+        start = np.asarray(start, dtype=np.float64)
+        if start.shape != (self._dim,):
+            # nalgebra panics on a length mismatch (ivp.rs:177-180); here it is an error value
+            raise IVPError(_abi.E_BAD_ARGUMENT, f"initial conditions have shape {start.shape}, dim is {self._dim}")
+        self._y0 = start.copy()
+        return self
+
+    def with_initial_conditions(self, start):
+        return self.with_initial_conditions_slice(start)
+
+    def with_derivative(self, rhs_name):
+        rid = lib().bacon_rhs_lookup(str(rhs_name).encode())
+        if rid < 0:
+            raise IVPError(_abi.E_BAD_ARGUMENT, f"no right-hand side named {rhs_name!r} is registered")
+        self._rhs = (rid, str(rhs_name))
+        return self
+
+    # ---- README aliases (README.md:33-39)
+    with_dt_max = with_maximum_dt
+    with_dt_min = with_minimum_dt
+    with_start = with_initial_time
+    with_end = with_ending_time
+
+    def build(self):
+        return self
+
+    # ---- engine knobs (not in the reference)
+    def with_semantics(self, semantics):
+        _check(lib().bacon_solver_with_semantics(self._h, int(semantics)))
+        return self
+
+    def with_flags(self, flags):
+        _check(lib().bacon_solver_with_flags(self._h, int(flags)))
+        return self
+
+    def with_history(self, capacity):
+        _check(lib().bacon_solver_with_history(self._h, int(capacity)))
+        return self
+
+    def with_max_attempts(self, cap):
+        _check(lib().bacon_solver_with_max_attempts(self._h, int(cap)))
+        return self
+
+    # ---- config
+    def _config(self, n_params, extra_flags=0):
+        cfg = _abi.Config()
+        _check(lib().bacon_solver_config(self._h, C.byref(cfg)))
+        cfg.n_params = n_params
+        cfg.flags |= extra_flags
+        return cfg
+
+    def _rhs_info(self):
+        if self._rhs is None:
+            raise IVPError(_abi.E_MISSING_PARAMETERS, "with_derivative was not called")
+        rid = self._rhs[0]
+        d, p = C.c_int(), C.c_int()
+        _check(lib().bacon_rhs_info(rid, None, C.byref(d), C.byref(p)))
+        if d.value != self._dim:
+            raise IVPError(_abi.E_BAD_ARGUMENT, f"rhs {self._rhs[1]!r} has dimension {d.value}, solver has {self._dim}")
+        return rid, d.value, p.value
+
+    # ---- solve(data) + collect_vec (rk.rs:249-343, ivp.rs:209-211): one trajectory
+    def solve(self, data=None, capacity=1 << 16):
+        """Integrate the single trajectory set by with_initial_conditions and return its
+        `Path`: a list of (t, y) accepted points.  A per-trajectory failure raises
+        IVPError after the points yielded before it (the reference yields Err once,
+        ivp.rs:232-235); the partial path is attached as `.path`."""
+        if self._y0 is None:
+            raise IVPError(_abi.E_MISSING_PARAMETERS, "with_initial_conditions was not called")
+        params = None if data is None else np.asarray(data, dtype=np.float64).reshape(-1, 1)
+        self.with_history(capacity)
+        try:
+            res = self.solve_ivp_ensemble(self._y0.reshape(self._dim, 1), params)
+        finally:
+            self.with_history(0)
+        path = res.path(0)
+        st = int(res.status[0])
+        if st != _abi.OK:
+            err = IVPError(st, "trajectory 0")
+            err.path = path
+            err.result = res
+            raise err
+        return path
+
+    def solve_ivp(self, rhs_name, data=None, **kw):  # README.md:40
+        return self.with_derivative(rhs_name).solve(data, **kw)
+
+    # ---- the new entry point: N initial conditions x N parameter sets
+    def solve_ivp_ensemble(self, y0, params=None, *, n_gpus=1, shared_params=False, rhs=None):
+        """y0: (dim, n) float64 host array; params: (n_params, n), or (n_params,) with
+        shared_params=True.  Host buffers in, host buffers out (H2D, kernel, D2H)."""
+        if rhs is not None:
+            self.with_derivative(rhs)
+        rid, dim, npar = self._rhs_info()
+        y0 = np.ascontiguousarray(y0, dtype=np.float64)
+        if y0.ndim != 2 or y0.shape[0] != dim:
+            raise IVPError(_abi.E_BAD_ARGUMENT, f"y0 must have shape ({dim}, n), got {y0.shape}")
+        n = y0.shape[1]
+        flags = 0
+        pptr = None
+        if npar > 0:
+            if params is None:
+                raise IVPError(_abi.E_MISSING_PARAMETERS, f"rhs needs {npar} parameter(s) per trajectory")
+            params = np.ascontiguousarray(params, dtype=np.float64)
+            if shared_params:
+                if params.shape != (npar,):
+                    raise IVPError(_abi.E_BAD_ARGUMENT, f"shared params must have shape ({npar},)")
+                flags |= _abi.FLAG_SHARED_PARAMS
+            elif params.shape != (npar, n):
+                raise IVPError(_abi.E_BAD_ARGUMENT, f"params must have shape ({npar}, {n}), got {params.shape}")
+            pptr = params.ctypes.data
+        cfg = self._config(npar, flags)
+        cap = cfg.history_capacity
+        arrays = {
+            "y_end": np.zeros((dim, n)), "t_end": np.zeros(n), "dt_end": np.zeros(n),
+            "status": np.full(n, -1, dtype=np.int32), "n_accept": np.zeros(n, dtype=np.uint32),
+            "n_reject": np.zeros(n, dtype=np.uint32), "n_rhs": np.zeros(n, dtype=np.uint32),
+        }
+        if cap > 0:
+            arrays["hist_t"] = np.zeros((n, cap))
+            arrays["hist_y"] = np.zeros((n, cap, dim))
+            arrays["hist_len"] = np.zeros(n, dtype=np.uint32)
+        res = _abi.Result(**{k: v.ctypes.data for k, v in arrays.items()})
+        L = lib()
+        if n_gpus == 1:
+            _check(L.bacon_ivp_solve_ensemble(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res)))
+        else:
+            _check(L.bacon_ivp_solve_ensemble_multi(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res), int(n_gpus)))
+        return EnsembleResult(arrays, last_launch())
+
+    # ---- device-resident variant: torch CUDA tensors in, torch CUDA tensors out, no copies
+    def solve_ivp_ensemble_device(self, y0, params=None, *, shared_params=False, out=None, stream=None, rhs=None):
+        import torch
+        if rhs is not None:
+            self.with_derivative(rhs)
+        rid, dim, npar = self._rhs_info()
+        if not (y0.is_cuda and y0.dtype == torch.float64 and y0.is_contiguous() and y0.shape[0] == dim):
+            raise IVPError(_abi.E_BAD_ARGUMENT, f"y0 must be a contiguous CUDA float64 tensor of shape ({dim}, n)")
+        n = y0.shape[1]
+        flags = 0
+        pptr = None
+        if npar > 0:
+            if params is None:
+                raise IVPError(_abi.E_MISSING_PARAMETERS, f"rhs needs {npar} parameter(s) per trajectory")
+            want = (npar,) if shared_params else (npar, n)
+            if not (params.is_cuda and params.dtype == torch.float64 and params.is_contiguous()
+                    and tuple(params.shape) == want):
+                raise IVPError(_abi.E_BAD_ARGUMENT, f"params must be a contiguous CUDA float64 tensor of shape {want}")
+            if shared_params:
+                flags |= _abi.FLAG_SHARED_PARAMS
+            pptr = params.data_ptr()
+        cfg = self._config(npar, flags)
+        cap = cfg.history_capacity
+        dev = y0.device
+        if out is None:
+            out = {
+                "y_end": torch.empty((dim, n), dtype=torch.float64, device=dev),
+                "t_end": torch.empty(n, dtype=torch.float64, device=dev),
+                "dt_end": torch.empty(n, dtype=torch.float64, device=dev),
+                "status": torch.full((n,), -1, dtype=torch.int32, device=dev),
+                "n_accept": torch.zeros(n, dtype=torch.int32, device=dev),
+                "n_reject": torch.zeros(n, dtype=torch.int32, device=dev),
+                "n_rhs": torch.zeros(n, dtype=torch.int32, device=dev),
+            }
+            if cap > 0:
+                out["hist_t"] = torch.zeros((n, cap), dtype=torch.float64, device=dev)
+                out["hist_y"] = torch.zeros((n, cap, dim), dtype=torch.float64, device=dev)
+                out["hist_len"] = torch.zeros(n, dtype=torch.int32, device=dev)
+        res = _abi.Result(**{k: v.data_ptr() for k, v in out.items()})
+        with torch.cuda.device(dev):
+            s = torch.cuda.current_stream(dev) if stream is None else stream
+            _check(lib().bacon_ivp_solve_ensemble_device(C.byref(cfg), rid, n, y0.data_ptr(), pptr, C.byref(res),
+                                                         C.c_void_p(s.cuda_stream)))
+        return out
+
+
+def last_launch():
+    info = _abi.LaunchInfo()
+    _check(lib().bacon_ivp_last_launch(C.byref(info)))
+    return {k: getattr(info, k) for k, _ in _abi.LaunchInfo._fields_}
+
+
+def fp64_peak_tflops(iters=1 << 15):
+    return float(lib().bacon_fp64_peak_tflops(int(iters), None))
+
+
+class RungeKutta45(_Solver):
+    """Runge-Kutta-Fehlberg 4(5) (src/ivp/rk.rs:561)."""
+    METHOD = _abi.RK45
+
+
+class RungeKutta23(_Solver):
+    """Bogacki-Shampine 3(2), "the second adaptive RK" (src/ivp/rk.rs:656)."""
+    METHOD = _abi.RK23
+
+
+class BDF6(_Solver):
+    """Backwards differentiation formula, order 6 with order-5 error estimate (src/ivp/bdf.rs:706)."""
+    METHOD = _abi.BDF6
+
+
+class BDF2(_Solver):
+    """Backwards differentiation formula, order 2 (src/ivp/bdf.rs:762)."""
+    METHOD = _abi.BDF2
+
+
+RK45 = RungeKutta45  # README.md:24
+RK23 = RungeKutta23

@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: accepted f64 trajectory-steps/s of the RK45 Lorenz-63 ensemble
+(BASELINE.json configs[1]: 2^20 trajectories, tol 1e-8, random initial conditions; T=5).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N ...            # CPU arm: the oracle port on the host cores
+
+A "step" is one pass of the hot path over the whole ensemble.  N>1: one rank per GPU (torchrun), rank r
+owns trajectories r, r+N, ... of a global ensemble of N*2^20 (weak scaling, no data-path collective);
+NCCL gathers final states and sums the statistics at the end of each step.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "accepted f64 trajectory-steps/sec (1M Lorenz RK45)"
+UNIT = "trajectory-steps/s"
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2: 64 DFMA/clk/SM at clocks.max.sm
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="trajectories per GPU (default 2^20)")
+    ap.add_argument("--t-end", type=float, default=0.0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from bacon_b200 import ensembles as E
+    w = dict(E.LORENZ)
+    if args.n:
+        w["n"] = args.n
+    if args.t_end:
+        w["t_end"] = args.t_end
+    return w
+
+
+def config_dict(w, n_gpus, extra=None):
+    c = {"workload": f"BASELINE configs[1]: RK45 ensemble, {w['n']} Lorenz-63 trajectories per GPU "
+                     f"(sigma=10, rho=28, beta=8/3), y0~U([-15,15]x[-20,20]x[5,40]) SplitMix64 seed 0x5EED0001, "
+                     f"t in [0,{w['t_end']}], tol {w['tol']}, dt in [{w['dt_min']},{w['dt_max']}], final state only",
+         "trajectories_per_gpu": w["n"], "global_trajectories": w["n"] * n_gpus, "method": "RK45",
+         "rhs": "lorenz", "semantics": "REF_CORRECTED", "parallelism": f"trajectory-sharded x{n_gpus} (i mod N)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_run(w, n_sample, threads=0):
+    """The oracle port (oracle/liboracle.so, OpenMP over trajectories = the reference's rayon arm) on the first
+    n_sample trajectories of the same seeded ensemble.  Returns (accepted steps, seconds, cores)."""
+    from bacon_b200 import _abi, ensembles as E
+    from oracle import oracle as O
+    O.build()
+    y0 = E.lorenz_y0(np.arange(n_sample))
+    p = np.array(w["params"])
+    cores = O.max_threads() if threads <= 0 else threads
+    t0 = time.perf_counter()
+    r = O.solve_ensemble(_abi.RK45, "lorenz", y0, p, shared_params=True, dt_min=w["dt_min"], dt_max=w["dt_max"],
+                         tol=w["tol"], t_start=w["t_start"], t_end=w["t_end"], n_threads=threads)
+    dt = time.perf_counter() - t0
+    assert (r["status"] == 0).all()
+    return int(r["n_accept"].sum()), dt, cores
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = workload(args)
+    cores = os.cpu_count() or 1
+    n_sample = args.cpu_sample or max(1024, min(w["n"], 4096 * cores))
+    for _ in range(min(args.warmup, 1)):
+        cpu_run(w, max(256, n_sample // 16))
+    steps_total, secs = 0, 0.0
+    for _ in range(args.steps):
+        s, dt, cores = cpu_run(w, n_sample)
+        steps_total += s
+        secs += dt
+    v = steps_total / secs
+    sample = f"first {n_sample} trajectories of the seeded ensemble per step, {args.steps} step(s)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(w, args.gpus, {"note": "CPU arm: C++ restatement of src/ivp/rk.rs (oracle port; the Rust "
+                                                     "reference cannot be built in this image), OpenMP over trajectories"}),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+    return 0
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- our arm
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import bacon_b200 as B
+    from bacon_b200 import ensembles as E
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = workload(args)
+    n = w["n"]
+    idx = np.arange(n, dtype=np.uint64) * np.uint64(world) + np.uint64(rank)  # trajectory i -> rank i mod N
+    y0_host = torch.from_numpy(E.lorenz_y0(idx)).pin_memory()
+    p_host = torch.tensor(w["params"], dtype=torch.float64).pin_memory()
+
+    solver = (B.RK45.new(3).with_dt_min(w["dt_min"]).with_dt_max(w["dt_max"]).with_tolerance(w["tol"])
+              .with_start(w["t_start"]).with_end(w["t_end"]).with_derivative("lorenz"))
+
+    # resident inputs/outputs for the device-timed `value`
+    y0 = y0_host.to(dev)
+    p = p_host.to(dev)
+    out = None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    gathered = torch.empty((world, 3, n), dtype=torch.float64, device=dev) if world > 1 else None
+    stats = torch.zeros(3, dtype=torch.float64, device=dev)
+
+    def step():
+        nonlocal out
+        out = solver.solve_ivp_ensemble_device(y0, p, shared_params=True, out=out)
+        # statistics + (N>1) the only collectives of the path: gather final states, sum counters
+        stats[0] = out["n_accept"].sum(dtype=torch.float64)
+        stats[1] = out["n_reject"].sum(dtype=torch.float64)
+        stats[2] = (out["status"] != 0).sum(dtype=torch.float64)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out["y_end"])
+            dist.all_reduce(stats)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    fp64_peak = B.fp64_peak_tflops(1 << 15) if rank == 0 else None  # roofline denominator, measured on this GPU
+    barrier()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)  # L2 flush between timed iterations (outside the event pairs)
+        ev[k][0].record()
+        kev[k][0].record()
+        out = solver.solve_ivp_ensemble_device(y0, p, shared_params=True, out=out)
+        kev[k][1].record()
+        stats[0] = out["n_accept"].sum(dtype=torch.float64)
+        stats[1] = out["n_reject"].sum(dtype=torch.float64)
+        stats[2] = (out["status"] != 0).sum(dtype=torch.float64)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out["y_end"])
+            dist.all_reduce(stats)
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.stop_flag = True
+    sampler.join()
+
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)        # whole steps (kernel + stats + collectives), this rank
+    ker_ms = sum(a.elapsed_time(b) for a, b in kev)       # the ensemble kernel alone
+    tmax = torch.tensor([dev_ms, ker_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)       # max over ranks
+    dev_ms, ker_ms = float(tmax[0]), float(tmax[1])
+    acc_total, rej_total, bad = (float(x) for x in stats.cpu())  # global sums of the LAST step (all steps identical)
+    assert bad == 0, f"{bad} trajectories did not finish with status Ok"
+    value = acc_total * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call: pinned host in, host out, copies inside the timed region
+    y0_np, p_np = y0_host.numpy(), p_host.numpy()
+    for _ in range(2):
+        r = solver.solve_ivp_ensemble(y0_np, p_np, shared_params=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = solver.solve_ivp_ensemble(y0_np, p_np, shared_params=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = float(r.n_accept.sum()) * world * args.steps / float(t_e2e[0])
+    h2d = y0_np.nbytes + p_np.nbytes
+    d2h = sum(getattr(r, k).nbytes for k in ("y_end", "t_end", "dt_end", "status", "n_accept", "n_reject", "n_rhs"))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant (only) kernel: FP64 vector pipe
+    flops_step = E.rk_flops("RK45", 3, E.F_RHS["lorenz"], (acc_total + rej_total) / world, acc_total / world)
+    achieved = flops_step * args.steps / (ker_ms * 1e-3) / 1e12  # TFLOP/s per GPU (kernel time = max over ranks)
+    peak = fp64_peak if fp64_peak and fp64_peak > 0 else FP64_NOMINAL_TFLOPS
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "measured on this GPU in this run: register-resident DFMA loop "
+                "(bacon_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
+                "nominal_peak": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
+                "flops_per_accepted_step": 230, "flops_per_attempt": 205,
+                "kernel": "ensemble_kernel<RkFastStepper<RhsLorenz,TabRKF45>>", "kernel_ms_per_launch": ker_ms / args.steps}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        n_sample = args.cpu_sample or max(1024, min(n, 8192 * cores))
+        s, dt, cores = cpu_run(w, n_sample)
+        cpu_baseline = {"value": s / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"first {n_sample} trajectories of the same seeded ensemble, one pass ({dt:.1f} s)"}
+
+    launch = B.last_launch()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": config_dict(w, world, {"l2": "256 MB buffer written between timed iterations",
+                                         "grid": launch["grid"], "block": launch["block"],
+                                         "regs_per_thread": launch["regs_per_thread"]}),
+        "accepted_steps_per_step": acc_total, "rejected_steps_per_step": rej_total, "wall_s": t_wall,
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * float(t_e2e[0]) / args.steps},
+        "gpu_launches": args.steps * world, "clocks": sampler.summary(),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(reference_arm(a) if a.impl == "reference" else ours(a))

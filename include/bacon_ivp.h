@@ -145,8 +145,8 @@ int bacon_ivp_validate(const bacon_ivp_config*);
  * "linear32", "exp", "decay", "quadratic", "cos", "harmonic".  User RHS are
  * CUDA device functors compiled against bacon_ivp_rhs.cuh and registered
  * through bacon_rhs_register. ------------------------- */
-struct bacon_launch_args; /* defined in bacon_ivp_rhs.cuh; opaque to C callers */
-typedef int (*bacon_launch_fn)(const struct bacon_launch_args*);
+struct bacon_launch_args; /* defined in bacon_b200/csrc/ivp_common.cuh; opaque to C callers */
+typedef int (*bacon_launch_fn)(struct bacon_launch_args*); /* fills grid/block/regs on return */
 
 typedef struct bacon_rhs_desc {
     const char* name;

@@ -1,0 +1,218 @@
+"""GPU parity of the RK path (K1/K2) against the CPU oracle, through the C ABI.
+
+strict kernels  : bit-exact with the oracle (same operation order, no FMA contraction)
+fast kernels    : final state within max(10*tol, 1e-12) relative, step counts side by side
+"""
+import numpy as np
+import pytest
+
+from bacon_b200 import _abi, ensembles as E
+from parity import band, rel_err, run_both
+
+pytestmark = pytest.mark.gpu
+
+LOR = dict(dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0.0)
+LOR_P = np.array(E.LORENZ["params"])
+
+
+def _assert_bit_exact(gpu, ref):
+    for k in ("status", "n_accept", "n_reject", "n_rhs"):
+        np.testing.assert_array_equal(getattr(gpu, k), ref[k], err_msg=k)
+    for k in ("y_end", "t_end", "dt_end"):
+        a, b = getattr(gpu, k), ref[k]
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), f"{k} differs bitwise: max |d|={np.abs(a - b).max()}"
+
+
+def test_readme_example_both_semantics(cuda, engine, oracle):
+    """BASELINE config 1: y'=y, t in [0,10], tol 1e-4, dt in [0.01,0.1] (README.md:32-40)."""
+    y0 = np.array([[1.0]])
+    cfg = dict(dt_min=0.01, dt_max=0.1, tol=1e-4, t_start=0.0, t_end=10.0)
+    gpu, ref = run_both(engine, oracle, "RK45", "exp", y0, **cfg)
+    assert gpu.status[0] == _abi.OK and gpu.n_accept[0] == 128 and gpu.n_reject[0] == 0
+    assert rel_err(gpu.y_end, ref["y_end"])[0] <= band(1e-4)
+    assert abs(gpu.y_end[0, 0] / np.exp(10.0) - 1.0) < 1e-6
+    # strict + corrected: bit-exact
+    gpu, ref = run_both(engine, oracle, "RK45", "exp", y0, strict=True, **cfg)
+    _assert_bit_exact(gpu, ref)
+    # the source exactly as written: 1 accepted point then MinimumTimeDeltaExceeded
+    gpu, ref = run_both(engine, oracle, "RK45", "exp", y0, semantics=_abi.SEM_LITERAL, **cfg)
+    _assert_bit_exact(gpu, ref)
+    assert gpu.status[0] == _abi.E_MIN_DT_EXCEEDED and gpu.n_accept[0] == 1
+    assert gpu.t_end[0] == pytest.approx(0.055) and gpu.y_end[0, 0] == pytest.approx(1.055)
+
+
+@pytest.mark.parametrize("method", ["RK45", "RK23"])
+def test_strict_bit_exact_lorenz(cuda, engine, oracle, method):
+    n = 4096
+    y0 = E.lorenz_y0(np.arange(n))
+    gpu, ref = run_both(engine, oracle, method, "lorenz", y0, LOR_P, shared_params=True, strict=True, t_end=0.5,
+                        **{**LOR, "tol": 1e-8 if method == "RK45" else 1e-6})
+    assert (gpu.status == _abi.OK).all()
+    _assert_bit_exact(gpu, ref)
+
+
+@pytest.mark.parametrize("method,rhs", [("RK45", "vdp"), ("RK23", "vdp"), ("RK45", "robertson"), ("RK45", "harmonic"),
+                                        ("RK23", "linear4"), ("RK45", "decay"), ("RK23", "quadratic")])
+def test_strict_bit_exact_other_rhs(cuda, engine, oracle, method, rhs):
+    n = 1000
+    rng = np.random.default_rng(7)
+    dim = {"vdp": 2, "robertson": 3, "harmonic": 2, "linear4": 4, "decay": 1, "quadratic": 1}[rhs]
+    npar = {"vdp": 1, "robertson": 3, "harmonic": 1, "linear4": 16, "decay": 0, "quadratic": 0}[rhs]
+    y0 = rng.uniform(0.1, 1.0, size=(dim, n))
+    params = rng.uniform(0.5, 2.0, size=(npar, n)) if npar else None
+    if rhs == "linear4":
+        params = rng.normal(size=(npar, n)) * 0.5
+    t_end = 0.01 if rhs == "robertson" else 2.0
+    gpu, ref = run_both(engine, oracle, method, rhs, y0, params, strict=True, dt_min=1e-9, dt_max=0.05, tol=1e-7,
+                        t_start=0.0, t_end=t_end)
+    _assert_bit_exact(gpu, ref)
+
+
+def test_literal_semantics_bit_exact(cuda, engine, oracle):
+    """REF_LITERAL on a y-dependent RHS: transposed stage matrix with stale k's (rk.rs:459/370)."""
+    n = 512
+    rng = np.random.default_rng(3)
+    y0 = rng.uniform(0.5, 1.5, size=(2, n))
+    w = rng.uniform(0.5, 2.0, size=(1, n))
+    for method in ("RK45", "RK23"):
+        gpu, ref = run_both(engine, oracle, method, "harmonic", y0, w, semantics=_abi.SEM_LITERAL, dt_min=1e-6,
+                            dt_max=0.01, tol=1e-3, t_start=0.0, t_end=0.2, max_attempts=20000)
+        _assert_bit_exact(gpu, ref)
+
+
+@pytest.mark.parametrize("method", ["RK45", "RK23"])
+def test_reference_rk_tests_literal_equals_corrected(cuda, engine, oracle, method):
+    """rk.rs:682-758: y'=-2t and y'=cos t ignore y, so LITERAL == CORRECTED == GPU and every
+    yielded point meets the reference's own assertion."""
+    for rhs, cfg, exact, eps, n_acc in [
+        ("quadratic", dict(dt_min=1e-4, dt_max=0.1, tol=1e-5, t_start=0.0, t_end=10.0), lambda t: 1.0 - t * t, 1e-4, 101),
+        ("cos", dict(dt_min=1e-3, dt_max=1e-2, tol=1e-4, t_start=0.0, t_end=10.0), lambda t: np.sin(t), 1e-2, 1001),
+    ]:
+        y0 = np.array([[1.0 if rhs == "quadratic" else 0.0]])
+        outs = []
+        for sem, strict in ((0, False), (0, True), (1, True)):
+            gpu, ref = run_both(engine, oracle, method, rhs, y0, semantics=sem, strict=strict, history=1100, **cfg)
+            assert gpu.status[0] == _abi.OK and gpu.n_accept[0] == n_acc and gpu.n_reject[0] == 0
+            assert ref["n_accept"][0] == n_acc
+            m = int(gpu.hist_len[0])
+            assert m == n_acc
+            t, y = gpu.hist_t[0, :m], gpu.hist_y[0, :m, 0]
+            assert np.abs(y - exact(t)).max() <= eps  # the reference's assertion, every yielded point
+            np.testing.assert_allclose(t, ref["hist_t"][0, :m], rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(y, ref["hist_y"][0, :m, 0], rtol=1e-9, atol=1e-12)
+            outs.append(gpu.y_end[0, 0])
+        assert max(outs) - min(outs) <= 1e-9 * max(1.0, abs(outs[0]))
+
+
+@pytest.mark.parametrize("method,tol,t_end", [("RK45", 1e-8, 5.0), ("RK23", 1e-6, 2.0)])
+def test_fast_lorenz_within_band(cuda, engine, oracle, method, tol, t_end):
+    """The headline kernel against the oracle (libm pow, no FMA) on the seeded config-2 ensemble."""
+    n = 16384
+    y0 = E.lorenz_y0(np.arange(n))
+    gpu, ref = run_both(engine, oracle, method, "lorenz", y0, LOR_P, shared_params=True, t_end=t_end,
+                        **{**LOR, "tol": tol})
+    assert (gpu.status == _abi.OK).all() and (ref["status"] == _abi.OK).all()
+    err = rel_err(gpu.y_end, ref["y_end"])
+    assert err.max() <= band(tol), f"worst relative error {err.max():.3e} > {band(tol):.1e}"
+    np.testing.assert_array_equal(gpu.t_end, ref["t_end"])
+    # step counts side by side: identical up to a handful of borderline accept/reject decisions
+    d_acc = np.abs(gpu.n_accept.astype(np.int64) - ref["n_accept"].astype(np.int64))
+    d_rej = np.abs(gpu.n_reject.astype(np.int64) - ref["n_reject"].astype(np.int64))
+    assert d_acc.max() <= 3 and d_rej.max() <= 3, (d_acc.max(), d_rej.max())
+    assert abs(int(gpu.n_accept.sum()) - int(ref["n_accept"].sum())) <= 1e-4 * ref["n_accept"].sum()
+    np.testing.assert_array_equal(gpu.n_rhs, (gpu.n_accept + gpu.n_reject) * (6 if method == "RK45" else 4))
+
+
+def test_fast_vdp_mu_sweep_within_band(cuda, engine, oracle):
+    """Config 3 shape: per-trajectory mu, strongly divergent step counts -> work-queue refill path."""
+    n = 8192
+    y0, mu = E.vdp_problem(np.arange(n) * (E.VDP["n"] // n), E.VDP["n"])
+    cfg = dict(dt_min=1e-12, dt_max=0.1, tol=1e-10, t_start=0.0, t_end=0.02)
+    gpu, ref = run_both(engine, oracle, "RK23", "vdp", y0, mu, **cfg)
+    assert (gpu.status == _abi.OK).all()
+    assert rel_err(gpu.y_end, ref["y_end"]).max() <= band(1e-10)
+    assert gpu.n_accept.max() > 3 * gpu.n_accept.min()  # the spread that motivates the refill
+    d_acc = np.abs(gpu.n_accept.astype(np.int64) - ref["n_accept"].astype(np.int64))
+    assert d_acc.max() <= 3
+
+
+def test_dense_output_matches_oracle_path(cuda, engine, oracle):
+    """K4: every accepted (t, y) of every trajectory, staged through shared memory."""
+    n = 3000  # not a multiple of the block size; refill + partial flushes
+    y0 = E.lorenz_y0(np.arange(n))
+    for strict in (True, False):
+        for cap in (600, 37):  # 37: odd capacity (scalar store path) and overflow
+            gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, strict=strict,
+                                history=cap, t_end=0.5, **LOR)
+            np.testing.assert_array_equal(gpu.hist_len, ref["hist_len"])
+            np.testing.assert_array_equal(gpu.status, ref["status"])
+            if cap == 37:
+                assert (gpu.status == _abi.E_HISTORY_OVERFLOW).all()
+            mask = np.arange(cap)[None, :] < gpu.hist_len[:, None]
+            if strict:
+                assert np.array_equal(gpu.hist_t[mask], ref["hist_t"][mask])
+                assert np.array_equal(gpu.hist_y[mask], ref["hist_y"][mask])
+                assert (gpu.hist_t[~mask] == 0).all()  # nothing written beyond hist_len
+            else:
+                if not np.array_equal(gpu.n_accept, ref["n_accept"]):
+                    continue  # a borderline accept/reject flip shifts indices; covered by the final-state band
+                np.testing.assert_allclose(gpu.hist_t[mask], ref["hist_t"][mask], rtol=1e-9)
+                np.testing.assert_allclose(gpu.hist_y[mask], ref["hist_y"][mask], rtol=1e-6, atol=1e-9)
+            # the last history point of a completed trajectory is the final state
+            ok = (gpu.status == _abi.OK)
+            last = gpu.hist_len.astype(np.int64) - 1
+            np.testing.assert_array_equal(gpu.hist_y[np.arange(n)[ok], last[ok]], gpu.y_end[:, ok].T)
+
+
+def test_failure_statuses_never_abort_the_batch(cuda, engine, oracle):
+    """Per-trajectory failures land in status[i] (the reference aborts one trajectory, ivp.rs:232-235)."""
+    n = 256
+    y0 = E.lorenz_y0(np.arange(n))
+    # (a) dt_min too large -> MinimumTimeDeltaExceeded for every trajectory, same as the oracle
+    for strict in (True, False):
+        gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, strict=strict,
+                            dt_min=5e-3, dt_max=0.1, tol=1e-8, t_start=0.0, t_end=5.0)
+        np.testing.assert_array_equal(gpu.status, ref["status"])
+        assert (gpu.status == _abi.E_MIN_DT_EXCEEDED).all()
+        np.testing.assert_array_equal(gpu.n_accept, ref["n_accept"])
+    # (b) attempt cap
+    gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, t_end=5.0, max_attempts=100, **LOR)
+    np.testing.assert_array_equal(gpu.status, ref["status"])
+    assert (gpu.status == _abi.E_MAX_ATTEMPTS).all() and (gpu.n_accept + gpu.n_reject == 100).all()
+    # (c) NaN initial condition in ONE trajectory: NonFinite there (the reference would spin forever), rest fine
+    y0b = y0.copy()
+    y0b[1, 17] = np.nan
+    gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0b, LOR_P, shared_params=True, t_end=0.2, **LOR)
+    assert gpu.status[17] == _abi.E_NONFINITE and ref["status"][17] == _abi.E_NONFINITE
+    ok = np.arange(n) != 17
+    assert (gpu.status[ok] == _abi.OK).all()
+    assert rel_err(gpu.y_end[:, ok], ref["y_end"][:, ok]).max() <= band(1e-8)
+
+
+def test_edge_sizes(cuda, engine, oracle):
+    """n = 1, ragged n around warp/block multiples, and n = 0."""
+    for n in (1, 31, 33, 127, 129, 1025):
+        y0 = E.lorenz_y0(np.arange(n))
+        gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, strict=True, t_end=0.1, **LOR)
+        assert np.array_equal(gpu.y_end.view(np.uint64), ref["y_end"].view(np.uint64))
+    from parity import make_solver
+    s = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.1, **LOR)
+    r = s.solve_ivp_ensemble(np.zeros((3, 0)), LOR_P, shared_params=True)
+    assert r.y_end.shape == (3, 0)
+
+
+def test_full_size_properties(cuda, engine):
+    """BASELINE config 2 at full size (2^20 trajectories, T=5): size-independent properties —
+    every trajectory reaches t_end exactly, the run is deterministic (bitwise idempotent), and the
+    ensemble mean of z stays on the Lorenz attractor's range."""
+    from parity import make_solver
+    n = E.LORENZ["n"]
+    y0 = E.lorenz_y0(np.arange(n))
+    s = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=E.LORENZ["t_end"], **LOR)
+    a = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+    b = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+    assert (a.status == _abi.OK).all() and (a.t_end == E.LORENZ["t_end"]).all()
+    assert np.array_equal(a.y_end.view(np.uint64), b.y_end.view(np.uint64))
+    np.testing.assert_array_equal(a.n_accept, b.n_accept)
+    assert 2500 < a.n_accept.mean() < 4500 and a.n_reject.sum() < 0.01 * a.n_accept.sum()
+    assert np.isfinite(a.y_end).all() and 15.0 < a.y_end[2].mean() < 32.0
