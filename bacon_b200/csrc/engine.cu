@@ -494,6 +494,9 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
                 for (size_t k = 0; k < s.n; ++k) s.hl.y0[(size_t)d * s.n + k] = y0[(size_t)d * n + g + k * G];
             if (P > 0) {
                 if (shared) std::memcpy(s.hl.params, params, sizeof(double) * P);
+                else if (cfg->flags & BACON_FLAG_PARAMS_AOS)
+                    for (size_t k = 0; k < s.n; ++k)
+                        std::memcpy(s.hl.params + k * P, params + (g + k * G) * (size_t)P, sizeof(double) * P);
                 else
                     for (int p = 0; p < P; ++p)
                         for (size_t k = 0; k < s.n; ++k) s.hl.params[(size_t)p * s.n + k] = params[(size_t)p * n + g + k * G];

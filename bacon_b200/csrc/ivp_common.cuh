@@ -88,8 +88,10 @@ __device__ __forceinline__ void load_problem(const bacon_launch_args& a, unsigne
     for (int d = 0; d < D; ++d) y[d] = a.y0[(size_t)d * a.n + i];
     if constexpr (P > 0) {
         const bool shared = (a.cfg.flags & BACON_FLAG_SHARED_PARAMS) != 0;
+        const bool aos = (a.cfg.flags & BACON_FLAG_PARAMS_AOS) != 0;
 #pragma unroll
-        for (int k = 0; k < P; ++k) p[k] = shared ? a.params[k] : a.params[(size_t)k * a.n + i];
+        for (int k = 0; k < P; ++k)
+            p[k] = shared ? a.params[k] : (aos ? a.params[(size_t)i * P + k] : a.params[(size_t)k * a.n + i]);
     }
 }
 

@@ -4,6 +4,7 @@
 // User RHS go through exactly the same two lines: see INTEGRATION.md.
 #include "launch.cuh"
 #include "rhs_builtin.cuh"
+#include "rk_warp_linear.cuh"
 
 using namespace bacon;
 
@@ -16,3 +17,22 @@ BACON_REGISTER_RHS(RhsQuadratic, "quadratic");
 BACON_REGISTER_RHS(RhsCos, "cos");
 BACON_REGISTER_RHS(RhsHarmonic, "harmonic");
 BACON_REGISTER_RHS(RhsLinear<4>, "linear4");
+
+// linear32 (BASELINE config 4): warp-per-trajectory kernels (rk_warp_linear.cuh)
+namespace {
+int register_linear32() {
+    bacon_rhs_desc d{};
+    d.name = "linear32";
+    d.dim = 32;
+    d.n_params = 32 * 32;
+#ifdef BACON_STRICT_FP
+    d.launch[1][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, true>;
+    d.launch[1][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, true>;
+#else
+    d.launch[0][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, false>;
+    d.launch[0][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, false>;
+#endif
+    return bacon_rhs_register(&d);
+}
+const int bacon_rhs_id_linear32 = register_linear32();
+}  // namespace

@@ -201,9 +201,10 @@ class _Solver:
         return self.with_derivative(rhs_name).solve(data, **kw)
 
     # ---- the new entry point: N initial conditions x N parameter sets
-    def solve_ivp_ensemble(self, y0, params=None, *, n_gpus=1, shared_params=False, rhs=None):
-        """y0: (dim, n) float64 host array; params: (n_params, n), or (n_params,) with
-        shared_params=True.  Host buffers in, host buffers out (H2D, kernel, D2H)."""
+    def solve_ivp_ensemble(self, y0, params=None, *, n_gpus=1, shared_params=False, params_aos=False, rhs=None):
+        """y0: (dim, n) float64 host array; params: (n_params, n), or (n, ...) = one contiguous block
+        per trajectory with params_aos=True, or (n_params,) with shared_params=True.
+        Host buffers in, host buffers out (H2D, kernel, D2H)."""
         if rhs is not None:
             self.with_derivative(rhs)
         rid, dim, npar = self._rhs_info()
@@ -221,6 +222,10 @@ class _Solver:
                 if params.shape != (npar,):
                     raise IVPError(_abi.E_BAD_ARGUMENT, f"shared params must have shape ({npar},)")
                 flags |= _abi.FLAG_SHARED_PARAMS
+            elif params_aos:
+                if params.size != npar * n or params.shape[0] != n:
+                    raise IVPError(_abi.E_BAD_ARGUMENT, f"AoS params must have shape ({n}, {npar}), got {params.shape}")
+                flags |= _abi.FLAG_PARAMS_AOS
             elif params.shape != (npar, n):
                 raise IVPError(_abi.E_BAD_ARGUMENT, f"params must have shape ({npar}, {n}), got {params.shape}")
             pptr = params.ctypes.data
@@ -244,7 +249,8 @@ class _Solver:
         return EnsembleResult(arrays, last_launch())
 
     # ---- device-resident variant: torch CUDA tensors in, torch CUDA tensors out, no copies
-    def solve_ivp_ensemble_device(self, y0, params=None, *, shared_params=False, out=None, stream=None, rhs=None):
+    def solve_ivp_ensemble_device(self, y0, params=None, *, shared_params=False, params_aos=False, out=None,
+                                  stream=None, rhs=None):
         import torch
         if rhs is not None:
             self.with_derivative(rhs)
@@ -257,12 +263,14 @@ class _Solver:
         if npar > 0:
             if params is None:
                 raise IVPError(_abi.E_MISSING_PARAMETERS, f"rhs needs {npar} parameter(s) per trajectory")
-            want = (npar,) if shared_params else (npar, n)
+            want = (npar,) if shared_params else ((n, npar) if params_aos else (npar, n))
             if not (params.is_cuda and params.dtype == torch.float64 and params.is_contiguous()
-                    and tuple(params.shape) == want):
+                    and params.numel() == want[0] * (want[1] if len(want) > 1 else 1) and params.shape[0] == want[0]):
                 raise IVPError(_abi.E_BAD_ARGUMENT, f"params must be a contiguous CUDA float64 tensor of shape {want}")
             if shared_params:
                 flags |= _abi.FLAG_SHARED_PARAMS
+            elif params_aos:
+                flags |= _abi.FLAG_PARAMS_AOS
             pptr = params.data_ptr()
         cfg = self._config(npar, flags)
         cap = cfg.history_capacity

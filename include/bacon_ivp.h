@@ -69,6 +69,7 @@ typedef enum bacon_status {
 #define BACON_FLAG_STRICT_FP 1u      /* no FMA contraction: bit-comparable with the CPU oracle */
 #define BACON_FLAG_SHARED_PARAMS 2u  /* params is [n_params], shared by all trajectories        */
 #define BACON_FLAG_BDF_NEWTON 4u     /* BDF: Newton + analytic-Jacobian LU instead of Broyden   */
+#define BACON_FLAG_PARAMS_AOS 8u     /* params is [n][n_params] (one contiguous block per trajectory) */
 
 /* One POD block = everything the reference builder collects before `solve`
  * (rk.rs:60-68 / bdf.rs:57-65), shared by the whole ensemble. */
@@ -163,8 +164,9 @@ int bacon_rhs_info(int rhs_id, const char** name, int* dim, int* n_params);
 
 /* ---- the solve: replaces `solve(data)` + `IVPIterator::collect_vec`
  * (rk.rs:249-343, ivp.rs:209-238) for n trajectories at once. --------------
- * y0 [dim][n] SoA; params [n_params][n] SoA (or [n_params] with
- * BACON_FLAG_SHARED_PARAMS, or NULL when n_params == 0). */
+ * y0 [dim][n] SoA; params [n_params][n] SoA (or [n][n_params] with
+ * BACON_FLAG_PARAMS_AOS, or [n_params] with BACON_FLAG_SHARED_PARAMS, or NULL
+ * when n_params == 0). */
 
 /* Host buffers: H2D, kernel, D2H on the current CUDA device. */
 int bacon_ivp_solve_ensemble(const bacon_ivp_config*, int rhs_id, size_t n, const double* y0,

@@ -73,7 +73,7 @@ def rhs_info(name):
 
 
 def solve_ensemble(method, rhs, y0, params=None, *, dt_min, dt_max, tol, t_start, t_end,
-                   semantics=_abi.SEM_CORRECTED, shared_params=False, history_capacity=0,
+                   semantics=_abi.SEM_CORRECTED, shared_params=False, params_aos=False, history_capacity=0,
                    max_attempts=0, pow_mode=0, n_threads=0):
     """Run the oracle on an ensemble.  y0: (dim, n) float64; params: (n_params, n) or (n_params,).
 
@@ -91,6 +91,9 @@ def solve_ensemble(method, rhs, y0, params=None, *, dt_min, dt_max, tol, t_start
         if shared_params:
             assert params.shape == (npar,)
             flags |= _abi.FLAG_SHARED_PARAMS
+        elif params_aos:
+            params = params.reshape(n, npar)
+            flags |= _abi.FLAG_PARAMS_AOS
         else:
             assert params.shape == (npar, n), (params.shape, npar, n)
         pptr = params.ctypes.data

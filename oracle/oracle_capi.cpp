@@ -131,7 +131,9 @@ template <class Rhs> static void run_one(const RunArgs& a, size_t i) {
     for (int d = 0; d < D; ++d) y0[d] = a.y0[(size_t)d * a.n + i];
     std::vector<double> p(P > 0 ? P : 1);
     const bool shared = (c.flags & BACON_FLAG_SHARED_PARAMS) != 0;
-    for (int k = 0; k < P; ++k) p[k] = shared ? a.params[k] : a.params[(size_t)k * a.n + i];
+    const bool aos = (c.flags & BACON_FLAG_PARAMS_AOS) != 0;
+    for (int k = 0; k < P; ++k)
+        p[k] = shared ? a.params[k] : (aos ? a.params[i * (size_t)P + k] : a.params[(size_t)k * a.n + i]);
     const bo::Mode mode = c.semantics == BACON_SEM_LITERAL ? bo::Mode::Literal : bo::Mode::Corrected;
     const bool keep = c.history_capacity > 0;
     bo::Solution<D> s;

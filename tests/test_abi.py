@@ -1,0 +1,151 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU, exports every
+symbol include/bacon_ivp.h declares, and the builder reproduces the reference's validation rules
+(src/ivp/rk.rs:168-256, identical in bdf.rs:176-264).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from bacon_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "bacon_ivp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_][\w\s\*]*?\b(bacon_\w+)\s*\(", src, flags=re.M)
+    return sorted(set(n for n in names if n != "bacon_launch_fn"))
+
+
+def test_header_and_python_mirror_agree():
+    assert declared_functions() == sorted(_abi.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(engine):
+    from bacon_b200._lib import lib
+    L = lib()
+    for name in declared_functions():
+        assert hasattr(L, name), f"libbacon_ivp.so does not export {name}"
+    assert L.bacon_abi_version() == _abi.ABI_VERSION
+    for code, name in _abi.STATUS_NAMES.items():
+        if code <= _abi.E_UNSUPPORTED:
+            assert L.bacon_status_name(code).decode() == name
+
+
+def test_struct_layouts_match_header():
+    # bacon_ivp_config: 6 x 4-byte fields, 5 doubles, one u64; bacon_ivp_result: 10 pointers
+    assert C.sizeof(_abi.Config) == 6 * 4 + 5 * 8 + 8
+    assert _abi.Config.dt_min.offset == 24 and _abi.Config.max_attempts.offset == 64
+    assert C.sizeof(_abi.Result) == 10 * C.sizeof(C.c_void_p)
+    assert C.sizeof(_abi.LaunchInfo) == 3 * 4 + 4 * 4
+
+
+def test_builtin_rhs_registry(engine):
+    from bacon_b200._lib import lib
+    L = lib()
+    want = {"lorenz": (3, 3), "vdp": (2, 1), "robertson": (3, 3), "exp": (1, 0), "decay": (1, 0),
+            "quadratic": (1, 0), "cos": (1, 0), "harmonic": (2, 1), "linear4": (4, 16), "linear32": (32, 1024)}
+    for name, (dim, npar) in want.items():
+        rid = L.bacon_rhs_lookup(name.encode())
+        assert rid >= 0, name
+        d, p = C.c_int(), C.c_int()
+        assert L.bacon_rhs_info(rid, None, C.byref(d), C.byref(p)) == 0
+        assert (d.value, p.value) == (dim, npar)
+    assert L.bacon_rhs_lookup(b"no_such_rhs") == -1
+
+
+@pytest.mark.parametrize("cls_name", ["RungeKutta45", "RungeKutta23", "BDF6", "BDF2"])
+def test_builder_validation_rules(engine, cls_name):
+    cls = getattr(engine, cls_name)
+    E = engine.IVPError
+    # with_tolerance: tol <= 0 -> ToleranceOOB (rk.rs:168-174)
+    for bad in (0.0, -1e-3):
+        with pytest.raises(E) as e:
+            cls.new(1).with_tolerance(bad)
+        assert e.value.variant == "ToleranceOOB"
+    # with_maximum_dt / with_minimum_dt: <= 0 -> TimeDeltaOOB (rk.rs:179-210)
+    for setter in ("with_maximum_dt", "with_minimum_dt", "with_dt_max", "with_dt_min"):
+        with pytest.raises(E) as e:
+            getattr(cls.new(1), setter)(0.0)
+        assert e.value.variant == "TimeDeltaOOB"
+    # ordering: a later max below min pulls min down; a later min above max pushes max up
+    s = cls.new(1).with_minimum_dt(0.5).with_maximum_dt(0.1).with_tolerance(1e-3).with_initial_time(0).with_ending_time(1)
+    cfg = s._config(0)
+    assert (cfg.dt_min, cfg.dt_max) == (0.1, 0.1)
+    s = cls.new(1).with_maximum_dt(0.1).with_minimum_dt(0.5).with_tolerance(1e-3).with_initial_time(0).with_ending_time(1)
+    cfg = s._config(0)
+    assert (cfg.dt_min, cfg.dt_max) == (0.5, 0.5)
+    # with_initial_time after end: end <= initial -> TimeStartOOB; with_ending_time: initial >= ending -> TimeEndOOB
+    with pytest.raises(E) as e:
+        cls.new(1).with_ending_time(1.0).with_initial_time(1.0)
+    assert e.value.variant == "TimeStartOOB"
+    with pytest.raises(E) as e:
+        cls.new(1).with_initial_time(2.0).with_ending_time(1.0)
+    assert e.value.variant == "TimeEndOOB"
+    with pytest.raises(E) as e:
+        cls.new(1).with_start(2.0).with_end(2.0)
+    assert e.value.variant == "TimeEndOOB"
+    # solve with anything unset -> MissingParameters (rk.rs:249-256)
+    full = dict(with_maximum_dt=0.1, with_minimum_dt=0.01, with_tolerance=1e-4, with_initial_time=0.0, with_ending_time=1.0)
+    for missing in full:
+        s = cls.new(1)
+        for k, v in full.items():
+            if k != missing:
+                getattr(s, k)(v)
+        with pytest.raises(E) as e:
+            s._config(0)
+        assert e.value.variant == "MissingParameters"
+    s = cls.new(1)
+    for k, v in full.items():
+        getattr(s, k)(v)
+    with pytest.raises(E) as e:  # no initial conditions
+        s.with_derivative("exp").solve()
+    assert e.value.variant == "MissingParameters"
+    with pytest.raises(E) as e:  # no derivative
+        cls.new(1).with_initial_conditions([1.0]).solve_ivp_ensemble([[1.0]])
+    assert e.value.variant == "MissingParameters"
+
+
+def test_validate_config_codes(engine):
+    from bacon_b200._lib import lib
+    L = lib()
+    ok = dict(method=_abi.RK45, dim=3, n_params=3, semantics=0, flags=0, history_capacity=0, dt_min=1e-9, dt_max=0.1,
+              tol=1e-8, t_start=0.0, t_end=5.0, max_attempts=0)
+    assert L.bacon_ivp_validate(C.byref(_abi.Config(**ok))) == 0
+    for patch, code in [(dict(tol=0.0), _abi.E_TOLERANCE_OOB), (dict(dt_min=-1.0), _abi.E_TIME_DELTA_OOB),
+                        (dict(dt_min=1.0, dt_max=0.5), _abi.E_TIME_DELTA_OOB), (dict(t_end=0.0), _abi.E_TIME_END_OOB),
+                        (dict(method=9), _abi.E_BAD_ARGUMENT), (dict(dim=0), _abi.E_BAD_ARGUMENT),
+                        (dict(semantics=5), _abi.E_BAD_ARGUMENT)]:
+        assert L.bacon_ivp_validate(C.byref(_abi.Config(**{**ok, **patch}))) == code
+        assert L.bacon_last_error()
+
+
+def test_solve_rejects_mismatched_arguments_before_touching_the_gpu(engine):
+    """Argument errors are reported by code without any CUDA call (works on a CPU-only box)."""
+    import numpy as np
+    s = (engine.RK45.new(3).with_dt_min(1e-9).with_dt_max(0.1).with_tolerance(1e-8).with_start(0).with_end(1)
+         .with_derivative("lorenz"))
+    with pytest.raises(engine.IVPError) as e:
+        s.solve_ivp_ensemble(np.zeros((2, 4)), np.zeros((3, 4)))
+    assert e.value.variant == "BadArgument"
+    with pytest.raises(engine.IVPError) as e:
+        s.solve_ivp_ensemble(np.zeros((3, 4)))  # lorenz needs params
+    assert e.value.variant == "MissingParameters"
+    with pytest.raises(engine.IVPError) as e:
+        engine.RK45.new(2).with_derivative("lorenz")._rhs_info()
+    assert e.value.variant == "BadArgument"
+    with pytest.raises(engine.IVPError):
+        engine.RK45.new(3).with_derivative("nope")
+
+
+def test_no_cpu_fallback_in_product_package():
+    """The product package never imports the oracle (it is test infrastructure)."""
+    pkg = os.path.join(ROOT, "bacon_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+                assert not re.search(r'#\s*include\s*[<"][^>"]*oracle', text), f
