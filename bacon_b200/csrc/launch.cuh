@@ -7,6 +7,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
+#include "bdf.cuh"
 #include "drive.cuh"
 #include "rk_fast.cuh"
 #include "rk_strict.cuh"
@@ -25,6 +28,10 @@ template <class K> inline int launch_persistent(K kernel, bacon_launch_args* a, 
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, kernel);
     if (e != cudaSuccess) return BACON_E_CUDA;
+    if (const char* env = getenv("BACON_IVP_BLOCKS_PER_SM")) {  // tuning knob: fewer resident CTAs than the occupancy limit
+        const int want = atoi(env);
+        if (want >= 1 && want < per_sm) per_sm = want;
+    }
     long long grid = (long long)per_sm * a->sm_count;
     const long long need = (long long)((a->n + ENSEMBLE_BLOCK - 1) / ENSEMBLE_BLOCK);
     if (grid > need) grid = need;
@@ -62,6 +69,16 @@ template <class Rhs, class Tab, int MINB = 1> int launch_rk_strict(bacon_launch_
     return launch_stepper<RkStrictStepper<Rhs, Tab::O>, MINB>(a);
 }
 
+// ---- BDF (Broyden as in the reference, or Newton + in-register LU with BACON_FLAG_BDF_NEWTON)
+template <class Rhs, class Coef, bool STRICT, int MINB = 2> int launch_bdf(bacon_launch_args* a) {
+    if (a->cfg.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;  // REF_LITERAL BDF: CPU oracle only
+    if (a->cfg.flags & BACON_FLAG_BDF_NEWTON) {
+        if (STRICT) return BACON_E_UNSUPPORTED;  // the strict build is the reference's own (Broyden) iteration
+        return launch_stepper<BdfStepper<Rhs, Coef, false, true>, MINB>(a);
+    }
+    return launch_stepper<BdfStepper<Rhs, Coef, STRICT, false>, MINB>(a);
+}
+
 // ---- registration: fills the launcher table of one RHS for THIS translation unit's build
 // flavour (fast, or strict when compiled with -DBACON_STRICT_FP -fmad=false) and hands it
 // to the engine through the C ABI (bacon_rhs_register merges the two flavours by name).
@@ -71,11 +88,17 @@ template <class Rhs> int register_rhs(const char* name) {
     d.dim = Rhs::DIM;
     d.n_params = Rhs::NPARAM;
 #ifdef BACON_STRICT_FP
-    d.launch[1][BACON_RK45] = &launch_rk_strict<Rhs, TabRKF45>;
-    d.launch[1][BACON_RK23] = &launch_rk_strict<Rhs, TabBS23>;
+    constexpr int S = 1;
 #else
-    d.launch[0][BACON_RK45] = &launch_rk_fast<Rhs, TabRKF45>;
-    d.launch[0][BACON_RK23] = &launch_rk_fast<Rhs, TabBS23>;
+    constexpr int S = 0;
+#endif
+#ifndef BACON_SKIP_RK
+    d.launch[S][BACON_RK45] = S ? &launch_rk_strict<Rhs, TabRKF45> : &launch_rk_fast<Rhs, TabRKF45>;
+    d.launch[S][BACON_RK23] = S ? &launch_rk_strict<Rhs, TabBS23> : &launch_rk_fast<Rhs, TabBS23>;
+#endif
+#ifndef BACON_SKIP_BDF
+    d.launch[S][BACON_BDF6] = &launch_bdf<Rhs, CoefBDF6, S != 0>;
+    d.launch[S][BACON_BDF2] = &launch_bdf<Rhs, CoefBDF2, S != 0>;
 #endif
     return bacon_rhs_register(&d);
 }

@@ -2,6 +2,8 @@
 // sides.  Compiled twice: as is (fast: FMA contraction, compile-time tableaux) and with
 // -DBACON_STRICT_FP -fmad=false (strict: the oracle's operation order, no contraction).
 // User RHS go through exactly the same two lines: see INTEGRATION.md.
+// The build splits RK and BDF instantiations into separate objects (-DBACON_SKIP_BDF / -DBACON_SKIP_RK)
+// only to compile them in parallel; the registry merges launcher tables by RHS name.
 #include "launch.cuh"
 #include "rhs_builtin.cuh"
 #include "rk_warp_linear.cuh"
@@ -18,6 +20,7 @@ BACON_REGISTER_RHS(RhsCos, "cos");
 BACON_REGISTER_RHS(RhsHarmonic, "harmonic");
 BACON_REGISTER_RHS(RhsLinear<4>, "linear4");
 
+#ifndef BACON_SKIP_RK
 // linear32 (BASELINE config 4): warp-per-trajectory kernels (rk_warp_linear.cuh)
 namespace {
 int register_linear32() {
@@ -36,3 +39,4 @@ int register_linear32() {
 }
 const int bacon_rhs_id_linear32 = register_linear32();
 }  // namespace
+#endif

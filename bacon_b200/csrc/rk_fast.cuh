@@ -110,14 +110,14 @@ template <class Rhs, class Tab> struct RkFastStepper {
             double Y[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                double s = Tab::a(i, j0) * f[j0][d];
+                double s = Tab::av(i, j0) * f[j0][d];
                 static_for<j0 + 1, i>([&](auto J) {
                     constexpr int j = decltype(J)::value;
-                    if constexpr (Tab::a(i, j) != 0.0) s = fma(Tab::a(i, j), f[j][d], s);
+                    if constexpr (Tab::a(i, j) != 0.0) s = fma(Tab::av(i, j), f[j][d], s);
                 });
                 Y[d] = fma(h, s, y[d]);
             }
-            rhs(fma(Tab::c(i), h, t), Y, p, f[i]);
+            rhs(fma(Tab::cv(i), h, t), Y, p, f[i]);
         });
 
         // embedded error, squared: q = || sum_j e_j f_j ||^2   ( = (||sum_j e_j k_j|| / dt)^2 )
@@ -125,10 +125,10 @@ template <class Rhs, class Tab> struct RkFastStepper {
         constexpr int e0 = first_nz_e<Tab>();
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            double s = Tab::e(e0) * f[e0][d];
+            double s = Tab::ev(e0) * f[e0][d];
             static_for<e0 + 1, O>([&](auto J) {
                 constexpr int j = decltype(J)::value;
-                if constexpr (Tab::e(j) != 0.0) s = fma(Tab::e(j), f[j][d], s);
+                if constexpr (Tab::e(j) != 0.0) s = fma(Tab::ev(j), f[j][d], s);
             });
             q = (d == 0) ? s * s : fma(s, s, q);
         }
@@ -142,10 +142,10 @@ template <class Rhs, class Tab> struct RkFastStepper {
             constexpr int b0 = first_nz_b<Tab>();
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                double s = Tab::b(b0) * f[b0][d];
+                double s = Tab::bv(b0) * f[b0][d];
                 static_for<b0 + 1, O>([&](auto J) {
                     constexpr int j = decltype(J)::value;
-                    if constexpr (Tab::b(j) != 0.0) s = fma(Tab::b(j), f[j][d], s);
+                    if constexpr (Tab::b(j) != 0.0) s = fma(Tab::bv(j), f[j][d], s);
                 });
                 y[d] = fma(h, s, y[d]);
             }

@@ -10,6 +10,27 @@
 
 namespace bacon {
 
+// Device-side copies in __constant__ memory.  The fast kernels know the STRUCTURE (which entries are
+// zero) at compile time from the constexpr accessors below, and read the VALUES as constant-bank
+// operands of DFMA/DMUL (c[0x3][..]) through cv/av/bv/ev: no immediates to materialise per use.
+#ifdef __CUDACC__
+static __constant__ double kRKF45_c[6] = {0.0, 1.0 / 4.0, 3.0 / 8.0, 12.0 / 13.0, 1.0, 1.0 / 2.0};
+static __constant__ double kRKF45_a[6][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0 / 4.0, 0, 0, 0, 0, 0},
+    {3.0 / 32.0, 9.0 / 32.0, 0, 0, 0, 0},
+    {1932.0 / 2197.0, -7200.0 / 2197.0, 7296.0 / 2197.0, 0, 0, 0},
+    {439.0 / 216.0, -8.0, 3680.0 / 513.0, -845.0 / 4104.0, 0, 0},
+    {-8.0 / 27.0, 2.0, -3544.0 / 2565.0, 1859.0 / 4104.0, -11.0 / 40.0, 0}};
+static __constant__ double kRKF45_b[6] = {25.0 / 216.0, 0.0, 1408.0 / 2565.0, 2197.0 / 4104.0, -(1.0 / 5.0), 0.0};
+static __constant__ double kRKF45_e[6] = {1.0 / 360.0, 0.0, -128.0 / 4275.0, -2197.0 / 75240.0, 1.0 / 50.0, 2.0 / 55.0};
+static __constant__ double kBS23_c[4] = {0.0, 1.0 / 2.0, 3.0 / 4.0, 1.0};
+static __constant__ double kBS23_a[4][4] = {{0, 0, 0, 0}, {1.0 / 2.0, 0, 0, 0}, {0, 3.0 / 4.0, 0, 0},
+                                            {2.0 / 9.0, 1.0 / 3.0, 4.0 / 9.0, 0}};
+static __constant__ double kBS23_b[4] = {2.0 / 9.0, 1.0 / 3.0, 4.0 / 9.0, 0.0};
+static __constant__ double kBS23_e[4] = {-5.0 / 72.0, 1.0 / 12.0, 1.0 / 9.0, -(1.0 / 8.0)};
+#endif
+
 // Runge-Kutta-Fehlberg 4(5): src/ivp/rk.rs:430-526
 //   c  = t_coefficients   rk.rs:443-450
 //   a  = k_coefficients   rk.rs:459-502 (rows as the source comments label them)
@@ -40,6 +61,12 @@ struct TabRKF45 {
         return v[i];
     }
     static constexpr double safety = 84.0 / 100.0;  // rk.rs:266-268 (intent)
+#ifdef __CUDACC__
+    __device__ __forceinline__ static double cv(int i) { return kRKF45_c[i]; }
+    __device__ __forceinline__ static double av(int i, int j) { return kRKF45_a[i][j]; }
+    __device__ __forceinline__ static double bv(int i) { return kRKF45_b[i]; }
+    __device__ __forceinline__ static double ev(int i) { return kRKF45_e[i]; }
+#endif
 };
 
 // Bogacki-Shampine 3(2): src/ivp/rk.rs:563-621 ("the second adaptive RK").
@@ -65,6 +92,12 @@ struct TabBS23 {
         return v[i];
     }
     static constexpr double safety = 84.0 / 100.0;
+#ifdef __CUDACC__
+    __device__ __forceinline__ static double cv(int i) { return kBS23_c[i]; }
+    __device__ __forceinline__ static double av(int i, int j) { return kBS23_a[i][j]; }
+    __device__ __forceinline__ static double bv(int i) { return kBS23_b[i]; }
+    __device__ __forceinline__ static double ev(int i) { return kBS23_e[i]; }
+#endif
 };
 
 // Runtime tableau for the strict (oracle-order) kernels.  `a` is what the

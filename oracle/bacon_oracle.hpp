@@ -476,6 +476,8 @@ template <int D, int O, class Rhs> struct BDFSolver {
     Rhs rhs;
     const double* params;
     Mode mode;
+    bool newton = false;  // NOT in the reference: Newton + LU on the analytic Jacobian (north-star item 4),
+                          // kept here so the device Newton path has a like-for-like CPU counterpart
     Counters cnt;
     int fail_code = 0;
     // value of the last Ok(...) (what the iterator yields)
@@ -542,7 +544,54 @@ template <int D, int O, class Rhs> struct BDFSolver {
         return true;
     }
 
+    // Newton on g(x) = 0 with g'(x) = I - dt*beta*J_f(t_{n+1}, x), dense LU with partial pivoting,
+    // stop when ||delta||_2 <= tol (same rule as bdf.rs:468), at most 998 iterations.
+    int newton_solve(bool higher, Vec<D>& result) {
+        const double tg = time + dt;
+        const double beta = higher ? coef.higher[0] : coef.lower[0];
+        Vec<D> x = state;
+        for (int n = 2; n < 1000; ++n) {
+            cnt.n_iter++;
+            double g[D];
+            if (!g_eval(higher, tg, x.data(), g)) return ST_USER;
+            double J[D][D];
+            rhs.jac(tg, x.data(), params, &J[0][0]);
+            double M[D][D], b[D];
+            for (int r = 0; r < D; ++r) {
+                b[r] = -g[r];
+                for (int c = 0; c < D; ++c) M[r][c] = (r == c ? 1.0 : 0.0) - (dt * beta) * J[r][c];
+            }
+            for (int i = 0; i < D; ++i) {
+                int piv = i;
+                double best = std::fabs(M[i][i]);
+                for (int r = i + 1; r < D; ++r)
+                    if (std::fabs(M[r][i]) > best) { best = std::fabs(M[r][i]); piv = r; }
+                if (best == 0.0) return ST_SINGULAR;
+                if (piv != i) {
+                    for (int c = 0; c < D; ++c) std::swap(M[i][c], M[piv][c]);
+                    std::swap(b[i], b[piv]);
+                }
+                const double inv_diag = 1.0 / M[i][i];
+                for (int r = i + 1; r < D; ++r) {
+                    const double l = M[r][i] * inv_diag;
+                    for (int c = i + 1; c < D; ++c) M[r][c] -= l * M[i][c];
+                    b[r] -= l * b[i];
+                }
+            }
+            double ss = 0.0;
+            for (int i = D - 1; i >= 0; --i) {
+                double acc = b[i];
+                for (int c = i + 1; c < D; ++c) acc -= M[i][c] * b[c];
+                b[i] = acc / M[i][i];
+            }
+            for (int d = 0; d < D; ++d) { x[d] += b[d]; ss += b[d] * b[d]; }
+            if (ss <= tolerance * tolerance) { result = x; return ST_OK; }
+        }
+        return ST_MAX_ITER;
+    }
+
     int secant(bool higher, Vec<D>& result) {
+        if (newton) return newton_solve(higher, result);
         // bdf.rs:403,405,423,454 pass self.time (t_n) to g (D7); intent t_{n+1}
         const double tg = (mode == Mode::Literal) ? time : time + dt;
         auto g = [&](const double* x, double* out) { return g_eval(higher, tg, x, out); };
@@ -685,8 +734,10 @@ inline Solution<D> solve_rk(const RkTableau<O>& T, Rhs rhs, const double* params
 template <int D, int O, class Rhs>
 inline Solution<D> solve_bdf(const BdfCoefficients<O>& C, Rhs rhs, const double* params,
                              const double* y0, double t0, double t1, double dtmin, double dtmax,
-                             double tol, Mode mode, uint64_t max_attempts, bool keep_path) {
+                             double tol, Mode mode, uint64_t max_attempts, bool keep_path,
+                             bool newton = false) {
     BDFSolver<D, O, Rhs> s(C, rhs, params, y0, t0, t1, dtmin, dtmax, tol, mode);
+    s.newton = newton;
     Solution<D> sol;
     drive<D>(s, max_attempts, keep_path, sol, [&](BDFSolver<D, O, Rhs>& st) {
         sol.path_t.push_back(st.out_t);

@@ -74,7 +74,7 @@ def rhs_info(name):
 
 def solve_ensemble(method, rhs, y0, params=None, *, dt_min, dt_max, tol, t_start, t_end,
                    semantics=_abi.SEM_CORRECTED, shared_params=False, params_aos=False, history_capacity=0,
-                   max_attempts=0, pow_mode=0, n_threads=0):
+                   max_attempts=0, pow_mode=0, n_threads=0, bdf_newton=False):
     """Run the oracle on an ensemble.  y0: (dim, n) float64; params: (n_params, n) or (n_params,).
 
     Returns a dict of numpy arrays with the same names/layouts as bacon_ivp_result.
@@ -84,7 +84,7 @@ def solve_ensemble(method, rhs, y0, params=None, *, dt_min, dt_max, tol, t_start
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
     assert y0.ndim == 2 and y0.shape[0] == dim, (y0.shape, dim)
     n = y0.shape[1]
-    flags = 0
+    flags = _abi.FLAG_BDF_NEWTON if bdf_newton else 0
     pptr = None
     if npar > 0:
         params = np.ascontiguousarray(params, dtype=np.float64)

@@ -33,6 +33,11 @@ struct RhsLorenz {  // p = (sigma, rho, beta)
         dy[2] = y[0] * y[1] - p[2] * y[2];
         return true;
     }
+    void jac(double, const double* y, const double* p, double* J) const {
+        J[0] = -p[0]; J[1] = p[0]; J[2] = 0.0;
+        J[3] = p[1] - y[2]; J[4] = -1.0; J[5] = -y[0];
+        J[6] = y[1]; J[7] = y[0]; J[8] = -p[2];
+    }
 };
 struct RhsVdp {  // p = (mu)
     static constexpr int DIM = 2, NPARAM = 1;
@@ -40,6 +45,10 @@ struct RhsVdp {  // p = (mu)
         dy[0] = y[1];
         dy[1] = (p[0] * (1.0 - y[0] * y[0])) * y[1] - y[0];
         return true;
+    }
+    void jac(double, const double* y, const double* p, double* J) const {
+        J[0] = 0.0; J[1] = 1.0;
+        J[2] = -2.0 * p[0] * y[0] * y[1] - 1.0; J[3] = p[0] * (1.0 - y[0] * y[0]);
     }
 };
 struct RhsRobertson {  // p = (k1, k2, k3)
@@ -53,6 +62,12 @@ struct RhsRobertson {  // p = (k1, k2, k3)
         dy[2] = c;
         return true;
     }
+    void jac(double, const double* y, const double* p, double* J) const {
+        const double k3y2 = p[2] * y[2], k3y1 = p[2] * y[1], k2y1 = 2.0 * p[1] * y[1];
+        J[0] = -p[0]; J[1] = k3y2; J[2] = k3y1;
+        J[3] = p[0]; J[4] = -k3y2 - k2y1; J[5] = -k3y1;
+        J[6] = 0.0; J[7] = k2y1; J[8] = 0.0;
+    }
 };
 template <int N> struct RhsLinear {  // p = A row-major [N][N]
     static constexpr int DIM = N, NPARAM = N * N;
@@ -64,22 +79,29 @@ template <int N> struct RhsLinear {  // p = A row-major [N][N]
         }
         return true;
     }
+    void jac(double, const double*, const double* p, double* J) const {
+        for (int i = 0; i < N * N; ++i) J[i] = p[i];
+    }
 };
 struct RhsExp {  // y' = y   (README.md:26-28, rk.rs:539-541, bdf.rs:769-771)
     static constexpr int DIM = 1, NPARAM = 0;
     bool operator()(double, const double* y, const double*, double* dy) const { dy[0] = y[0]; return true; }
+    void jac(double, const double*, const double*, double* J) const { J[0] = 1.0; }
 };
 struct RhsDecay {  // y' = -y  (bdf.rs:781-783)
     static constexpr int DIM = 1, NPARAM = 0;
     bool operator()(double, const double* y, const double*, double* dy) const { dy[0] = -y[0]; return true; }
+    void jac(double, const double*, const double*, double* J) const { J[0] = -1.0; }
 };
 struct RhsQuadratic {  // y' = -2t (rk.rs:664-666, bdf.rs:773-775)
     static constexpr int DIM = 1, NPARAM = 0;
     bool operator()(double t, const double*, const double*, double* dy) const { dy[0] = -2.0 * t; return true; }
+    void jac(double, const double*, const double*, double* J) const { J[0] = 0.0; }
 };
 struct RhsCos {  // y' = cos t (rk.rs:668-670, bdf.rs:777-779)
     static constexpr int DIM = 1, NPARAM = 0;
     bool operator()(double t, const double*, const double*, double* dy) const { dy[0] = std::cos(t); return true; }
+    void jac(double, const double*, const double*, double* J) const { J[0] = 0.0; }
 };
 struct RhsHarmonic {  // y'' = -w^2 y ; p = (w)
     static constexpr int DIM = 2, NPARAM = 1;
@@ -87,6 +109,9 @@ struct RhsHarmonic {  // y'' = -w^2 y ; p = (w)
         dy[0] = y[1];
         dy[1] = -(p[0] * p[0]) * y[0];
         return true;
+    }
+    void jac(double, const double*, const double* p, double* J) const {
+        J[0] = 0.0; J[1] = 1.0; J[2] = -(p[0] * p[0]); J[3] = 0.0;
     }
 };
 
@@ -136,6 +161,7 @@ template <class Rhs> static void run_one(const RunArgs& a, size_t i) {
         p[k] = shared ? a.params[k] : (aos ? a.params[i * (size_t)P + k] : a.params[(size_t)k * a.n + i]);
     const bo::Mode mode = c.semantics == BACON_SEM_LITERAL ? bo::Mode::Literal : bo::Mode::Corrected;
     const bool keep = c.history_capacity > 0;
+    const bool newton = (c.flags & BACON_FLAG_BDF_NEWTON) != 0;
     bo::Solution<D> s;
     switch (c.method) {
         case BACON_RK45:
@@ -148,11 +174,11 @@ template <class Rhs> static void run_one(const RunArgs& a, size_t i) {
             break;
         case BACON_BDF6:
             s = bo::solve_bdf<D, 7>(bo::coefficients_bdf6(), Rhs{}, p.data(), y0, c.t_start, c.t_end,
-                                    c.dt_min, c.dt_max, c.tol, mode, c.max_attempts, keep);
+                                    c.dt_min, c.dt_max, c.tol, mode, c.max_attempts, keep, newton);
             break;
         default:
             s = bo::solve_bdf<D, 3>(bo::coefficients_bdf2(), Rhs{}, p.data(), y0, c.t_start, c.t_end,
-                                    c.dt_min, c.dt_max, c.tol, mode, c.max_attempts, keep);
+                                    c.dt_min, c.dt_max, c.tol, mode, c.max_attempts, keep, newton);
             break;
     }
     store<D>(a, i, s);

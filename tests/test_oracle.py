@@ -1,0 +1,170 @@
+"""Pins the CPU oracle (oracle/) before anything is compared against it (CPU only, no GPU):
+
+ * every test problem the reference holds for this path, replayed with the reference's own
+   assertion on every yielded point (rk.rs:682-758; bdf.rs:785-1063 in REF_CORRECTED, and the
+   vacuous empty-path outcome of the same tests in REF_LITERAL);
+ * the known answers of src/tests/roots/mod.rs:169-221 for the Broyden + LU code BDF shares;
+ * the predicted-answer table of SURVEY.md §8c;
+ * independent anchors: closed forms and SciPy DOP853 / Radau (tests/golden/anchors.json).
+The Rust reference cannot be executed in this image: "parity unpinned" for the RK stage matrix
+and for BDF beyond these anchors (see oracle/bacon_oracle.hpp header).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from bacon_b200 import _abi
+from bacon_b200 import ensembles as E
+from reference_cases import BDF_CASES, RK_CASES, bdf_cfg
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "anchors.json")))
+M = {"RK45": _abi.RK45, "RK23": _abi.RK23, "BDF6": _abi.BDF6, "BDF2": _abi.BDF2}
+
+
+@pytest.mark.parametrize("method", ["RK45", "RK23"])
+@pytest.mark.parametrize("case", RK_CASES, ids=[c[0] for c in RK_CASES])
+def test_reference_rk_tests(oracle, method, case):
+    name, rhs, y0, cfg, exact, eps, n_acc = case
+    outs = []
+    for sem in (_abi.SEM_CORRECTED, _abi.SEM_LITERAL):
+        r = oracle.solve_ensemble(M[method], rhs, np.array([[y0]]), semantics=sem, history_capacity=1100, **cfg)
+        assert r["status"][0] == _abi.OK and r["n_accept"][0] == n_acc and r["n_reject"][0] == 0
+        m = int(r["hist_len"][0])
+        t, y = r["hist_t"][0, :m], r["hist_y"][0, :m, 0]
+        assert np.abs(y - exact(t)).max() <= eps  # the reference's assertion
+        assert t[-1] == cfg["t_end"]
+        outs.append((t.copy(), y.copy()))
+    # y-independent RHS: the stage matrix never matters, so LITERAL == CORRECTED bit for bit
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("case", BDF_CASES, ids=[c[0] for c in BDF_CASES])
+def test_reference_bdf_tests(oracle, case):
+    name, method, rhs, y0, t_end, exact, eps, n_yield, lit_t = case
+    r = oracle.solve_ensemble(M[method], rhs, np.array([[y0]]), history_capacity=25000, **bdf_cfg(t_end))
+    assert r["status"][0] == _abi.OK
+    m = int(r["hist_len"][0])
+    assert m == r["n_accept"][0] and m > 0
+    if n_yield is not None:
+        assert m == n_yield
+    t, y = r["hist_t"][0, :m], r["hist_y"][0, :m, 0]
+    assert np.abs(y - exact(t)).max() <= eps  # the reference's assertion, now over a non-empty path
+    assert np.all(np.diff(t) > 0)
+    # as written (D4-D6): the rollback `time -= dt - order` jumps past t_end -> Done with an EMPTY path,
+    # so the reference's own assertion loop runs zero times
+    lit = oracle.solve_ensemble(M[method], rhs, np.array([[y0]]), semantics=_abi.SEM_LITERAL, history_capacity=16,
+                                **bdf_cfg(t_end))
+    assert lit["status"][0] == _abi.OK and lit["n_accept"][0] == 0 and lit["hist_len"][0] == 0
+    assert lit["t_end"][0] == pytest.approx(lit_t, abs=1e-3)
+
+
+def test_roots_secant_known_answers(oracle):
+    """src/tests/roots/mod.rs:169-221 — same Broyden + LU code as bdf.rs:414-475."""
+    for central in (False, True):  # `above + below` as written (roots/mod.rs:249) and the central difference
+        rc, sol, it = oracle.roots_secant(0, [0.1, 0.1, -0.1], 0.1, 1e-5, central=central)
+        assert rc == 0 and np.allclose(sol, [0.5, 0.0, -0.52359877], atol=1e-5)
+        rc, sol, it = oracle.roots_secant(1, [0.7, 1.8], 0.1, 1e-6, central=central)
+        assert rc == 0 and abs(sol[0] + 0.703467) <= 1e-6 and abs(sol[1] - 1.85718) <= 1e-5
+        rc, sol, it = oracle.roots_secant(1, [0.7, 4.7], 0.1, 1e-6, central=central)
+        assert rc == 0 and abs(sol[0] + 0.703467) <= 1e-6 and abs(sol[1] - 4.5364) <= 1e-5
+        rc, sol, it = oracle.roots_secant(2, [0.6], 0.1, 1e-4, central=central)
+        assert rc == 0 and abs(sol[0] - 0.739085) <= 1e-6
+
+
+def test_predicted_answers_readme_and_doc_example(oracle):
+    """SURVEY.md §8c table, BASELINE config 1 (README.md:32-40) and rk.rs:544-552."""
+    y0 = np.array([[1.0]])
+    cfg = dict(dt_min=0.01, dt_max=0.1, tol=1e-4, t_start=0.0, t_end=10.0)
+    r = oracle.solve_ensemble(_abi.RK45, "exp", y0, **cfg)
+    assert (r["status"][0], r["n_accept"][0], r["n_reject"][0]) == (_abi.OK, 128, 0)
+    assert r["y_end"][0, 0] == pytest.approx(22026.4819, rel=1e-8)
+    assert abs(r["y_end"][0, 0] / np.exp(10.0) - 1.0) == pytest.approx(7.3e-7, rel=0.05)
+    r = oracle.solve_ensemble(_abi.RK45, "exp", y0, semantics=_abi.SEM_LITERAL, **cfg)
+    assert r["status"][0] == _abi.E_MIN_DT_EXCEEDED and r["n_accept"][0] == 1
+    assert r["t_end"][0] == pytest.approx(0.055) and r["y_end"][0, 0] == pytest.approx(1.055)
+    r = oracle.solve_ensemble(_abi.RK45, "exp", y0, semantics=_abi.SEM_LITERAL, **{**cfg, "dt_min": 1e-3})
+    assert r["status"][0] == _abi.E_MIN_DT_EXCEEDED and r["n_accept"][0] == 1 and r["t_end"][0] == pytest.approx(0.0505)
+
+
+def test_lorenz_against_scipy(oracle):
+    p = np.array(E.LORENZ["params"])
+    cfg = dict(dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0.0)
+    r = oracle.solve_ensemble(_abi.RK45, "lorenz", np.ones((3, 1)), p, shared_params=True, t_end=1.0, **cfg)
+    assert (r["n_accept"][0], r["n_reject"][0]) == (925, 2)
+    np.testing.assert_allclose(r["y_end"][:, 0], GOLD["lorenz_111_T1"], rtol=2e-9)
+    np.testing.assert_allclose(r["y_end"][:, 0], [-9.3785700104, -8.3570337871, 29.3623253376], rtol=1e-10)
+    y0 = E.lorenz_y0(np.arange(16))
+    r = oracle.solve_ensemble(_abi.RK45, "lorenz", y0, p, shared_params=True, t_end=2.0, **cfg)
+    gold = np.array(GOLD["lorenz_seeded16_T2"]).T
+    err = np.sqrt(((r["y_end"] - gold) ** 2).sum(0)) / np.sqrt((gold ** 2).sum(0))
+    assert err.max() < 1e-7  # global error of the tol-1e-8 integration itself
+    # RK23 converges to the same anchors
+    r = oracle.solve_ensemble(_abi.RK23, "lorenz", np.ones((3, 1)), p, shared_params=True, t_end=1.0, **{**cfg, "tol": 1e-7})
+    np.testing.assert_allclose(r["y_end"][:, 0], GOLD["lorenz_111_T1"], rtol=1e-6)
+
+
+def test_vdp_and_linear32_against_anchors(oracle):
+    for mu in (0.1, 1.0, 5.0):
+        r = oracle.solve_ensemble(_abi.RK23, "vdp", np.array([[2.0], [0.0]]), np.array([[mu]]), dt_min=1e-12, dt_max=0.1,
+                                  tol=1e-10, t_start=0.0, t_end=0.25)
+        assert r["status"][0] == _abi.OK
+        np.testing.assert_allclose(r["y_end"][:, 0], GOLD["vdp_T025"][str(mu)], rtol=1e-8, atol=1e-10)
+    y0, A = E.linear32_problem(np.arange(4))
+    r = oracle.solve_ensemble(_abi.RK45, "linear32", y0, A, params_aos=True, dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0.0,
+                              t_end=4.0, history_capacity=256)
+    gold = np.array(GOLD["linear32_seeded4_T4"]).T
+    err = np.sqrt(((r["y_end"] - gold) ** 2).sum(0)) / np.sqrt((gold ** 2).sum(0))
+    assert (r["status"] == _abi.OK).all() and err.max() < 1e-6
+    assert (r["hist_len"] > 100).all() and (r["hist_len"] < 256).all()  # config 4: ~160 points, capacity 256
+
+
+def test_robertson_bdf6_against_radau(oracle):
+    """5005 yielded points, y(0.5) = SciPy Radau to 9 digits; Broyden and Newton agree."""
+    k = np.array([0.04, 3e7, 1e4])
+    y0 = np.array([[1.0], [0.0], [0.0]])
+    cfg = dict(dt_min=1e-10, dt_max=1e-4, tol=1e-6, t_start=0.0, t_end=0.5)
+    br = oracle.solve_ensemble(_abi.BDF6, "robertson", y0, k, shared_params=True, **cfg)
+    nw = oracle.solve_ensemble(_abi.BDF6, "robertson", y0, k, shared_params=True, bdf_newton=True, **cfg)
+    for r in (br, nw):
+        assert r["status"][0] == _abi.OK and r["n_accept"][0] == 5005
+        np.testing.assert_allclose(r["y_end"][:, 0], GOLD["robertson_T05"], rtol=2e-8)
+    np.testing.assert_allclose(br["y_end"], nw["y_end"], rtol=1e-9)
+    # as written: finite-difference "Jacobian" is a SUM (bdf.rs:407) -> near rank-1 -> failure
+    # with dt_max = 1e-4 the first rejected speculative step jumps time forward by O - dt (bdf.rs:622, D6) past
+    # t_end: Done with nothing yielded; with dt_max = 1e-2 the sum-"Jacobian" yields NaN -> MaximumIterationsExceeded
+    lit = oracle.solve_ensemble(_abi.BDF6, "robertson", y0, k, shared_params=True, semantics=_abi.SEM_LITERAL, **cfg)
+    assert lit["status"][0] == _abi.OK and lit["n_accept"][0] == 0 and lit["t_end"][0] > 7.0
+    lit = oracle.solve_ensemble(_abi.BDF6, "robertson", y0, k, shared_params=True, semantics=_abi.SEM_LITERAL,
+                                **{**cfg, "dt_max": 1e-2})
+    assert lit["status"][0] == _abi.E_MAX_ITER and lit["n_accept"][0] == 0
+
+
+def test_pow_vs_sqrt_sqrt(oracle):
+    """rk.rs:401 calls powf(x, 1/4); the strict device kernels use sqrt(sqrt(x)).  Both are within 1 ulp,
+    and the final states they lead to agree far inside the parity band."""
+    x = np.exp(np.random.default_rng(1).uniform(np.log(1e-12), np.log(1e12), 200000))
+    a, b = oracle.fourth_root(x)
+    assert (np.abs(a - b) <= np.spacing(a)).all()
+    assert (a == b).mean() > 0.7
+    y0 = E.lorenz_y0(np.arange(64))
+    cfg = dict(dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0.0, t_end=5.0)
+    p = np.array(E.LORENZ["params"])
+    r0 = oracle.solve_ensemble(_abi.RK45, "lorenz", y0, p, shared_params=True, pow_mode=0, **cfg)
+    r1 = oracle.solve_ensemble(_abi.RK45, "lorenz", y0, p, shared_params=True, pow_mode=1, **cfg)
+    err = np.sqrt(((r0["y_end"] - r1["y_end"]) ** 2).sum(0)) / np.sqrt((r0["y_end"] ** 2).sum(0))
+    assert err.max() < 1e-9
+
+
+def test_oracle_failure_statuses(oracle):
+    y0 = E.lorenz_y0(np.arange(8))
+    p = np.array(E.LORENZ["params"])
+    r = oracle.solve_ensemble(_abi.RK45, "lorenz", y0, p, shared_params=True, dt_min=5e-3, dt_max=0.1, tol=1e-8, t_start=0, t_end=5)
+    assert (r["status"] == _abi.E_MIN_DT_EXCEEDED).all()
+    r = oracle.solve_ensemble(_abi.RK45, "lorenz", y0, p, shared_params=True, dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0, t_end=5,
+                              max_attempts=50)
+    assert (r["status"] == _abi.E_MAX_ATTEMPTS).all() and (r["n_accept"] + r["n_reject"] == 50).all()
+    y0[0, 3] = np.nan
+    r = oracle.solve_ensemble(_abi.RK45, "lorenz", y0, p, shared_params=True, dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0, t_end=0.1)
+    assert r["status"][3] == _abi.E_NONFINITE and (np.delete(r["status"], 3) == _abi.OK).all()
