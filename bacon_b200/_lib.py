@@ -9,7 +9,8 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbacon_ivp.so")
+# BACON_IVP_LIB: load another build of the same ABI (A/B timing of kernel variants on one box)
+LIB_PATH = os.environ.get("BACON_IVP_LIB") or os.path.join(_HERE, "libbacon_ivp.so")
 _LIB = None
 
 

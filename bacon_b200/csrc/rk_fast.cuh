@@ -36,6 +36,10 @@ __device__ __forceinline__ double inv_eighth_root(double x) {
     return fma(z * 0.125, r, z);        // Newton on z^-8 = x
 }
 
+// a <= b / a < b for doubles that are >= +0 (or NaN, which orders above everything): integer pipe
+__device__ __forceinline__ bool pos_le(double a, double b) { return __double_as_longlong(a) <= __double_as_longlong(b); }
+__device__ __forceinline__ bool pos_lt(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
+
 template <class Tab, int I> __host__ __device__ constexpr int first_nz_a() {
     for (int j = 0; j < I; ++j)
         if (Tab::a(I, j) != 0.0) return j;
@@ -67,6 +71,7 @@ template <class Rhs, class Tab> struct RkFastStepper {
     double y[D], p[P > 0 ? P : 1];
     double t, dt;
     uint32_t n_acc, n_rej, n_att;
+    bool clamped;  // the previous attempt used dt = t_end - t
 
     __device__ __forceinline__ explicit RkFastStepper(const bacon_launch_args& a) {
         t_start = a.cfg.t_start;
@@ -81,11 +86,13 @@ template <class Rhs, class Tab> struct RkFastStepper {
         t = t_start;
         dt = dt0;
         n_acc = n_rej = n_att = 0;
+        clamped = false;
     }
     __device__ __forceinline__ void reset(const bacon_launch_args& a, unsigned long long idx, bool live) {
         t = t_start;
         dt = dt0;
         n_acc = n_rej = n_att = 0;
+        clamped = false;
         if (live) load_problem<D, P>(a, idx, y, p);
     }
     __device__ __forceinline__ uint32_t n_rhs() const { return n_att * (uint32_t)O; }
@@ -98,9 +105,12 @@ template <class Rhs, class Tab> struct RkFastStepper {
         const Rhs rhs{};
         yielded = false;
         if (n_att >= cap) return BACON_E_MAX_ATTEMPTS;
-        if (t >= t_end) return BACON_OK;  // rk.rs:362-364
+        // rk.rs:362-364.  t can only have reached t_end in an attempt whose step was clamped to land on it
+        // (otherwise t_new = t + dt < t_end was just tested), so the FP64 compare is skipped otherwise.
+        if (clamped && t >= t_end) return BACON_OK;
         double h = dt;
-        if (t + h >= t_end) h = t_end - t;  // rk.rs:366-368
+        clamped = t + h >= t_end;
+        if (clamped) h = t_end - t;  // rk.rs:366-368
 
         double f[O][D];
         rhs(t, y, p, f[0]);
@@ -134,9 +144,11 @@ template <class Rhs, class Tab> struct RkFastStepper {
         }
 
         n_att++;
-        if (q != q) return BACON_E_NONFINITE;  // the reference would Redo forever (D8)
-
-        const bool accepted = q <= tol2;  // rk.rs:392
+        // Comparisons of non-negative doubles are done on their bit patterns (integer pipe): the FP64
+        // pipe is the bound of this kernel and a DSETP costs it as much as a DFMA.  A NaN q has a bit
+        // pattern above every finite value, so it is "not accepted" and is diagnosed on that rare path.
+        const bool accepted = pos_le(q, tol2);  // rk.rs:392
+        if (!accepted && q != q) return BACON_E_NONFINITE;  // the reference would Redo forever (D8)
         if (accepted) {
             t += h;
             constexpr int b0 = first_nz_b<Tab>();
@@ -150,13 +162,20 @@ template <class Rhs, class Tab> struct RkFastStepper {
                 y[d] = fma(h, s, y[d]);
             }
         }
-        // rk.rs:400-412; outside [1e-6, 1e8] the clamp to [0.1, 4] decides anyway
-        const double x = fmin(fmax(q * inv_tol2, 1e-6), 1e8);
-        const double delta = fmin(fmax(Tab::safety * inv_eighth_root(x), 0.1), 4.0);
-        dt = fmin(h * delta, dt_max);
-        if (dt < dt_min && t < t_end) {  // rk.rs:414-416 (fails before the point is yielded)
-            if (!accepted) n_rej++;
-            return BACON_E_MIN_DT_EXCEEDED;
+        // rk.rs:400-412; outside [1e-6, 1e8] the clamp of delta to [0.1, 4] decides anyway
+        double x = q * inv_tol2;
+        x = pos_lt(x, 1e-6) ? 1e-6 : x;
+        x = pos_lt(1e8, x) ? 1e8 : x;
+        double delta = Tab::safety * inv_eighth_root(x);
+        delta = pos_lt(delta, 0.1) ? 0.1 : delta;
+        delta = pos_lt(4.0, delta) ? 4.0 : delta;
+        dt = h * delta;
+        dt = pos_lt(dt_max, dt) ? dt_max : dt;
+        if (pos_lt(dt, dt_min)) {
+            if (t < t_end) {  // rk.rs:414-416 (fails before the point is yielded)
+                if (!accepted) n_rej++;
+                return BACON_E_MIN_DT_EXCEEDED;
+            }
         }
         if (accepted) {
             n_acc++;

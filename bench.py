@@ -137,7 +137,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def summary(self):
         med = float(np.median(self.samples)) if self.samples else None
@@ -176,19 +176,16 @@ def ours(args):
     p = p_host.to(dev)
     out = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    gathered = torch.empty((world, 3, n), dtype=torch.float64, device=dev) if world > 1 else None
-    stats = torch.zeros(3, dtype=torch.float64, device=dev)
+    from bacon_b200.shard import gather_final_states, reduce_stats_device
+    state = {"stats": None, "y_all": None}
 
     def step():
+        """One pass of the hot path over this rank's shard + the only collectives of the path (N>1):
+        all-gather of the final states into global trajectory order, all-reduce of the counters."""
         nonlocal out
         out = solver.solve_ivp_ensemble_device(y0, p, shared_params=True, out=out)
-        # statistics + (N>1) the only collectives of the path: gather final states, sum counters
-        stats[0] = out["n_accept"].sum(dtype=torch.float64)
-        stats[1] = out["n_reject"].sum(dtype=torch.float64)
-        stats[2] = (out["status"] != 0).sum(dtype=torch.float64)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out["y_end"])
-            dist.all_reduce(stats)
+        state["stats"] = reduce_stats_device(out["n_accept"], out["n_reject"], out["n_rhs"], out["status"])
+        state["y_all"] = gather_final_states(out["y_end"], n * world, world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,12 +211,8 @@ def ours(args):
         kev[k][0].record()
         out = solver.solve_ivp_ensemble_device(y0, p, shared_params=True, out=out)
         kev[k][1].record()
-        stats[0] = out["n_accept"].sum(dtype=torch.float64)
-        stats[1] = out["n_reject"].sum(dtype=torch.float64)
-        stats[2] = (out["status"] != 0).sum(dtype=torch.float64)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out["y_end"])
-            dist.all_reduce(stats)
+        state["stats"] = reduce_stats_device(out["n_accept"], out["n_reject"], out["n_rhs"], out["status"])
+        state["y_all"] = gather_final_states(out["y_end"], n * world, world)
         ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -232,7 +225,7 @@ def ours(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)       # max over ranks
     dev_ms, ker_ms = float(tmax[0]), float(tmax[1])
-    acc_total, rej_total, bad = (float(x) for x in stats.cpu())  # global sums of the LAST step (all steps identical)
+    acc_total, rej_total, _, bad = (float(x) for x in state["stats"].cpu())  # global sums of the last step (all steps identical)
     assert bad == 0, f"{bad} trajectories did not finish with status Ok"
     value = acc_total * args.steps / (dev_ms * 1e-3)
 

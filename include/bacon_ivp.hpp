@@ -1,0 +1,165 @@
+// bacon_ivp.hpp — C++ host-side mirror of bacon_sci::ivp's solver front end over the C ABI
+// (header only; link with -lbacon_ivp).  The reference is compiled code (Rust) and no Rust
+// toolchain exists in the build image, so this is the compiled-language façade that is
+// actually built and tested; rust/ holds the same façade written in Rust (unverified).
+//
+// Names and error behaviour follow the `IVPSolver` builder trait (src/ivp.rs:134-190) as
+// implemented in src/ivp/rk.rs:118-343 and src/ivp/bdf.rs:124-332.  Rust's
+// `Result<Self, IVPError>` becomes "returns *this or throws bacon::IVPError"; the error
+// carries the same variant (src/ivp.rs:50-76).  README aliases (README.md:24-40) included.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "bacon_ivp.h"
+
+namespace bacon {
+
+struct IVPError : std::runtime_error {
+    int code;  // bacon_status; 1..12 are the IVPError variants of src/ivp.rs:50-76
+    IVPError(int c, const std::string& what) : std::runtime_error(std::string(bacon_status_name(c)) + ": " + what), code(c) {}
+};
+
+inline void check(int rc) {
+    if (rc != 0) throw IVPError(rc, bacon_last_error());
+}
+
+// One trajectory's `Path` (src/ivp.rs:203): accepted (t, y) points.
+using Path = std::vector<std::pair<double, std::vector<double>>>;
+
+struct EnsembleResult {
+    size_t n = 0;
+    int dim = 0, capacity = 0;
+    std::vector<double> y_end, t_end, dt_end, hist_t, hist_y;  // layouts of bacon_ivp_result
+    std::vector<int32_t> status;
+    std::vector<uint32_t> n_accept, n_reject, n_rhs, hist_len;
+    bacon_ivp_launch_info launch{};
+    double y(size_t i, int d) const { return y_end[(size_t)d * n + i]; }
+    Path path(size_t i) const {
+        Path p;
+        for (uint32_t k = 0; k < hist_len[i]; ++k) {
+            const double* row = &hist_y[(i * capacity + k) * dim];
+            p.emplace_back(hist_t[i * capacity + k], std::vector<double>(row, row + dim));
+        }
+        return p;
+    }
+};
+
+template <int METHOD> class Solver {
+    bacon_solver* h_;
+    int dim_;
+    int rhs_ = -1;
+    std::vector<double> y0_;
+
+  public:
+    explicit Solver(int dim) : h_(bacon_solver_new(METHOD, dim)), dim_(dim) {
+        if (!h_) throw IVPError(BACON_E_BAD_ARGUMENT, bacon_last_error());
+    }
+    ~Solver() { bacon_solver_free(h_); }
+    Solver(const Solver&) = delete;
+    Solver& operator=(const Solver&) = delete;
+    Solver(Solver&& o) noexcept : h_(o.h_), dim_(o.dim_), rhs_(o.rhs_), y0_(std::move(o.y0_)) { o.h_ = nullptr; }
+
+    static Solver new_dyn(int size) { return Solver(size); }  // ivp.rs:163
+    int dim() const { return dim_; }
+
+    Solver& with_tolerance(double tol) { check(bacon_solver_with_tolerance(h_, tol)); return *this; }          // rk.rs:168
+    Solver& with_maximum_dt(double v) { check(bacon_solver_with_maximum_dt(h_, v)); return *this; }            // rk.rs:179
+    Solver& with_minimum_dt(double v) { check(bacon_solver_with_minimum_dt(h_, v)); return *this; }            // rk.rs:197
+    Solver& with_initial_time(double v) { check(bacon_solver_with_initial_time(h_, v)); return *this; }        // rk.rs:212
+    Solver& with_ending_time(double v) { check(bacon_solver_with_ending_time(h_, v)); return *this; }          // rk.rs:224
+    Solver& with_initial_conditions_slice(const std::vector<double>& y0) {                                      // ivp.rs:177
+        if ((int)y0.size() != dim_) throw IVPError(BACON_E_BAD_ARGUMENT, "initial conditions do not match dim()");
+        y0_ = y0;
+        return *this;
+    }
+    Solver& with_initial_conditions(const std::vector<double>& y0) { return with_initial_conditions_slice(y0); }
+    Solver& with_derivative(const std::string& rhs_name) {                                                      // ivp.rs:186
+        rhs_ = bacon_rhs_lookup(rhs_name.c_str());
+        if (rhs_ < 0) throw IVPError(BACON_E_BAD_ARGUMENT, "no right-hand side named '" + rhs_name + "'");
+        return *this;
+    }
+    // README.md:33-39
+    Solver& with_dt_max(double v) { return with_maximum_dt(v); }
+    Solver& with_dt_min(double v) { return with_minimum_dt(v); }
+    Solver& with_start(double v) { return with_initial_time(v); }
+    Solver& with_end(double v) { return with_ending_time(v); }
+    Solver& build() { return *this; }
+    // engine knobs
+    Solver& with_semantics(int s) { check(bacon_solver_with_semantics(h_, s)); return *this; }
+    Solver& with_flags(uint32_t f) { check(bacon_solver_with_flags(h_, f)); return *this; }
+    Solver& with_history(int cap) { check(bacon_solver_with_history(h_, cap)); return *this; }
+    Solver& with_max_attempts(uint64_t cap) { check(bacon_solver_with_max_attempts(h_, cap)); return *this; }
+
+    bacon_ivp_config config() const {
+        bacon_ivp_config c;
+        check(bacon_solver_config(h_, &c));
+        return c;
+    }
+
+    // N initial conditions x N parameter sets.  y0: [dim][n]; params: [n_params][n] (or [n_params] shared).
+    EnsembleResult solve_ivp_ensemble(size_t n, const double* y0, const double* params, bool shared_params = false,
+                                      int n_gpus = 1) const {
+        if (rhs_ < 0) throw IVPError(BACON_E_MISSING_PARAMETERS, "with_derivative was not called");
+        bacon_ivp_config c = config();
+        int d = 0, np = 0;
+        check(bacon_rhs_info(rhs_, nullptr, &d, &np));
+        c.n_params = np;
+        if (shared_params) c.flags |= BACON_FLAG_SHARED_PARAMS;
+        EnsembleResult r;
+        r.n = n;
+        r.dim = c.dim;
+        r.capacity = c.history_capacity;
+        r.y_end.resize((size_t)c.dim * n);
+        r.t_end.resize(n);
+        r.dt_end.resize(n);
+        r.status.assign(n, -1);
+        r.n_accept.resize(n);
+        r.n_reject.resize(n);
+        r.n_rhs.resize(n);
+        bacon_ivp_result o{};
+        o.y_end = r.y_end.data();
+        o.t_end = r.t_end.data();
+        o.dt_end = r.dt_end.data();
+        o.status = r.status.data();
+        o.n_accept = r.n_accept.data();
+        o.n_reject = r.n_reject.data();
+        o.n_rhs = r.n_rhs.data();
+        if (c.history_capacity > 0) {
+            r.hist_t.resize(n * c.history_capacity);
+            r.hist_y.resize(n * c.history_capacity * c.dim);
+            r.hist_len.resize(n);
+            o.hist_t = r.hist_t.data();
+            o.hist_y = r.hist_y.data();
+            o.hist_len = r.hist_len.data();
+        }
+        check(bacon_ivp_solve_ensemble_multi(&c, rhs_, n, y0, params, &o, n_gpus));
+        check(bacon_ivp_last_launch(&r.launch));
+        return r;
+    }
+
+    // solve(data) + collect_vec (rk.rs:249-343, ivp.rs:209-211): the single trajectory set by with_initial_conditions
+    Path solve(const std::vector<double>& data = {}, int capacity = 1 << 16) {
+        if (y0_.empty()) throw IVPError(BACON_E_MISSING_PARAMETERS, "with_initial_conditions was not called");
+        with_history(capacity);
+        EnsembleResult r = solve_ivp_ensemble(1, y0_.data(), data.empty() ? nullptr : data.data());
+        with_history(0);
+        if (r.status[0] != BACON_OK) throw IVPError(r.status[0], "trajectory failed after " + std::to_string(r.hist_len[0]) + " point(s)");
+        return r.path(0);
+    }
+    Path solve_ivp(const std::string& rhs_name, const std::vector<double>& data = {}) {  // README.md:40
+        return with_derivative(rhs_name).solve(data);
+    }
+};
+
+using RungeKutta45 = Solver<BACON_RK45>;  // rk.rs:561
+using RungeKutta23 = Solver<BACON_RK23>;  // rk.rs:656
+using BDF6 = Solver<BACON_BDF6>;          // bdf.rs:706
+using BDF2 = Solver<BACON_BDF2>;          // bdf.rs:762
+using RK45 = RungeKutta45;                // README.md:24
+using RK23 = RungeKutta23;
+
+}  // namespace bacon

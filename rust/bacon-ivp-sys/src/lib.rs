@@ -1,0 +1,96 @@
+//! Raw bindings to `include/bacon_ivp.h` (ABI version 1).  UNVERIFIED: no Rust toolchain in the build image.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_double, c_int, c_void};
+
+pub const BACON_RK45: c_int = 0;
+pub const BACON_RK23: c_int = 1;
+pub const BACON_BDF6: c_int = 2;
+pub const BACON_BDF2: c_int = 3;
+
+pub const BACON_SEM_CORRECTED: i32 = 0;
+pub const BACON_SEM_LITERAL: i32 = 1;
+pub const BACON_FLAG_STRICT_FP: u32 = 1;
+pub const BACON_FLAG_SHARED_PARAMS: u32 = 2;
+pub const BACON_FLAG_BDF_NEWTON: u32 = 4;
+pub const BACON_FLAG_PARAMS_AOS: u32 = 8;
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct bacon_ivp_config {
+    pub method: i32,
+    pub dim: i32,
+    pub n_params: i32,
+    pub semantics: i32,
+    pub flags: u32,
+    pub history_capacity: i32,
+    pub dt_min: c_double,
+    pub dt_max: c_double,
+    pub tol: c_double,
+    pub t_start: c_double,
+    pub t_end: c_double,
+    pub max_attempts: u64,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct bacon_ivp_result {
+    pub y_end: *mut c_double,
+    pub t_end: *mut c_double,
+    pub dt_end: *mut c_double,
+    pub status: *mut i32,
+    pub n_accept: *mut u32,
+    pub n_reject: *mut u32,
+    pub n_rhs: *mut u32,
+    pub hist_t: *mut c_double,
+    pub hist_y: *mut c_double,
+    pub hist_len: *mut u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct bacon_ivp_launch_info {
+    pub kernel_ms: f32,
+    pub h2d_ms: f32,
+    pub d2h_ms: f32,
+    pub grid: i32,
+    pub block: i32,
+    pub regs_per_thread: i32,
+    pub n_kernels: i32,
+}
+
+#[repr(C)]
+pub struct bacon_solver {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn bacon_abi_version() -> c_int;
+    pub fn bacon_solver_new(method: c_int, dim: c_int) -> *mut bacon_solver;
+    pub fn bacon_solver_free(s: *mut bacon_solver);
+    pub fn bacon_solver_with_tolerance(s: *mut bacon_solver, tol: c_double) -> c_int;
+    pub fn bacon_solver_with_maximum_dt(s: *mut bacon_solver, max: c_double) -> c_int;
+    pub fn bacon_solver_with_minimum_dt(s: *mut bacon_solver, min: c_double) -> c_int;
+    pub fn bacon_solver_with_initial_time(s: *mut bacon_solver, t: c_double) -> c_int;
+    pub fn bacon_solver_with_ending_time(s: *mut bacon_solver, t: c_double) -> c_int;
+    pub fn bacon_solver_with_semantics(s: *mut bacon_solver, semantics: c_int) -> c_int;
+    pub fn bacon_solver_with_flags(s: *mut bacon_solver, flags: u32) -> c_int;
+    pub fn bacon_solver_with_history(s: *mut bacon_solver, capacity: c_int) -> c_int;
+    pub fn bacon_solver_with_max_attempts(s: *mut bacon_solver, cap: u64) -> c_int;
+    pub fn bacon_solver_config(s: *const bacon_solver, out: *mut bacon_ivp_config) -> c_int;
+    pub fn bacon_ivp_validate(cfg: *const bacon_ivp_config) -> c_int;
+    pub fn bacon_rhs_lookup(name: *const c_char) -> c_int;
+    pub fn bacon_rhs_count() -> c_int;
+    pub fn bacon_rhs_info(id: c_int, name: *mut *const c_char, dim: *mut c_int, n_params: *mut c_int) -> c_int;
+    pub fn bacon_ivp_solve_ensemble(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, y0: *const c_double,
+                                    params: *const c_double, out: *const bacon_ivp_result) -> c_int;
+    pub fn bacon_ivp_solve_ensemble_device(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, d_y0: *const c_double,
+                                           d_params: *const c_double, d_out: *const bacon_ivp_result,
+                                           stream: *mut c_void) -> c_int;
+    pub fn bacon_ivp_solve_ensemble_multi(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, y0: *const c_double,
+                                          params: *const c_double, out: *const bacon_ivp_result, n_gpus: c_int) -> c_int;
+    pub fn bacon_ivp_last_launch(out: *mut bacon_ivp_launch_info) -> c_int;
+    pub fn bacon_last_error() -> *const c_char;
+    pub fn bacon_status_name(status: c_int) -> *const c_char;
+    pub fn bacon_fp64_peak_tflops(iters: c_int, stream: *mut c_void) -> c_double;
+    pub fn bacon_device_sm_count() -> c_int;
+}

@@ -1,0 +1,183 @@
+//! `bacon_sci::ivp`'s solver front end (src/ivp.rs:134-190, src/ivp/rk.rs:118-343, src/ivp/bdf.rs:124-332 of
+//! aftix/bacon 0.16.2) over the B200 ensemble engine.  UNVERIFIED: no Rust toolchain in the build image; the C++ and
+//! Python mirrors of this file are the tested ones.
+//!
+//! ```ignore
+//! use bacon_ivp::{RK45, IVPSolver};
+//! let solver = RK45::new(1)?.with_dt_min(0.01)?.with_dt_max(0.1)?.with_tolerance(1e-4)?
+//!     .with_initial_conditions(&[1.0])?.with_start(0.0)?.with_end(10.0)?.build();
+//! let path = solver.solve_ivp("exp", &[])?;                       // README.md:32-40
+//! let ens = RK45::new(3)?.with_dt_min(1e-9)?.with_dt_max(0.1)?.with_tolerance(1e-8)?
+//!     .with_start(0.0)?.with_end(5.0)?.with_derivative("lorenz")?
+//!     .solve_ivp_ensemble(&y0 /* [3][n] */, &params /* [3][n] */, false)?;
+//! ```
+use bacon_ivp_sys as sys;
+use std::ffi::{CStr, CString};
+
+/// Mirror of `IVPError` (src/ivp.rs:50-76); discriminants are `bacon_status`.
+#[derive(thiserror::Error, Debug, Clone, Copy, PartialEq, Eq)]
+#[repr(i32)]
+pub enum IVPError {
+    #[error("the solver does not have all required parameters set")] MissingParameters = 1,
+    #[error("user error in the derivative")] UserError = 2,
+    #[error("the given tolerance was out of bounds")] ToleranceOOB = 3,
+    #[error("the given time delta was out of bounds")] TimeDeltaOOB = 4,
+    #[error("the given ending time was out of bounds")] TimeEndOOB = 5,
+    #[error("the given starting time was out of bounds")] TimeStartOOB = 6,
+    #[error("a conversion from a necessary primitive failed")] FromPrimitiveFailure = 7,
+    #[error("the time step fell below the parameter minimum allowed value")] MinimumTimeDeltaExceeded = 8,
+    #[error("the number of iterations exceeded the maximum allowable")] MaximumIterationsExceeded = 9,
+    #[error("a matrix was unable to be inverted")] SingularMatrix = 10,
+    #[error("attempted to build a dynamic solver with static dimension")] DynamicOnStatic = 11,
+    #[error("attempted to build a static solver with dynamic dimension")] StaticOnDynamic = 12,
+    #[error("non-finite error estimate")] NonFinite = 13,
+    #[error("attempt cap reached")] MaxAttempts = 14,
+    #[error("more accepted points than the history capacity")] HistoryOverflow = 15,
+    #[error("CUDA error")] Cuda = 16,
+    #[error("bad argument")] BadArgument = 17,
+    #[error("combination not built")] Unsupported = 18,
+}
+
+fn check(rc: i32) -> Result<(), IVPError> {
+    if rc == 0 { Ok(()) } else if (1..=18).contains(&rc) { Err(unsafe { std::mem::transmute::<i32, IVPError>(rc) }) } else { Err(IVPError::Cuda) }
+}
+
+pub fn last_error() -> String {
+    unsafe { CStr::from_ptr(sys::bacon_last_error()).to_string_lossy().into_owned() }
+}
+
+/// One trajectory's accepted points (src/ivp.rs:203).
+pub type Path = Vec<(f64, Vec<f64>)>;
+
+pub struct EnsembleResult {
+    pub n: usize,
+    pub dim: usize,
+    pub y_end: Vec<f64>,   // [dim][n]
+    pub t_end: Vec<f64>,
+    pub dt_end: Vec<f64>,
+    pub status: Vec<i32>,
+    pub n_accept: Vec<u32>,
+    pub n_reject: Vec<u32>,
+    pub n_rhs: Vec<u32>,
+    pub hist_t: Vec<f64>,  // [n][cap]
+    pub hist_y: Vec<f64>,  // [n][cap][dim]
+    pub hist_len: Vec<u32>,
+    pub capacity: usize,
+}
+
+impl EnsembleResult {
+    pub fn path(&self, i: usize) -> Path {
+        (0..self.hist_len[i] as usize)
+            .map(|k| {
+                let row = (i * self.capacity + k) * self.dim;
+                (self.hist_t[i * self.capacity + k], self.hist_y[row..row + self.dim].to_vec())
+            })
+            .collect()
+    }
+}
+
+pub struct Solver<const METHOD: i32> {
+    h: *mut sys::bacon_solver,
+    dim: usize,
+    rhs: Option<i32>,
+    y0: Option<Vec<f64>>,
+}
+
+impl<const METHOD: i32> Drop for Solver<METHOD> {
+    fn drop(&mut self) { unsafe { sys::bacon_solver_free(self.h) } }
+}
+
+macro_rules! setter {
+    ($name:ident, $ffi:ident) => {
+        pub fn $name(self, v: f64) -> Result<Self, IVPError> { check(unsafe { sys::$ffi(self.h, v) })?; Ok(self) }
+    };
+}
+
+impl<const METHOD: i32> Solver<METHOD> {
+    /// `IVPSolver::new` / `new_dyn` (src/ivp.rs:159-163); the dimension is checked against the RHS at solve time.
+    pub fn new(dim: usize) -> Result<Self, IVPError> {
+        let h = unsafe { sys::bacon_solver_new(METHOD, dim as i32) };
+        if h.is_null() { return Err(IVPError::BadArgument); }
+        Ok(Self { h, dim, rhs: None, y0: None })
+    }
+    pub fn new_dyn(size: usize) -> Result<Self, IVPError> { Self::new(size) }
+    pub fn dim(&self) -> usize { self.dim }
+
+    setter!(with_tolerance, bacon_solver_with_tolerance);        // rk.rs:168
+    setter!(with_maximum_dt, bacon_solver_with_maximum_dt);      // rk.rs:179
+    setter!(with_minimum_dt, bacon_solver_with_minimum_dt);      // rk.rs:197
+    setter!(with_initial_time, bacon_solver_with_initial_time);  // rk.rs:212
+    setter!(with_ending_time, bacon_solver_with_ending_time);    // rk.rs:224
+    // README.md:33-38
+    setter!(with_dt_max, bacon_solver_with_maximum_dt);
+    setter!(with_dt_min, bacon_solver_with_minimum_dt);
+    setter!(with_start, bacon_solver_with_initial_time);
+    setter!(with_end, bacon_solver_with_ending_time);
+
+    pub fn with_initial_conditions_slice(mut self, start: &[f64]) -> Result<Self, IVPError> {   // ivp.rs:177
+        if start.len() != self.dim { return Err(IVPError::BadArgument); }
+        self.y0 = Some(start.to_vec());
+        Ok(self)
+    }
+    pub fn with_initial_conditions(self, start: &[f64]) -> Result<Self, IVPError> { self.with_initial_conditions_slice(start) }
+    /// `with_derivative` (ivp.rs:186): the RHS is a registered CUDA device functor, looked up by name.
+    pub fn with_derivative(mut self, rhs: &str) -> Result<Self, IVPError> {
+        let c = CString::new(rhs).map_err(|_| IVPError::BadArgument)?;
+        let id = unsafe { sys::bacon_rhs_lookup(c.as_ptr()) };
+        if id < 0 { return Err(IVPError::BadArgument); }
+        self.rhs = Some(id);
+        Ok(self)
+    }
+    pub fn with_history(self, cap: usize) -> Result<Self, IVPError> { check(unsafe { sys::bacon_solver_with_history(self.h, cap as i32) })?; Ok(self) }
+    pub fn with_flags(self, flags: u32) -> Result<Self, IVPError> { check(unsafe { sys::bacon_solver_with_flags(self.h, flags) })?; Ok(self) }
+    pub fn with_semantics(self, s: i32) -> Result<Self, IVPError> { check(unsafe { sys::bacon_solver_with_semantics(self.h, s) })?; Ok(self) }
+    pub fn build(self) -> Self { self }
+
+    /// N initial conditions x N parameter sets: y0 is [dim][n], params [n_params][n] (or [n_params] when shared).
+    pub fn solve_ivp_ensemble(&self, y0: &[f64], params: &[f64], shared_params: bool) -> Result<EnsembleResult, IVPError> {
+        let rhs = self.rhs.ok_or(IVPError::MissingParameters)?;
+        let mut cfg = sys::bacon_ivp_config::default();
+        check(unsafe { sys::bacon_solver_config(self.h, &mut cfg) })?;
+        let (mut d, mut np) = (0, 0);
+        check(unsafe { sys::bacon_rhs_info(rhs, std::ptr::null_mut(), &mut d, &mut np) })?;
+        cfg.n_params = np;
+        if shared_params { cfg.flags |= sys::BACON_FLAG_SHARED_PARAMS; }
+        if y0.len() % self.dim != 0 { return Err(IVPError::BadArgument); }
+        let n = y0.len() / self.dim;
+        let cap = cfg.history_capacity as usize;
+        let mut r = EnsembleResult {
+            n, dim: self.dim, capacity: cap,
+            y_end: vec![0.0; self.dim * n], t_end: vec![0.0; n], dt_end: vec![0.0; n], status: vec![-1; n],
+            n_accept: vec![0; n], n_reject: vec![0; n], n_rhs: vec![0; n],
+            hist_t: vec![0.0; n * cap], hist_y: vec![0.0; n * cap * self.dim], hist_len: vec![0; n],
+        };
+        let out = sys::bacon_ivp_result {
+            y_end: r.y_end.as_mut_ptr(), t_end: r.t_end.as_mut_ptr(), dt_end: r.dt_end.as_mut_ptr(),
+            status: r.status.as_mut_ptr(), n_accept: r.n_accept.as_mut_ptr(), n_reject: r.n_reject.as_mut_ptr(),
+            n_rhs: r.n_rhs.as_mut_ptr(),
+            hist_t: if cap > 0 { r.hist_t.as_mut_ptr() } else { std::ptr::null_mut() },
+            hist_y: if cap > 0 { r.hist_y.as_mut_ptr() } else { std::ptr::null_mut() },
+            hist_len: if cap > 0 { r.hist_len.as_mut_ptr() } else { std::ptr::null_mut() },
+        };
+        let pptr = if params.is_empty() { std::ptr::null() } else { params.as_ptr() };
+        check(unsafe { sys::bacon_ivp_solve_ensemble(&cfg, rhs, n, y0.as_ptr(), pptr, &out) })?;
+        Ok(r)
+    }
+
+    /// `solve(data)` + `collect_vec` (rk.rs:249-343, ivp.rs:209-211) for the trajectory set by with_initial_conditions.
+    pub fn solve(self, data: &[f64]) -> Result<Path, IVPError> {
+        let y0 = self.y0.clone().ok_or(IVPError::MissingParameters)?;
+        let s = self.with_history(1 << 16)?;
+        let r = s.solve_ivp_ensemble(&y0, data, false)?;
+        check(r.status[0])?;
+        Ok(r.path(0))
+    }
+    pub fn solve_ivp(self, rhs: &str, data: &[f64]) -> Result<Path, IVPError> { self.with_derivative(rhs)?.solve(data) }   // README.md:40
+}
+
+pub type RungeKutta45 = Solver<{ sys::BACON_RK45 }>;  // rk.rs:561
+pub type RungeKutta23 = Solver<{ sys::BACON_RK23 }>;  // rk.rs:656
+pub type BDF6 = Solver<{ sys::BACON_BDF6 }>;          // bdf.rs:706
+pub type BDF2 = Solver<{ sys::BACON_BDF2 }>;          // bdf.rs:762
+pub type RK45 = RungeKutta45;                         // README.md:24
+pub type RK23 = RungeKutta23;

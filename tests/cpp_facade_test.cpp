@@ -1,0 +1,43 @@
+// Exercises include/bacon_ivp.hpp.  `validate`: builder rules only (no GPU).  `solve`: README example on the GPU.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "bacon_ivp.hpp"
+
+#define EXPECT_THROW_CODE(expr, want)                                                \
+    do {                                                                             \
+        int got = 0;                                                                 \
+        try { expr; } catch (const bacon::IVPError& e) { got = e.code; }             \
+        if (got != (want)) { std::printf("FAIL %s: code %d, want %d\n", #expr, got, (want)); return 1; } \
+    } while (0)
+
+int main(int argc, char** argv) {
+    using namespace bacon;
+    const bool solve = argc > 1 && std::strcmp(argv[1], "solve") == 0;
+    EXPECT_THROW_CODE(RK45(1).with_tolerance(0.0), BACON_E_TOLERANCE_OOB);
+    EXPECT_THROW_CODE(RK45(1).with_dt_min(-1.0), BACON_E_TIME_DELTA_OOB);
+    EXPECT_THROW_CODE(BDF6(1).with_maximum_dt(0.0), BACON_E_TIME_DELTA_OOB);
+    EXPECT_THROW_CODE(RK23(1).with_end(1.0).with_start(2.0), BACON_E_TIME_START_OOB);
+    EXPECT_THROW_CODE(RK23(1).with_start(2.0).with_end(1.0), BACON_E_TIME_END_OOB);
+    EXPECT_THROW_CODE(RK45(1).with_dt_min(0.01).config(), BACON_E_MISSING_PARAMETERS);
+    EXPECT_THROW_CODE(RK45(1).with_derivative("nope"), BACON_E_BAD_ARGUMENT);
+    {
+        RK45 s(1);
+        s.with_minimum_dt(0.5).with_maximum_dt(0.1).with_tolerance(1e-3).with_start(0).with_end(1);
+        const bacon_ivp_config c = s.config();
+        if (c.dt_min != 0.1 || c.dt_max != 0.1) { std::printf("FAIL min/max ordering\n"); return 1; }
+    }
+    if (solve) {  // README.md:24-40
+        RK45 s(1);
+        s.with_dt_min(0.01).with_dt_max(0.1).with_tolerance(1e-4).with_initial_conditions({1.0}).with_start(0.0).with_end(10.0).build();
+        const Path path = s.solve_ivp("exp");
+        if (path.size() != 128) { std::printf("FAIL path size %zu\n", path.size()); return 1; }
+        for (const auto& pt : path)
+            if (std::fabs(pt.second[0] - std::exp(pt.first)) > 2e-2 * std::exp(pt.first)) { std::printf("FAIL accuracy\n"); return 1; }
+        if (path.back().first != 10.0) { std::printf("FAIL end time\n"); return 1; }
+        std::printf("solve ok: %zu points, y(10) = %.10g\n", path.size(), path.back().second[0]);
+    }
+    std::printf("ok\n");
+    return 0;
+}

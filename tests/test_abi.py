@@ -149,3 +149,30 @@ def test_no_cpu_fallback_in_product_package():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "liboracle" not in text and "from oracle" not in text and "import oracle" not in text, f
                 assert not re.search(r'#\s*include\s*[<"][^>"]*oracle', text), f
+
+
+def test_user_rhs_plugin_builds_and_registers(engine):
+    """North-star: user right-hand sides plug in through the same C ABI.  examples/user_rhs.cu is compiled
+    against include/bacon_ivp_rhs.cuh for sm_100a (nvcc cross-compiles here) and registers on load."""
+    import subprocess
+    from bacon_b200._lib import lib
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    L = lib()
+    C.CDLL(os.path.join(ROOT, "examples", "libuser_rhs.so"), mode=C.RTLD_GLOBAL)
+    for name, dim, npar in (("brusselator", 2, 2), ("pendulum", 2, 1)):
+        rid = L.bacon_rhs_lookup(name.encode())
+        assert rid >= 0
+        d, p = C.c_int(), C.c_int()
+        L.bacon_rhs_info(rid, None, C.byref(d), C.byref(p))
+        assert (d.value, p.value) == (dim, npar)
+
+
+def test_cpp_facade_validation():
+    """include/bacon_ivp.hpp (the compiled-language mirror of the reference builder): validation rules, no GPU."""
+    import subprocess
+    exe = "/tmp/bacon_cpp_facade_test"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp_facade_test.cpp"),
+                    "-o", exe, "-L" + os.path.join(ROOT, "bacon_b200"), "-lbacon_ivp", "-Wl,-rpath," + os.path.join(ROOT, "bacon_b200")],
+                   check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.strip().endswith("ok")

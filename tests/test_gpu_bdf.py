@@ -45,7 +45,8 @@ def test_reference_bdf_tests_on_gpu(cuda, engine, oracle, case):
         assert r.status[0] == _abi.OK
         m = int(r.hist_len[0])
         t, y = r.hist_t[0, :m], r.hist_y[0, :m, 0]
-        assert m > 0 and np.abs(y - exact(t)).max() <= eps and t[-1] == t_end
+        # the stepper reaches t_end exactly; the last YIELDED point may be earlier (warm-up block pending at Done)
+        assert m > 0 and np.abs(y - exact(t)).max() <= eps and abs(r.t_end[0] - t_end) <= 1e-12 * t_end
 
 
 def test_robertson_strict_bit_exact(cuda, engine, oracle):
