@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""bench_configs.py — the other BASELINE.json configs (parity-test cases, not the headline bench line):
+
+  3  Van der Pol mu-sweep, 2^22 trajectories, RK23 ("the second adaptive RK"), tol 1e-10
+  4  32-dim linear ODE y' = A y, 2^18 trajectories with per-trajectory A, RK45, dense output to HBM (capacity 256)
+  5  Robertson kinetics, 2^20 trajectories, BDF6 with the batched in-register 3x3 Newton LU (and Broyden), tol 1e-6
+
+  python bench_configs.py --config 3 [--scale 0.25] [--steps 3]
+
+One JSON line per run: accepted trajectory-steps/s (device-resident, CUDA events on the launch stream), algorithmic
+FLOP/s against the FP64 peak measured in the same run, dense-output GB/s against MEASURED_PEAKS.json's HBM figure,
+and the CPU oracle on a bounded sub-sample of the same seeded ensemble.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, required=True, choices=[3, 4, 5])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the config's trajectory count")
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--broyden", action="store_true", help="config 5 with the reference's Broyden iteration instead of Newton+LU")
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    import torch
+
+    import bacon_b200 as B
+    from bacon_b200 import _abi, ensembles as E
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    kw_dev = {}
+    if args.config == 3:
+        w = dict(E.VDP)
+        n = max(1024, int(w["n"] * args.scale))
+        idx = np.arange(n, dtype=np.int64)
+        y0, par = E.vdp_problem(idx * (w["n"] // n), w["n"])  # same mu range at any scale
+        make = B.RungeKutta23
+        flags, hist = 0, 0
+    elif args.config == 4:
+        w = dict(E.LINEAR32)
+        n = max(256, int(w["n"] * args.scale))
+        y0, par = E.linear32_problem(np.arange(n))
+        par = par.reshape(n, 1024)
+        make = B.RungeKutta45
+        flags, hist = 0, w["history_capacity"]
+        kw_dev["params_aos"] = True
+    else:
+        w = dict(E.ROBERTSON)
+        n = max(1024, int(w["n"] * args.scale))
+        y0, par = E.robertson_problem(np.arange(n))
+        make = B.BDF6
+        flags, hist = (0 if args.broyden else _abi.FLAG_BDF_NEWTON), 0
+    dim = w["dim"]
+    s = (make.new(dim).with_minimum_dt(w["dt_min"]).with_maximum_dt(w["dt_max"]).with_tolerance(w["tol"])
+         .with_initial_time(w["t_start"]).with_ending_time(w["t_end"]).with_derivative(w["rhs"]).with_flags(flags)
+         .with_history(hist))
+
+    d_y0 = torch.from_numpy(np.ascontiguousarray(y0)).to(dev)
+    d_par = torch.from_numpy(np.ascontiguousarray(par)).to(dev)
+    out = None
+    for _ in range(max(args.warmup, 1)):
+        out = s.solve_ivp_ensemble_device(d_y0, d_par, out=out, **kw_dev)
+    torch.cuda.synchronize()
+    peak = B.fp64_peak_tflops(1 << 15)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k)
+        ev[k][0].record()
+        out = s.solve_ivp_ensemble_device(d_y0, d_par, out=out, **kw_dev)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    st = out["status"].cpu().numpy()
+    acc = out["n_accept"].cpu().numpy().astype(np.int64)
+    rej = out["n_reject"].cpu().numpy().astype(np.int64)
+    nrhs = out["n_rhs"].cpu().numpy().astype(np.int64)
+    ok_status = (0, _abi.E_HISTORY_OVERFLOW) if hist else (0,)
+    n_bad = int((~np.isin(st, ok_status)).sum())
+    launch = B.last_launch()
+
+    line = {"config": args.config, "workload": f"{w['rhs']} x {n} trajectories, {w['method']}, tol {w['tol']}, "
+            f"t in [{w['t_start']},{w['t_end']}], dt in [{w['dt_min']},{w['dt_max']}]"
+            + (f", dense output capacity {hist}" if hist else "") + (", Newton+LU" if flags & _abi.FLAG_BDF_NEWTON else ""),
+            "metric": "accepted f64 trajectory-steps/sec", "value": float(acc.sum()) / (ms * 1e-3), "unit": "trajectory-steps/s",
+            "ms_per_pass": ms, "n": n, "accepted": int(acc.sum()), "rejected": int(rej.sum()), "n_rhs": int(nrhs.sum()),
+            "accept_min_max": [int(acc.min()), int(acc.max())], "failed": n_bad, "dtype": "f64", "data": "synthetic",
+            "grid": launch["grid"], "block": launch["block"], "regs_per_thread": launch["regs_per_thread"]}
+    if args.config in (3, 4):
+        fl = E.rk_flops(w["method"], dim, E.F_RHS[w["rhs"]], float((acc + rej).sum()), float(acc.sum()))
+    else:  # BDF: event-counted: RHS evaluations dominate; 15*D per g-evaluation on top
+        fl = float(nrhs.sum()) * (E.F_RHS["robertson"] + 15 * dim)
+    tf = fl / (ms * 1e-3) / 1e12
+    line["roofline"] = {"bound": "fp64", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                        "peak_source": "DFMA loop measured in this run"}
+    if hist:
+        pts = np.minimum(acc, hist).sum()
+        gb = float(pts) * 8 * (1 + dim) / 1e9
+        hp, src = hbm_peak()
+        line["dense_output"] = {"bytes_per_accepted_step": 8 * (1 + dim), "GB_written": gb, "achieved_GBs": gb / (ms * 1e-3),
+                                "peak_GBs": hp, "frac": gb / (ms * 1e-3) / hp, "peak_source": src}
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        cores = os.cpu_count() or 1
+        m = args.cpu_sample or {3: 16 * cores, 4: 64 * cores, 5: 16 * cores}[args.config]
+        m = min(m, n)
+        sel = np.linspace(0, n - 1, m).astype(np.int64)  # spread over the ensemble (the mu-sweep is ordered)
+        yy = np.ascontiguousarray(y0[:, sel])
+        pp = np.ascontiguousarray(par[sel]) if args.config == 4 else np.ascontiguousarray(par[:, sel])
+        t0 = time.perf_counter()
+        r = O.solve_ensemble({"RK23": _abi.RK23, "RK45": _abi.RK45, "BDF6": _abi.BDF6}[w["method"]], w["rhs"], yy, pp,
+                             params_aos=(args.config == 4), dt_min=w["dt_min"], dt_max=w["dt_max"], tol=w["tol"],
+                             t_start=w["t_start"], t_end=w["t_end"], bdf_newton=bool(flags & _abi.FLAG_BDF_NEWTON))
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": float(r["n_accept"].sum()) / dt, "unit": "trajectory-steps/s", "cores": cores,
+                                "kind": "port", "sample": f"{m} trajectories spread over the same seeded ensemble ({dt:.1f} s)"}
+        # parity of the sample, side by side
+        g = out["y_end"][:, torch.from_numpy(sel).to(dev)].cpu().numpy()
+        err = np.sqrt(((g - r["y_end"]) ** 2).sum(0)) / np.maximum(np.sqrt((r["y_end"] ** 2).sum(0)), 1e-300)
+        line["parity_sample"] = {"worst_rel_err": float(err.max()), "band": max(10 * w["tol"], 1e-12),
+                                 "accepted_gpu": int(acc[sel].sum()), "accepted_cpu": int(r["n_accept"].sum()),
+                                 "rejected_gpu": int(rej[sel].sum()), "rejected_cpu": int(r["n_reject"].sum())}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
