@@ -631,18 +631,20 @@ int bacon_device_sm_count(void) {
 }  // extern "C"
 
 // ---------------------------------------------------------------- FP64 peak probe
-// Register-resident DFMA chains: the denominator of the RK kernels' roofline
-// (MEASURED_PEAKS.json has HBM and bf16 only).  16 independent chains per thread,
-// 8 resident warps per SM sub-partition: the FP64 pipe is the only limiter.
+// Register-resident DFMA chains: the denominator of the RK kernels' roofline (MEASURED_PEAKS.json
+// has HBM and bf16 only).  16 independent chains per thread, 8 resident warps per SM sub-partition,
+// x = fma(x, a, x): two distinct register sources per DFMA, which is the form that reaches the pipe's
+// full rate (tools/fp64_peak.cu: 37.0 TFLOP/s = 99.5 % of 148 SM x 64 DFMA/clk x 1.965 GHz on this
+// pool's B200s; DFMAs with three distinct register sources top out near 34 TFLOP/s).
 namespace {
 constexpr int kPeakChains = 16;
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double a, double b) {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double a) {
     double x[kPeakChains];
 #pragma unroll
-    for (int k = 0; k < kPeakChains; ++k) x[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+    for (int k = 0; k < kPeakChains; ++k) x[k] = 1e-3 * (threadIdx.x + k + 1);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int k = 0; k < kPeakChains; ++k) x[k] = fma(x[k], a, b);
+        for (int k = 0; k < kPeakChains; ++k) x[k] = fma(x[k], a, x[k]);
     }
     double s = 0.0;
 #pragma unroll
@@ -663,11 +665,11 @@ extern "C" double bacon_fp64_peak_tflops(int iters, void* stream) {
     cudaEventCreate(&e1);
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = sm * 4, block = 256;
-    fp64_peak_kernel<<<grid, block, 0, st>>>(sink, 64, 0.999999, 1e-9);  // warm-up
+    fp64_peak_kernel<<<grid, block, 0, st>>>(sink, 64, -1e-9);  // warm-up
     double best = -1.0;
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0, st);
-        fp64_peak_kernel<<<grid, block, 0, st>>>(sink, iters, 0.999999, 1e-9);
+        fp64_peak_kernel<<<grid, block, 0, st>>>(sink, iters, -1e-9);
         cudaEventRecord(e1, st);
         if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
         float ms = 0.f;

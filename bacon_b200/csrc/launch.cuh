@@ -55,7 +55,10 @@ template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* 
 }
 
 // ---- fast (FMA, compile-time tableau), REF_CORRECTED only
-template <class Rhs, class Tab, int MINB = 4> int launch_rk_fast(bacon_launch_args* a) {
+#ifndef BACON_RK_MINB
+#define BACON_RK_MINB 4  // resident 128-thread CTAs per SM the fast RK kernels are compiled for (register budget)
+#endif
+template <class Rhs, class Tab, int MINB = BACON_RK_MINB> int launch_rk_fast(bacon_launch_args* a) {
     if (a->cfg.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;
     return launch_stepper<RkFastStepper<Rhs, Tab>, MINB>(a);
 }

@@ -4,41 +4,68 @@
 //
 // What is kept from the reference, statement by statement:
 //   * Done when t >= end (rk.rs:362-364); last step clamped: t+dt >= end -> dt = end-t (:366-368)
-//   * O stage evaluations per attempt, no FSAL (:370-384)
-//   * error = || sum_j e_j k_j ||_2 / dt, absolute, Euclidean (:386-390)
+//   * O stage evaluations per attempt, no FSAL; k_j = f_j * dt stored per stage (:370-384)
+//   * stage argument y + sum_j a_ij k_j (:371-374), error = || sum_j e_j k_j ||_2 / dt (:386-390)
 //   * accept iff error <= tol; then t += dt, y += sum_j b_j k_j (:392-398)
 //   * dt *= clamp(safety*(tol/error)^(1/4), 0.1, 4) on EVERY attempt (:400-408), dt = min(dt, dt_max) (:410-412)
 //   * dt < dt_min && t < end -> MinimumTimeDeltaExceeded, before the point is yielded (:414-416)
 //   * dt0 = (dt_max + dt_min)/2 (rk.rs:315)
-// What is re-expressed for the FP64 pipe (results agree with the oracle to rounding,
-// inside the parity band max(10*tol, 1e-12); the strict kernel is the bit-exact one):
-//   * stages keep the unscaled derivative f_j (k_j = dt*f_j): Y_i = fma(dt, sum_j a_ij f_j, y),
-//     so error = ||sum_j e_j f_j|| needs neither the division by dt nor O*D multiplies by dt
-//   * accept test on the squared norm; (tol/error)^(1/4) = (error^2/tol^2)^(-1/8) from an SFU
-//     seed (MUFU sqrt, sqrt, rsqrt in fp32) + one Newton step in fp64 (|rel err| < 1e-12)
-//   * tableau coefficients are compile-time constants: zeros emit nothing, the rest are
-//     constant-bank operands of DFMA
+// How it is laid out for the FP64 pipe of sm_100a (measured with tools/fp64_peak.cu: a DFMA whose three
+// sources are three different registers issues at 2/3 rate, 24.7 vs 37.0 TFLOP/s; DMUL/DADD and DFMAs
+// with a uniform-register/constant operand run at full rate):
+//   * every tableau combination is a chain  acc = fma(coef, k_j, acc)  started FROM y (stage
+//     argument, solution update), so the coefficient is a uniform-register operand (values in
+//     __constant__ memory, loaded once outside the loop); structural zeros emit nothing
+//   * the accept test compares squared quantities on the integer pipe: ||E||^2 <= (tol*dt)^2
+//   * the step-size factor (tol/error)^(1/4) = ((tol*dt)^2/||E||^2)^(1/8) is evaluated on the SFU in the
+//     log domain: exponents by integer arithmetic, 2x MUFU.LG2 on the mantissas, 1x MUFU.EX2.
+//     Relative accuracy ~2e-7: below the ~1e-6 rounding noise of the embedded error estimate itself (a
+//     cancelling sum, sum_j e_j = 0), which already makes dt differ at that level between any two
+//     correct evaluations.  It only ever sets the NEXT step size; no FP64 division, sqrt or pow.
+// Results agree with the oracle inside the parity band max(10*tol, 1e-12); the strict kernels
+// (rk_strict.cuh) are the bit-exact form.
 #pragma once
 #include "ivp_common.cuh"
 #include "tableaux.cuh"
 
 namespace bacon {
 
-// x^(-1/8), x in [1e-6, 1e8]
+// a <= b / a < b for doubles that are >= +0 (or NaN, which orders above everything): integer pipe
+__device__ __forceinline__ bool pos_le(double a, double b) { return __double_as_longlong(a) <= __double_as_longlong(b); }
+__device__ __forceinline__ bool pos_lt(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
+
+// log2 of a non-negative double to fp32 accuracy without touching the FP64 pipe: exponent from the bit
+// pattern, MUFU.LG2 on the mantissa rebuilt as a float in [1, 2).  0 -> about -1023, inf -> +1024.
+__device__ __forceinline__ float log2_pos(double x) {
+    const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
+    const int e = (int)(hi >> 20) - 1023;
+    float m = __uint_as_float(0x3f800000u | ((hi & 0xfffffu) << 3) | (lo >> 29));
+    asm("lg2.approx.ftz.f32 %0, %0;" : "+f"(m));
+    return (float)e + m;
+}
+
+// clamp(safety * (num/den)^(1/8), 0.1, 4) as a double; num, den >= 0.  The clamp values are the exact
+// doubles the reference multiplies by (rk.rs:402-406).
+__device__ __forceinline__ double step_factor(double num, double den, float safety) {
+    float l = 0.125f * (log2_pos(num) - log2_pos(den));
+    asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(l));
+    const float d = safety * l;
+    const unsigned fb = __float_as_uint(d);  // float -> double on the integer pipe (only used when 0.1 < d < 4)
+    const double dd = __hiloint2double((int)((fb >> 3) + (896u << 20)), (int)(fb << 29));
+    return !(d > 0.1f) ? 0.1 : (d >= 4.0f ? 4.0 : dd);
+}
+
+// x^(-1/8), x in [1e-6, 1e8]: SFU seed + one Newton step in fp64 (used by the warp-per-trajectory kernel)
 __device__ __forceinline__ double inv_eighth_root(double x) {
     float s = (float)x;
     asm("sqrt.approx.ftz.f32 %0, %0;" : "+f"(s));
     asm("sqrt.approx.ftz.f32 %0, %0;" : "+f"(s));
     asm("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(s));
-    double z = (double)s;
+    const double z = (double)s;
     const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
     const double r = fma(-x, z8, 1.0);  // 1 - x z^8
     return fma(z * 0.125, r, z);        // Newton on z^-8 = x
 }
-
-// a <= b / a < b for doubles that are >= +0 (or NaN, which orders above everything): integer pipe
-__device__ __forceinline__ bool pos_le(double a, double b) { return __double_as_longlong(a) <= __double_as_longlong(b); }
-__device__ __forceinline__ bool pos_lt(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
 
 template <class Tab, int I> __host__ __device__ constexpr int first_nz_a() {
     for (int j = 0; j < I; ++j)
@@ -55,6 +82,12 @@ template <class Tab> __host__ __device__ constexpr int first_nz_e() {
         if (Tab::e(j) != 0.0) return j;
     return -1;
 }
+// is k_j used by a later stage, the error estimate or the solution update?
+template <class Tab> __host__ __device__ constexpr bool stage_used(int j) {
+    for (int i = j + 1; i < Tab::O; ++i)
+        if (Tab::a(i, j) != 0.0) return true;
+    return Tab::e(j) != 0.0 || Tab::b(j) != 0.0;
+}
 
 // Stepper concept used by ensemble_kernel (drive.cuh):
 //   D;  ctor(args);  reset(args, idx, live);  int attempt(bool& yielded)  (-1 = keep going, else a
@@ -65,7 +98,7 @@ template <class Rhs, class Tab> struct RkFastStepper {
     static constexpr int O = Tab::O;
 
     // ensemble-wide constants (registers / uniform registers)
-    double t_start, t_end, dt_min, dt_max, tol2, inv_tol2, dt0;
+    double t_start, t_end, dt_min, dt_max, tol, dt0;
     uint32_t cap;
     // one trajectory
     double y[D], p[P > 0 ? P : 1];
@@ -78,8 +111,7 @@ template <class Rhs, class Tab> struct RkFastStepper {
         t_end = a.cfg.t_end;
         dt_min = a.cfg.dt_min;
         dt_max = a.cfg.dt_max;
-        tol2 = a.cfg.tol * a.cfg.tol;
-        inv_tol2 = 1.0 / tol2;
+        tol = a.cfg.tol;
         dt0 = (dt_max + dt_min) * 0.5;  // rk.rs:315
         cap = (a.cfg.max_attempts == 0 || a.cfg.max_attempts > 0xFFFFFFFEull) ? 0xFFFFFFFEu
                                                                                : (uint32_t)a.cfg.max_attempts;
@@ -112,64 +144,60 @@ template <class Rhs, class Tab> struct RkFastStepper {
         clamped = t + h >= t_end;
         if (clamped) h = t_end - t;  // rk.rs:366-368
 
-        double f[O][D];
-        rhs(t, y, p, f[0]);
-        static_for<1, O>([&](auto I) {
+        // stages: k_i = h * f(t + c_i h, y + sum_j a_ij k_j)   (rk.rs:370-384)
+        double k[O][D];
+        static_for<0, O>([&](auto I) {
             constexpr int i = decltype(I)::value;
-            constexpr int j0 = first_nz_a<Tab, i>();
-            double Y[D];
+            double Y[D], fi[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                double s = Tab::av(i, j0) * f[j0][d];
-                static_for<j0 + 1, i>([&](auto J) {
+                double s = y[d];
+                static_for<0, i>([&](auto J) {
                     constexpr int j = decltype(J)::value;
-                    if constexpr (Tab::a(i, j) != 0.0) s = fma(Tab::av(i, j), f[j][d], s);
+                    if constexpr (Tab::a(i, j) != 0.0) s = fma(Tab::av(i, j), k[j][d], s);
                 });
-                Y[d] = fma(h, s, y[d]);
+                Y[d] = s;
             }
-            rhs(fma(Tab::cv(i), h, t), Y, p, f[i]);
+            if constexpr (i == 0) rhs(t, Y, p, fi);
+            else rhs(fma(Tab::cv(i), h, t), Y, p, fi);
+#pragma unroll
+            for (int d = 0; d < D; ++d) k[i][d] = stage_used<Tab>(i) ? h * fi[d] : 0.0;
         });
 
-        // embedded error, squared: q = || sum_j e_j f_j ||^2   ( = (||sum_j e_j k_j|| / dt)^2 )
+        // embedded error, squared: q = || sum_j e_j k_j ||^2   (rk.rs:386-390 is sqrt(q)/h)
         double q = 0.0;
         constexpr int e0 = first_nz_e<Tab>();
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            double s = Tab::ev(e0) * f[e0][d];
+            double s = Tab::ev(e0) * k[e0][d];
             static_for<e0 + 1, O>([&](auto J) {
                 constexpr int j = decltype(J)::value;
-                if constexpr (Tab::e(j) != 0.0) s = fma(Tab::ev(j), f[j][d], s);
+                if constexpr (Tab::e(j) != 0.0) s = fma(Tab::ev(j), k[j][d], s);
             });
             q = (d == 0) ? s * s : fma(s, s, q);
         }
+        const double th = tol * h;
+        const double th2 = th * th;
 
         n_att++;
-        // Comparisons of non-negative doubles are done on their bit patterns (integer pipe): the FP64
-        // pipe is the bound of this kernel and a DSETP costs it as much as a DFMA.  A NaN q has a bit
-        // pattern above every finite value, so it is "not accepted" and is diagnosed on that rare path.
-        const bool accepted = pos_le(q, tol2);  // rk.rs:392
+        // error <= tol  <=>  q <= (tol h)^2.  A NaN q has a bit pattern above every finite value, so it is
+        // "not accepted" and is diagnosed on that (rare) path.
+        const bool accepted = pos_le(q, th2);               // rk.rs:392
         if (!accepted && q != q) return BACON_E_NONFINITE;  // the reference would Redo forever (D8)
         if (accepted) {
             t += h;
-            constexpr int b0 = first_nz_b<Tab>();
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                double s = Tab::bv(b0) * f[b0][d];
-                static_for<b0 + 1, O>([&](auto J) {
+                double s = y[d];
+                static_for<0, O>([&](auto J) {
                     constexpr int j = decltype(J)::value;
-                    if constexpr (Tab::b(j) != 0.0) s = fma(Tab::bv(j), f[j][d], s);
+                    if constexpr (Tab::b(j) != 0.0) s = fma(Tab::bv(j), k[j][d], s);
                 });
-                y[d] = fma(h, s, y[d]);
+                y[d] = s;
             }
         }
-        // rk.rs:400-412; outside [1e-6, 1e8] the clamp of delta to [0.1, 4] decides anyway
-        double x = q * inv_tol2;
-        x = pos_lt(x, 1e-6) ? 1e-6 : x;
-        x = pos_lt(1e8, x) ? 1e8 : x;
-        double delta = Tab::safety * inv_eighth_root(x);
-        delta = pos_lt(delta, 0.1) ? 0.1 : delta;
-        delta = pos_lt(4.0, delta) ? 4.0 : delta;
-        dt = h * delta;
+        // rk.rs:400-412: (tol/error)^(1/4) = (th2/q)^(1/8)
+        dt = h * step_factor(th2, q, (float)Tab::safety);
         dt = pos_lt(dt_max, dt) ? dt_max : dt;
         if (pos_lt(dt, dt_min)) {
             if (t < t_end) {  // rk.rs:414-416 (fails before the point is yielded)

@@ -260,7 +260,8 @@ def ours(args):
                 "(bacon_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
                 "nominal_peak": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
                 "flops_per_accepted_step": 230, "flops_per_attempt": 205,
-                "kernel": "ensemble_kernel<RkFastStepper<RhsLorenz,TabRKF45>>", "kernel_ms_per_launch": ker_ms / args.steps}
+                "kernel": "ensemble_kernel<RkFastStepper<RhsLorenz,TabRKF45>>", "kernel_ms_per_launch": ker_ms / args.steps,
+                "kernel_ms_each_rank0": [round(a.elapsed_time(b), 3) for a, b in kev]}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """bench_configs.py — the other BASELINE.json configs (parity-test cases, not the headline bench line):
 
+  2  (dense-output variant of the headline) Lorenz-63 RK45, 2^18 trajectories, EVERY accepted point to HBM
   3  Van der Pol mu-sweep, 2^22 trajectories, RK23 ("the second adaptive RK"), tol 1e-10
   4  32-dim linear ODE y' = A y, 2^18 trajectories with per-trajectory A, RK45, dense output to HBM (capacity 256)
   5  Robertson kinetics, 2^20 trajectories, BDF6 with the batched in-register 3x3 Newton LU (and Broyden), tol 1e-6
@@ -32,7 +33,7 @@ def hbm_peak():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, required=True, choices=[3, 4, 5])
+    ap.add_argument("--config", type=int, required=True, choices=[2, 3, 4, 5])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the config's trajectory count")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
@@ -49,7 +50,14 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     kw_dev = {}
-    if args.config == 3:
+    if args.config == 2:
+        w = dict(E.LORENZ, n=1 << 18)
+        n = max(1024, int(w["n"] * args.scale))
+        y0 = E.lorenz_y0(np.arange(n))
+        par = np.tile(np.array(w["params"])[:, None], (1, n))
+        make = B.RungeKutta45
+        flags, hist = 0, 4608
+    elif args.config == 3:
         w = dict(E.VDP)
         n = max(1024, int(w["n"] * args.scale))
         idx = np.arange(n, dtype=np.int64)
@@ -106,7 +114,7 @@ def main():
             "ms_per_pass": ms, "n": n, "accepted": int(acc.sum()), "rejected": int(rej.sum()), "n_rhs": int(nrhs.sum()),
             "accept_min_max": [int(acc.min()), int(acc.max())], "failed": n_bad, "dtype": "f64", "data": "synthetic",
             "grid": launch["grid"], "block": launch["block"], "regs_per_thread": launch["regs_per_thread"]}
-    if args.config in (3, 4):
+    if args.config in (2, 3, 4):
         fl = E.rk_flops(w["method"], dim, E.F_RHS[w["rhs"]], float((acc + rej).sum()), float(acc.sum()))
     else:  # BDF: event-counted: RHS evaluations dominate; 15*D per g-evaluation on top
         fl = float(nrhs.sum()) * (E.F_RHS["robertson"] + 15 * dim)
@@ -123,7 +131,7 @@ def main():
         from oracle import oracle as O
         O.build()
         cores = os.cpu_count() or 1
-        m = args.cpu_sample or {3: 16 * cores, 4: 64 * cores, 5: 16 * cores}[args.config]
+        m = args.cpu_sample or {2: 8192 * cores, 3: 1024 * cores, 4: 4096 * cores, 5: 8192 * cores}[args.config]  # ~10 s of CPU work
         m = min(m, n)
         sel = np.linspace(0, n - 1, m).astype(np.int64)  # spread over the ensemble (the mu-sweep is ordered)
         yy = np.ascontiguousarray(y0[:, sel])
