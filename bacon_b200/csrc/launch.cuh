@@ -76,8 +76,10 @@ template <class Rhs, class Tab, int MINB = 1> int launch_rk_strict(bacon_launch_
 template <class Rhs, class Coef, bool STRICT, int MINB = 2> int launch_bdf(bacon_launch_args* a) {
     if (a->cfg.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;  // REF_LITERAL BDF: CPU oracle only
     if (a->cfg.flags & BACON_FLAG_BDF_NEWTON) {
-        if (STRICT) return BACON_E_UNSUPPORTED;  // the strict build is the reference's own (Broyden) iteration
-        return launch_stepper<BdfStepper<Rhs, Coef, false, true>, MINB>(a);
+        // the strict build is the reference's own (Broyden) iteration.  `if constexpr`: a strict translation
+        // unit (-fmad=false) must not instantiate a kernel that a fast one also defines under the same name.
+        if constexpr (STRICT) return BACON_E_UNSUPPORTED;
+        else return launch_stepper<BdfStepper<Rhs, Coef, false, true>, MINB>(a);
     }
     return launch_stepper<BdfStepper<Rhs, Coef, STRICT, false>, MINB>(a);
 }
@@ -96,8 +98,16 @@ template <class Rhs> int register_rhs(const char* name) {
     constexpr int S = 0;
 #endif
 #ifndef BACON_SKIP_RK
-    d.launch[S][BACON_RK45] = S ? &launch_rk_strict<Rhs, TabRKF45> : &launch_rk_fast<Rhs, TabRKF45>;
-    d.launch[S][BACON_RK23] = S ? &launch_rk_strict<Rhs, TabBS23> : &launch_rk_fast<Rhs, TabBS23>;
+    // `if constexpr`, not `?:` — a conditional expression would instantiate BOTH launchers in BOTH builds, and the
+    // two objects would then carry same-named kernels compiled with different -fmad settings (one of which the
+    // runtime picks arbitrarily).  Each kernel must exist in exactly one object: tests/test_abi.py checks it.
+    if constexpr (S) {
+        d.launch[S][BACON_RK45] = &launch_rk_strict<Rhs, TabRKF45>;
+        d.launch[S][BACON_RK23] = &launch_rk_strict<Rhs, TabBS23>;
+    } else {
+        d.launch[S][BACON_RK45] = &launch_rk_fast<Rhs, TabRKF45>;
+        d.launch[S][BACON_RK23] = &launch_rk_fast<Rhs, TabBS23>;
+    }
 #endif
 #ifndef BACON_SKIP_BDF
     d.launch[S][BACON_BDF6] = &launch_bdf<Rhs, CoefBDF6, S != 0>;

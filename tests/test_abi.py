@@ -176,3 +176,20 @@ def test_cpp_facade_validation():
                    check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert out.strip().endswith("ok")
+
+
+def test_every_kernel_exists_in_exactly_one_object(engine):
+    """The library links a fast (FMA) and a strict (-fmad=false) build of the same headers.  A kernel name that
+    appears in both objects would be launched from whichever copy the runtime registered last (found once: the
+    headline kernel ran without FMA contraction in its right-hand side)."""
+    import shutil
+    import subprocess
+    from bacon_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-symbols", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    entries = [l.split()[-1] for l in out.splitlines() if "STT_FUNC" in l and "STO_ENTRY" in l]
+    assert len(entries) > 100
+    dup = sorted({e for e in entries if entries.count(e) > 1})
+    assert not dup, dup[:4]
