@@ -38,7 +38,7 @@ STATUS_NAMES = {
 }
 
 SEM_CORRECTED, SEM_LITERAL = 0, 1
-FLAG_STRICT_FP, FLAG_SHARED_PARAMS, FLAG_BDF_NEWTON, FLAG_PARAMS_AOS = 1, 2, 4, 8
+FLAG_STRICT_FP, FLAG_SHARED_PARAMS, FLAG_BDF_NEWTON, FLAG_PARAMS_AOS, FLAG_ZERO_COPY = 1, 2, 4, 8, 16
 
 
 class Config(C.Structure):
@@ -79,5 +79,5 @@ EXPORTED_SYMBOLS = [
     "bacon_ivp_validate", "bacon_rhs_register", "bacon_rhs_lookup", "bacon_rhs_count",
     "bacon_rhs_info", "bacon_ivp_solve_ensemble", "bacon_ivp_solve_ensemble_device",
     "bacon_ivp_solve_ensemble_multi", "bacon_ivp_last_launch", "bacon_last_error",
-    "bacon_status_name", "bacon_fp64_peak_tflops", "bacon_device_sm_count",
+    "bacon_status_name", "bacon_fp64_peak_tflops", "bacon_device_sm_count", "bacon_host_alloc", "bacon_host_free",
 ]

@@ -56,6 +56,8 @@ def lib():
         "bacon_status_name": (C.c_char_p, [i32]),
         "bacon_fp64_peak_tflops": (dbl, [i32, vp]),
         "bacon_device_sm_count": (i32, []),
+        "bacon_host_alloc": (vp, [sz]),
+        "bacon_host_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

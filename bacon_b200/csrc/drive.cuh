@@ -32,14 +32,16 @@ __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB) ensemble_kernel(const __
     bool live = idx < n;
     s.reset(a, idx, live);
 
-    while (__any_sync(FULL_MASK, live)) {
+    if (!__any_sync(FULL_MASK, live)) return;
+    for (;;) {
         int st = -1;
         bool yielded = false;
         const uint32_t n_acc_before = s.n_acc;
         if (live) st = s.attempt(yielded);
         hist.push(yielded, n_acc_before, idx, s.out_t(), s.out_y());
 
-        const bool fin = live && st >= 0;
+        // one vote per attempt: st >= 0 only on live lanes whose trajectory retired in this attempt
+        const bool fin = st >= 0;
         if (__any_sync(FULL_MASK, fin)) {
             hist.retire(fin, idx, s.n_acc);
             if (fin) {
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB) ensemble_kernel(const __
                 hist.begin();
                 s.reset(a, idx, live);
             }
+            if (!__any_sync(FULL_MASK, live)) return;  // the warp can only run dry right after a retirement
         }
     }
 }

@@ -13,8 +13,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/bacon_ivp.h"
@@ -108,6 +110,29 @@ int ensure_host_buf(DeviceCtx& c, size_t bytes) {
     CUDA_TRY(cudaMallocHost(&c.h_buf, bytes));
     c.h_cap = bytes;
     return 0;
+}
+
+// ---------------------------------------------------------------- pinned host blocks (bacon_host_alloc)
+struct PinnedPool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;   // size -> block, reused by exact (rounded) size
+    std::unordered_map<void*, size_t> live;     // blocks handed out
+    size_t cached = 0;
+    static constexpr size_t kMaxCached = (size_t)2 << 30;
+};
+PinnedPool& pinned_pool() {
+    static PinnedPool* p = new PinnedPool();
+    return *p;
+}
+
+// host pointer -> is it page-locked, and what does the device call it?
+bool pinned_device_pointer(const void* host, void** dev) {
+    if (!host) { *dev = nullptr; return true; }
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    *dev = at.devicePointer;
+    return true;
 }
 
 // thread-local timing events of the device entry point (one pair per device)
@@ -473,6 +498,59 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
     std::vector<Shard> shards(G);
     std::lock_guard<std::mutex> lk_all(g_ctx_mu);  // host-buffer solves are serialised per process
 
+    // Zero-copy: per-trajectory I/O is a few dozen bytes against thousands of register-only steps, so with
+    // page-locked caller buffers the persistent kernel can read its initial conditions and post its
+    // retirement records over the host link itself; nothing is staged and nothing is left to copy at the end.
+    // (Not for large per-trajectory parameter blocks: those are streamed once by DMA instead.)
+    const size_t in_doubles = (size_t)D + (shared ? 0 : (size_t)P);
+    if (G == 1 && cap == 0 && in_doubles <= 32 && (cfg->flags & BACON_FLAG_ZERO_COPY)) {
+        void *zy0 = nullptr, *zp = nullptr;
+        bacon_ivp_result z{};
+        bool ok = pinned_device_pointer(y0, &zy0) && pinned_device_pointer(P > 0 ? params : nullptr, &zp);
+        void* t = nullptr;
+#define ZC(field, type)                                    \
+    ok = ok && pinned_device_pointer(out->field, &t);      \
+    z.field = (type*)t
+        ZC(y_end, double);
+        ZC(t_end, double);
+        ZC(dt_end, double);
+        ZC(status, int32_t);
+        ZC(n_accept, uint32_t);
+        ZC(n_reject, uint32_t);
+        ZC(n_rhs, uint32_t);
+#undef ZC
+        if (ok) {
+            DeviceCtx* ctx = nullptr;
+            rc = get_ctx(dev0, &ctx);
+            if (rc != 0) return rc;
+            cudaStream_t st = ctx->stream;
+            bacon_launch_args a{};
+            a.cfg = *cfg;
+            a.n = n;
+            a.y0 = (const double*)zy0;
+            a.params = (const double*)zp;
+            a.out = z;
+            a.stream = st;
+            a.sm_count = ctx->sm_count;
+            a.work_counter = ctx->counters + ctx->next_counter;
+            ctx->next_counter = (ctx->next_counter + 1) % kCounterSlots;
+            CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+            CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+            rc = fn(&a);
+            if (rc != 0) return fail(rc, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+            g_last_launch.kernel_ms = ms;
+            g_last_launch.grid = a.grid;
+            g_last_launch.block = a.block;
+            g_last_launch.regs_per_thread = a.regs_per_thread;
+            g_last_launch.n_kernels = a.n_kernels;
+            return 0;
+        }
+    }
+
     for (int g = 0; g < G; ++g) {
         Shard& s = shards[g];
         s.dev = (G == 1) ? dev0 : g;
@@ -530,6 +608,10 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
             a.work_counter = s.ctx->counters + s.ctx->next_counter;
             s.ctx->next_counter = (s.ctx->next_counter + 1) % kCounterSlots;
             CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+            if (cap) {  // slots beyond hist_len read as zero on the host (the staging buffer is reused between calls)
+                CUDA_TRY(cudaMemsetAsync(s.dl.out.hist_t, 0, sizeof(double) * s.n * cap, st));
+                CUDA_TRY(cudaMemsetAsync(s.dl.out.hist_y, 0, sizeof(double) * s.n * cap * D, st));
+            }
             CUDA_TRY(cudaEventRecord(s.ctx->ev[1], st));
             rc = fn(&a);
             if (rc != 0) return fail(rc, "kernel launch failed on device %d: %s", s.dev, cudaGetErrorString(cudaGetLastError()));
@@ -602,6 +684,52 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
     g_last_launch.regs_per_thread = shards[0].filled.regs_per_thread;
     g_last_launch.n_kernels = G * shards[0].filled.n_kernels;
     return 0;
+}
+
+void* bacon_host_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    const size_t want = align_up(bytes, (size_t)1 << 16);
+    PinnedPool& P = pinned_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.free_blocks.find(want);
+    void* p = nullptr;
+    if (it != P.free_blocks.end()) {
+        p = it->second;
+        P.free_blocks.erase(it);
+        P.cached -= want;
+    } else {
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped);
+        if (e != cudaSuccess) {
+            // drop the cache and retry once
+            for (auto& kv : P.free_blocks) cudaFreeHost(kv.second);
+            P.free_blocks.clear();
+            P.cached = 0;
+            cudaGetLastError();
+            e = cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped);
+        }
+        if (e != cudaSuccess) {
+            fail(BACON_E_CUDA, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return nullptr;
+        }
+    }
+    P.live[p] = want;
+    return p;
+}
+
+void bacon_host_free(void* p) {
+    if (!p) return;
+    PinnedPool& P = pinned_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    auto it = P.live.find(p);
+    if (it == P.live.end()) return;  // not ours
+    const size_t sz = it->second;
+    P.live.erase(it);
+    if (P.cached + sz <= PinnedPool::kMaxCached) {
+        P.free_blocks.emplace(sz, p);
+        P.cached += sz;
+    } else {
+        cudaFreeHost(p);
+    }
 }
 
 int bacon_ivp_last_launch(bacon_ivp_launch_info* out) {

@@ -19,9 +19,15 @@
 //   * the accept test compares squared quantities on the integer pipe: ||E||^2 <= (tol*dt)^2
 //   * the step-size factor (tol/error)^(1/4) = ((tol*dt)^2/||E||^2)^(1/8) is evaluated on the SFU in the
 //     log domain: exponents by integer arithmetic, 2x MUFU.LG2 on the mantissas, 1x MUFU.EX2.
-//     Relative accuracy ~2e-7: below the ~1e-6 rounding noise of the embedded error estimate itself (a
+//     Relative accuracy ~3e-7: below the ~1e-6 rounding noise of the embedded error estimate itself (a
 //     cancelling sum, sum_j e_j = 0), which already makes dt differ at that level between any two
 //     correct evaluations.  It only ever sets the NEXT step size; no FP64 division, sqrt or pow.
+//   * the hot path holds no FP64 compare at all: "t + dt >= end" is tested as dt >= end - t on the bit
+//     patterns (the two differ only when the sum rounds onto `end`, where both forms take the same step
+//     h up to one ulp), and everything rare (last step, Done, reject, NaN, dt < dt_min, attempt cap) sits
+//     behind two branches.  Measured with tools/fp64_mix.cu: integer/ALU instructions issued next to a
+//     saturated FP64 pipe are not free (each costs about half a DFMA slot), so the loop is trimmed to
+//     what the reference's step needs.
 // Results agree with the oracle inside the parity band max(10*tol, 1e-12); the strict kernels
 // (rk_strict.cuh) are the bit-exact form.
 #pragma once
@@ -30,29 +36,27 @@
 
 namespace bacon {
 
-// a <= b / a < b for doubles that are >= +0 (or NaN, which orders above everything): integer pipe
+// a <= b / a < b for doubles that are >= +0 (or NaN, which orders above everything): integer pipe.
+// (A DSETP occupies the FP64 pipe for as long as a DFMA does.)
 __device__ __forceinline__ bool pos_le(double a, double b) { return __double_as_longlong(a) <= __double_as_longlong(b); }
 __device__ __forceinline__ bool pos_lt(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
 
-// log2 of a non-negative double to fp32 accuracy without touching the FP64 pipe: exponent from the bit
-// pattern, MUFU.LG2 on the mantissa rebuilt as a float in [1, 2).  0 -> about -1023, inf -> +1024.
-__device__ __forceinline__ float log2_pos(double x) {
-    const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
-    const int e = (int)(hi >> 20) - 1023;
-    float m = __uint_as_float(0x3f800000u | ((hi & 0xfffffu) << 3) | (lo >> 29));
-    asm("lg2.approx.ftz.f32 %0, %0;" : "+f"(m));
-    return (float)e + m;
-}
-
-// clamp(safety * (num/den)^(1/8), 0.1, 4) as a double; num, den >= 0.  The clamp values are the exact
-// doubles the reference multiplies by (rk.rs:402-406).
+// clamp(safety * (num/den)^(1/8), 0.1, 4) as a double; num, den >= 0.  SFU, log domain: the exponent
+// difference is integer arithmetic on the high words, the mantissas (top 20 bits rebuilt as floats in
+// [1, 2)) go through MUFU.LG2, the result through MUFU.EX2.  den = 0 -> 4, den = inf -> 0.1.
+// Relative accuracy ~3e-7 (the clamp bounds are the floats nearest 0.1 and 4).
 __device__ __forceinline__ double step_factor(double num, double den, float safety) {
-    float l = 0.125f * (log2_pos(num) - log2_pos(den));
+    const int hn = __double2hiint(num), hd = __double2hiint(den);
+    const int de = (hn >> 20) - (hd >> 20);
+    float mn = __uint_as_float(0x3f800000u | (((unsigned)hn << 3) & 0x007ffff8u));
+    float md = __uint_as_float(0x3f800000u | (((unsigned)hd << 3) & 0x007ffff8u));
+    asm("lg2.approx.ftz.f32 %0, %0;" : "+f"(mn));
+    asm("lg2.approx.ftz.f32 %0, %0;" : "+f"(md));
+    float l = 0.125f * ((float)de + (mn - md));
     asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(l));
-    const float d = safety * l;
-    const unsigned fb = __float_as_uint(d);  // float -> double on the integer pipe (only used when 0.1 < d < 4)
-    const double dd = __hiloint2double((int)((fb >> 3) + (896u << 20)), (int)(fb << 29));
-    return !(d > 0.1f) ? 0.1 : (d >= 4.0f ? 4.0 : dd);
+    const float d = fminf(fmaxf(safety * l, 0.1f), 4.0f);
+    const unsigned fb = __float_as_uint(d);  // float -> double on the integer pipe (d is a normal float)
+    return __hiloint2double((int)((fb >> 3) + (896u << 20)), (int)(fb << 29));
 }
 
 // x^(-1/8), x in [1e-6, 1e8]: SFU seed + one Newton step in fp64 (used by the warp-per-trajectory kernel)
@@ -103,8 +107,8 @@ template <class Rhs, class Tab> struct RkFastStepper {
     // one trajectory
     double y[D], p[P > 0 ? P : 1];
     double t, dt;
-    uint32_t n_acc, n_rej, n_att;
-    bool clamped;  // the previous attempt used dt = t_end - t
+    uint32_t n_acc, n_att;
+    uint32_t n_rej;  // valid once attempt() has returned a status (>= 0)
 
     __device__ __forceinline__ explicit RkFastStepper(const bacon_launch_args& a) {
         t_start = a.cfg.t_start;
@@ -118,13 +122,11 @@ template <class Rhs, class Tab> struct RkFastStepper {
         t = t_start;
         dt = dt0;
         n_acc = n_rej = n_att = 0;
-        clamped = false;
     }
     __device__ __forceinline__ void reset(const bacon_launch_args& a, unsigned long long idx, bool live) {
         t = t_start;
         dt = dt0;
         n_acc = n_rej = n_att = 0;
-        clamped = false;
         if (live) load_problem<D, P>(a, idx, y, p);
     }
     __device__ __forceinline__ uint32_t n_rhs() const { return n_att * (uint32_t)O; }
@@ -132,17 +134,22 @@ template <class Rhs, class Tab> struct RkFastStepper {
     __device__ __forceinline__ const double (&out_y() const)[D] { return y; }
     __device__ __forceinline__ const double (&end_y() const)[D] { return y; }
 
-    // one IVPStepper::step call (rk.rs:361-423)
+    // one IVPStepper::step call (rk.rs:361-423).  Exits (return >= 0) set n_rej = attempts that were
+    // rejected and reported as such; on the hot path it is implied by n_att - n_acc.
     __device__ __forceinline__ int attempt(bool& yielded) {
         const Rhs rhs{};
         yielded = false;
-        if (n_att >= cap) return BACON_E_MAX_ATTEMPTS;
-        // rk.rs:362-364.  t can only have reached t_end in an attempt whose step was clamped to land on it
-        // (otherwise t_new = t + dt < t_end was just tested), so the FP64 compare is skipped otherwise.
-        if (clamped && t >= t_end) return BACON_OK;
+        // rk.rs:362-368.  rem <= 0 (Done) and rem <= dt (clamp the last step) are ONE signed compare of bit
+        // patterns: dt > 0, and a negative or zero double is <= every positive one as a signed integer.
+        const double rem = t_end - t;
         double h = dt;
-        clamped = t + h >= t_end;
-        if (clamped) h = t_end - t;  // rk.rs:366-368
+        const bool last = __double_as_longlong(rem) <= __double_as_longlong(dt);
+        if (n_att >= cap || last) {
+            n_rej = n_att - n_acc;
+            if (n_att >= cap) return BACON_E_MAX_ATTEMPTS;
+            if (!(t < t_end)) return BACON_OK;  // rk.rs:362-364
+            if (t + dt >= t_end) h = rem;       // rk.rs:366-368, the reference's own test on this rare path
+        }
 
         // stages: k_i = h * f(t + c_i h, y + sum_j a_ij k_j)   (rk.rs:370-384)
         double k[O][D];
@@ -180,10 +187,13 @@ template <class Rhs, class Tab> struct RkFastStepper {
         const double th2 = th * th;
 
         n_att++;
-        // error <= tol  <=>  q <= (tol h)^2.  A NaN q has a bit pattern above every finite value, so it is
-        // "not accepted" and is diagnosed on that (rare) path.
-        const bool accepted = pos_le(q, th2);               // rk.rs:392
-        if (!accepted && q != q) return BACON_E_NONFINITE;  // the reference would Redo forever (D8)
+        // error <= tol  <=>  q <= (tol h)^2   (rk.rs:392).  A NaN q has a bit pattern above every finite
+        // value: it is "not accepted" and diagnosed on the reject path.
+        const bool accepted = pos_le(q, th2);
+        // rk.rs:400-412: (tol/error)^(1/4) = (th2/q)^(1/8)
+        double dtn = h * step_factor(th2, q, (float)Tab::safety);
+        dtn = pos_lt(dt_max, dtn) ? dt_max : dtn;
+        dt = dtn;
         if (accepted) {
             t += h;
 #pragma unroll
@@ -196,20 +206,19 @@ template <class Rhs, class Tab> struct RkFastStepper {
                 y[d] = s;
             }
         }
-        // rk.rs:400-412: (tol/error)^(1/4) = (th2/q)^(1/8)
-        dt = h * step_factor(th2, q, (float)Tab::safety);
-        dt = pos_lt(dt_max, dt) ? dt_max : dt;
-        if (pos_lt(dt, dt_min)) {
-            if (t < t_end) {  // rk.rs:414-416 (fails before the point is yielded)
-                if (!accepted) n_rej++;
+        if (!accepted || pos_lt(dtn, dt_min)) {  // rare
+            if (!accepted && q != q) {           // the reference would Redo forever (D8)
+                n_rej = n_att - n_acc - 1;
+                return BACON_E_NONFINITE;
+            }
+            if (pos_lt(dtn, dt_min) && t < t_end) {  // rk.rs:414-416: fails before the point is yielded
+                n_rej = n_att - n_acc - (accepted ? 1u : 0u);
                 return BACON_E_MIN_DT_EXCEEDED;
             }
         }
         if (accepted) {
             n_acc++;
             yielded = true;
-        } else {
-            n_rej++;
         }
         return -1;
     }

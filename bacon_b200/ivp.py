@@ -15,6 +15,7 @@ The right-hand side is a CUDA device functor registered in the library
 per-trajectory parameter block plays the role of the reference's `UserData`.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -34,6 +35,45 @@ class IVPError(Exception):
 def _check(rc):
     if rc != 0:
         raise IVPError(rc, last_error())
+
+
+class PinnedBlock:
+    """One page-locked host block from `bacon_host_alloc`, carved into numpy arrays.  The arrays keep the
+    block alive (ndarray.base -> ctypes view -> this object); it returns to the library's cache when the
+    last of them is dropped."""
+
+    def __init__(self, nbytes):
+        self.nbytes = max(int(nbytes), 1)
+        self.ptr = lib().bacon_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise IVPError(_abi.E_CUDA, last_error())
+        self._off = 0
+        self._fin = weakref.finalize(self, lib().bacon_host_free, self.ptr)
+
+    def take(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape)) if len(shape) else 1
+        nb = count * dtype.itemsize
+        off = (self._off + 255) // 256 * 256
+        if off + nb > self.nbytes:
+            raise IVPError(_abi.E_BAD_ARGUMENT, "pinned block too small")
+        self._off = off + nb
+        if nb == 0:
+            return np.zeros(shape, dtype=dtype)
+        view = (C.c_char * nb).from_address(self.ptr + off)
+        view._owner = self
+        return np.frombuffer(view, dtype=dtype).reshape(shape)
+
+    @staticmethod
+    def size_for(specs):
+        return sum((int(np.prod(sh)) * np.dtype(dt).itemsize + 255) // 256 * 256 + 256 for sh, dt in specs)
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """A numpy array in page-locked memory (uninitialised): inputs built here reach the GPU by async DMA."""
+    shape = tuple(np.atleast_1d(shape).tolist()) if not isinstance(shape, tuple) else shape
+    blk = PinnedBlock(PinnedBlock.size_for([(shape, dtype)]))
+    return blk.take(shape, dtype)
 
 
 class EnsembleResult:
@@ -201,10 +241,15 @@ class _Solver:
         return self.with_derivative(rhs_name).solve(data, **kw)
 
     # ---- the new entry point: N initial conditions x N parameter sets
-    def solve_ivp_ensemble(self, y0, params=None, *, n_gpus=1, shared_params=False, params_aos=False, rhs=None):
+    def solve_ivp_ensemble(self, y0, params=None, *, n_gpus=1, shared_params=False, params_aos=False, rhs=None,
+                           zero_copy=True):
         """y0: (dim, n) float64 host array; params: (n_params, n), or (n, ...) = one contiguous block
         per trajectory with params_aos=True, or (n_params,) with shared_params=True.
-        Host buffers in, host buffers out (H2D, kernel, D2H)."""
+        Host buffers in, host buffers out (H2D, kernel, D2H).  The result arrays live in page-locked memory
+        from the library (`bacon_host_alloc`), so the D2H leg is an asynchronous DMA; inputs made with
+        `pinned_empty` get the same treatment.  zero_copy (default; applies on 1 GPU, final state only, when
+        every buffer is pinned and the per-trajectory input is small): the kernel reads and writes the host
+        buffers itself, no staging copies; otherwise the staged path runs."""
         if rhs is not None:
             self.with_derivative(rhs)
         rid, dim, npar = self._rhs_info()
@@ -229,19 +274,27 @@ class _Solver:
             elif params.shape != (npar, n):
                 raise IVPError(_abi.E_BAD_ARGUMENT, f"params must have shape ({npar}, {n}), got {params.shape}")
             pptr = params.ctypes.data
+        if zero_copy:
+            flags |= _abi.FLAG_ZERO_COPY
         cfg = self._config(npar, flags)
         cap = cfg.history_capacity
-        arrays = {
-            "y_end": np.zeros((dim, n)), "t_end": np.zeros(n), "dt_end": np.zeros(n),
-            "status": np.full(n, -1, dtype=np.int32), "n_accept": np.zeros(n, dtype=np.uint32),
-            "n_reject": np.zeros(n, dtype=np.uint32), "n_rhs": np.zeros(n, dtype=np.uint32),
-        }
-        if cap > 0:
-            arrays["hist_t"] = np.zeros((n, cap))
-            arrays["hist_y"] = np.zeros((n, cap, dim))
-            arrays["hist_len"] = np.zeros(n, dtype=np.uint32)
-        res = _abi.Result(**{k: v.ctypes.data for k, v in arrays.items()})
         L = lib()
+        _check(L.bacon_ivp_validate(C.byref(cfg)))  # argument errors before anything touches the GPU
+        specs = {"y_end": ((dim, n), np.float64), "t_end": ((n,), np.float64), "dt_end": ((n,), np.float64),
+                 "status": ((n,), np.int32), "n_accept": ((n,), np.uint32), "n_reject": ((n,), np.uint32),
+                 "n_rhs": ((n,), np.uint32)}
+        if cap > 0:
+            specs.update({"hist_t": ((n, cap), np.float64), "hist_y": ((n, cap, dim), np.float64),
+                          "hist_len": ((n,), np.uint32)})
+        if n == 0:
+            arrays = {k: np.zeros(sh, dtype=dt) for k, (sh, dt) in specs.items()}
+        else:
+            block = PinnedBlock(PinnedBlock.size_for(specs.values()))
+            arrays = {k: block.take(sh, dt) for k, (sh, dt) in specs.items()}
+            arrays["status"].fill(-1)
+            if cap > 0:
+                arrays["hist_len"].fill(0)
+        res = _abi.Result(**{k: v.ctypes.data for k, v in arrays.items()})
         if n_gpus == 1:
             _check(L.bacon_ivp_solve_ensemble(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res)))
         else:

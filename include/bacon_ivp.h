@@ -70,6 +70,10 @@ typedef enum bacon_status {
 #define BACON_FLAG_SHARED_PARAMS 2u  /* params is [n_params], shared by all trajectories        */
 #define BACON_FLAG_BDF_NEWTON 4u     /* BDF: Newton + analytic-Jacobian LU instead of Broyden   */
 #define BACON_FLAG_PARAMS_AOS 8u     /* params is [n][n_params] (one contiguous block per trajectory) */
+#define BACON_FLAG_ZERO_COPY 16u     /* host entry point, 1 GPU, final state only, every buffer from
+                                        bacon_host_alloc: the kernel reads y0/params and writes the
+                                        per-trajectory records straight from/to pinned host memory
+                                        (no staging copy; ignored when a buffer is not pinned)          */
 
 /* One POD block = everything the reference builder collects before `solve`
  * (rk.rs:60-68 / bdf.rs:57-65), shared by the whole ensemble. */
@@ -182,6 +186,15 @@ int bacon_ivp_solve_ensemble_device(const bacon_ivp_config*, int rhs_id, size_t 
  * n_gpus visible devices of this process (one stream per device). */
 int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config*, int rhs_id, size_t n, const double* y0,
                                    const double* params, const bacon_ivp_result* out, int n_gpus);
+
+/* Page-locked host memory for the host entry points (cached by size inside the
+ * library; cudaHostAlloc is slow).  Buffers from here make the H2D/D2H legs of
+ * bacon_ivp_solve_ensemble asynchronous DMA transfers; pageable buffers work
+ * too but are copied through the driver's bounce buffer.  The reference's
+ * counterpart is the `Vec` that `collect_vec` returns (ivp.rs:209-211): the
+ * caller owns the result storage. */
+void* bacon_host_alloc(size_t bytes); /* NULL on failure (see bacon_last_error) */
+void bacon_host_free(void* p);        /* NULL is a no-op                         */
 
 int bacon_ivp_last_launch(bacon_ivp_launch_info* out);
 const char* bacon_last_error(void); /* thread-local message for the last rc != 0 */

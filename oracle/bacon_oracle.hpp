@@ -684,6 +684,255 @@ template <int D, int O, class Rhs> struct BDFSolver {
 };
 
 // ------------------------------------------------------------------------
+// Adams predictor-corrector coefficients (adams.rs:635-650 Adams5, :695-712 Adams3)
+//   predictor: Adams-Bashforth weights, newest derivative first, padded with a zero
+//   corrector: Adams-Moulton weights, implicit derivative first
+//   error_coefficient: 19/270 for BOTH (adams.rs:652-654, :714-716)
+// ------------------------------------------------------------------------
+template <int O> struct AdamsCoefficients { double predictor[O]; double corrector[O]; double error; };
+
+inline AdamsCoefficients<5> coefficients_adams5() {
+    AdamsCoefficients<5> c{};
+    const double tf = 24.0, s = 720.0;
+    const double p[5] = {55.0 / tf, -59.0 / tf, 37.0 / tf, -9.0 / tf, 0.0};
+    const double q[5] = {251.0 / s, 646.0 / s, -264.0 / s, 106.0 / s, -19.0 / s};
+    for (int i = 0; i < 5; ++i) { c.predictor[i] = p[i]; c.corrector[i] = q[i]; }
+    c.error = 19.0 / 270.0;
+    return c;
+}
+inline AdamsCoefficients<3> coefficients_adams3() {
+    AdamsCoefficients<3> c{};
+    const double p[3] = {1.0 + 1.0 / 2.0, -(1.0 / 2.0), 0.0};            // adams.rs:697-703
+    const double q[3] = {5.0 / 12.0, 2.0 / 3.0, -(1.0 / 12.0)};          // adams.rs:705-711
+    for (int i = 0; i < 3; ++i) { c.predictor[i] = p[i]; c.corrector[i] = q[i]; }
+    c.error = 19.0 / 270.0;
+    return c;
+}
+
+// ------------------------------------------------------------------------
+// AdamsSolver (adams.rs:72-122 fields, :340-394 RK4 start-up, :398-566 step).
+// No defect of the D1-D9 kind on this path: Literal == Corrected.
+// ------------------------------------------------------------------------
+template <int D, int O, class Rhs> struct AdamsSolver {
+    double dt_max, dt_min, time, end, tolerance;
+    double dt;
+    Vec<D> state;
+    AdamsCoefficients<O> coef;
+    std::deque<std::pair<double, Vec<D>>> prev_values;
+    std::deque<Vec<D>> prev_derivatives;
+    Vec<D> implicit_derivs{}, save_state{};
+    double one_tenth, one_sixth, half, two, four, order;
+    size_t yield_memory = 0;
+    Rhs rhs;
+    const double* params;
+    PowMode pow_mode;  // q = (tol / (2 error))^(1/order): libm pow, as f64::powf (adams.rs:527, :553)
+    Counters cnt;
+    int fail_code = 0;
+    double out_t = 0.0;
+    Vec<D> out_y{};
+
+    // Adams::solve (adams.rs:249-337)
+    AdamsSolver(const AdamsCoefficients<O>& C, Rhs f, const double* p, const double* y0, double t0, double t1,
+                double dtmin, double dtmax, double tol)
+        : dt_max(dtmax), dt_min(dtmin), time(t0), end(t1), tolerance(tol), coef(C), rhs(f), params(p),
+          pow_mode(PowMode::LibmPow) {
+        two = 2.0;
+        half = 1.0 / two;        // :259
+        one_sixth = 1.0 / 6.0;   // :260-262
+        one_tenth = 1.0 / 10.0;  // :263-265
+        four = two * two;        // :266
+        order = static_cast<double>(O);  // :288
+        dt = (dtmax + dtmin) * half;     // :297
+        for (int d = 0; d < D; ++d) state[d] = y0[d];
+    }
+
+    bool f(double t, const double* y, double* dy) {
+        cnt.n_rhs++;
+        return rhs(t, y, params, dy);
+    }
+
+    // adams.rs:340-394: like bdf.rs:346-387, and additionally stores f(t, y) of every stored point
+    bool runge_kutta(int iterations) {
+        for (int i = 0; i < iterations; ++i) {
+            Vec<D> k1, k2, k3, k4, inter;
+            double dy[D];
+            if (!f(time, state.data(), dy)) return false;
+            for (int d = 0; d < D; ++d) k1[d] = dy[d] * dt;
+            for (int d = 0; d < D; ++d) inter[d] = state[d] + k1[d] * half;
+            if (!f(time + half * dt, inter.data(), dy)) return false;
+            for (int d = 0; d < D; ++d) k2[d] = dy[d] * dt;
+            for (int d = 0; d < D; ++d) inter[d] = state[d] + k2[d] * half;
+            if (!f(time + half * dt, inter.data(), dy)) return false;
+            for (int d = 0; d < D; ++d) k3[d] = dy[d] * dt;
+            for (int d = 0; d < D; ++d) inter[d] = state[d] + k3[d];
+            if (!f(time + dt, inter.data(), dy)) return false;
+            for (int d = 0; d < D; ++d) k4[d] = dy[d] * dt;
+            if (i != 0) {  // :372-380
+                Vec<D> der;
+                if (!f(time, state.data(), der.data())) return false;
+                prev_derivatives.push_back(der);
+                prev_values.push_back({time, state});
+            }
+            for (int d = 0; d < D; ++d)  // :382
+                state[d] += (((k1[d] + k2[d] * two) + k3[d] * two) + k4[d]) * one_sixth;
+            time += dt;  // :383
+        }
+        Vec<D> der;  // :385-391
+        if (!f(time, state.data(), der.data())) return false;
+        prev_derivatives.push_back(der);
+        prev_values.push_back({time, state});
+        return true;
+    }
+
+    // adams.rs:410-566
+    StepKind step() {
+        cnt.n_steps++;
+        if (yield_memory > 0 && yield_memory < (size_t)O) {  // :415-427
+            const size_t get_item = O - yield_memory - 1;
+            yield_memory -= 1;
+            if (yield_memory == 0) yield_memory = O + 1;
+            out_t = prev_values[get_item].first;
+            out_y = prev_values[get_item].second;
+            cnt.n_accept++;
+            return StepKind::Ok;
+        }
+        if (yield_memory == (size_t)O + 1) {  // :434-440
+            yield_memory = 0;
+            prev_values.push_back({time, state});
+            prev_values.pop_front();
+            out_t = time; out_y = state;
+            cnt.n_accept++;
+            return StepKind::Ok;
+        }
+        if (time >= end) return StepKind::Done;  // :442-444
+
+        if (time + dt >= end) {  // :446-450
+            dt = end - time;
+            if (!runge_kutta(1)) { fail_code = ST_USER; return StepKind::Failure; }
+            out_t = time; out_y = prev_values.back().second;
+            cnt.n_accept++;
+            return StepKind::Ok;
+        }
+
+        if (prev_values.empty()) {  // :452-463
+            save_state = state;
+            if (time + dt * (order - 1.0) >= end) dt = (end - time) / (order - 1.0);
+            if (!runge_kutta(O - 1)) { fail_code = ST_USER; return StepKind::Failure; }
+            yield_memory = O;
+            return StepKind::Redo;
+        }
+
+        // predictor (Adams-Bashforth) :465-470
+        Vec<D> sp, predictor, corrector;
+        for (int d = 0; d < D; ++d) sp[d] = prev_derivatives[0][d] * coef.predictor[O - 2];
+        for (int i = 1; i < O - 1; ++i) {
+            const double c = coef.predictor[O - i - 2];
+            for (int d = 0; d < D; ++d) sp[d] += prev_derivatives[i][d] * c;
+        }
+        for (int d = 0; d < D; ++d) predictor[d] = state[d] + sp[d] * dt;
+
+        // corrector (Adams-Moulton) :472-483
+        if (!f(time + dt, predictor.data(), implicit_derivs.data())) { fail_code = ST_USER; return StepKind::Failure; }
+        for (int d = 0; d < D; ++d) sp[d] = implicit_derivs[d] * coef.corrector[0];
+        for (int i = 0; i < O - 1; ++i) {
+            const double c = coef.corrector[O - i - 1];
+            for (int d = 0; d < D; ++d) sp[d] += prev_derivatives[i][d] * c;
+        }
+        for (int d = 0; d < D; ++d) corrector[d] = state[d] + sp[d] * dt;
+
+        Vec<D> difference;
+        for (int d = 0; d < D; ++d) difference[d] = corrector[d] - predictor[d];  // :485
+        const double error = coef.error / dt * norm2<D>(difference);             // :486
+
+        if (std::isnan(error)) {  // same hazard as D8: neither branch below can make progress
+            fail_code = ST_NONFINITE;
+            return StepKind::Failure;
+        }
+
+        if (error <= tolerance) {  // :488
+            state = corrector;
+            time += dt;
+            if (yield_memory == (size_t)O) {  // :498-501
+                yield_memory -= 1;
+                return StepKind::Redo;
+            }
+            prev_derivatives.push_back(implicit_derivs);  // :503-509
+            prev_values.push_back({time, state});
+            prev_values.pop_front();
+            prev_derivatives.pop_front();
+
+            if (error < one_tenth * tolerance) {  // :511-529
+                const double q = std::pow(tolerance / (two * error), 1.0 / order);
+                if (q > four) dt *= four;
+                else dt *= q;
+                if (dt > dt_max) dt = dt_max;
+                prev_values.clear();
+                prev_derivatives.clear();
+            }
+            out_t = time; out_y = state;
+            cnt.n_accept++;
+            return StepKind::Ok;  // :531
+        }
+
+        cnt.n_reject++;
+        if (yield_memory == (size_t)O) {  // :538-542
+            time -= dt * (order - 1.0);
+            state = save_state;
+        }
+        const double q = std::pow(tolerance / (two * error), 1.0 / order);  // :544-545
+        if (q < one_tenth) dt *= one_tenth;  // :547-551
+        else dt *= q;
+        if (dt < dt_min) {  // :553-555
+            fail_code = ST_MIN_DT;
+            return StepKind::Failure;
+        }
+        prev_values.clear();  // :557-558
+        prev_derivatives.clear();
+        return StepKind::Redo;
+    }
+};
+
+// ------------------------------------------------------------------------
+// EulerSolver (ivp.rs:306-344): fixed step, yields the OLD (time, state) of every step —
+// the initial condition is the first point and the final state is never yielded.
+// Builder (ivp.rs:386-471): with_tolerance is a no-op (:390-392); each of with_maximum_dt /
+// with_minimum_dt sets dt, or averages with the dt already set (:396-421).
+// ------------------------------------------------------------------------
+template <int D, class Rhs> struct EulerSolver {
+    double dt, time, end;
+    Vec<D> state;
+    Rhs rhs;
+    const double* params;
+    Counters cnt;
+    int fail_code = 0;
+    double out_t = 0.0;
+    Vec<D> out_y{};
+
+    EulerSolver(Rhs f, const double* p, const double* y0, double t0, double t1, double step)
+        : dt(step), time(t0), end(t1), rhs(f), params(p) {
+        for (int d = 0; d < D; ++d) state[d] = y0[d];
+    }
+
+    StepKind step() {
+        cnt.n_steps++;
+        if (time >= end) return StepKind::Done;       // ivp.rs:321-323
+        if (time + dt >= end) dt = end - time;        // :324-326
+        double dy[D];
+        cnt.n_rhs++;
+        if (!rhs(time, state.data(), params, dy)) {   // :328-329
+            fail_code = ST_USER;
+            return StepKind::Failure;
+        }
+        out_t = time;                                  // :331-332
+        out_y = state;
+        for (int d = 0; d < D; ++d) state[d] += dy[d] * dt;  // :334
+        time += dt;                                    // :335
+        cnt.n_accept++;
+        return StepKind::Ok;                           // :337
+    }
+};
+
+// ------------------------------------------------------------------------
 // IVPIterator drive loop (ivp.rs:220-238) + collect_vec (ivp.rs:209-211)
 // ------------------------------------------------------------------------
 template <int D> struct Solution {
@@ -740,6 +989,33 @@ inline Solution<D> solve_bdf(const BdfCoefficients<O>& C, Rhs rhs, const double*
     s.newton = newton;
     Solution<D> sol;
     drive<D>(s, max_attempts, keep_path, sol, [&](BDFSolver<D, O, Rhs>& st) {
+        sol.path_t.push_back(st.out_t);
+        sol.path_y.push_back(st.out_y);
+    });
+    return sol;
+}
+
+template <int D, int O, class Rhs>
+inline Solution<D> solve_adams(const AdamsCoefficients<O>& C, Rhs rhs, const double* params, const double* y0,
+                               double t0, double t1, double dtmin, double dtmax, double tol,
+                               uint64_t max_attempts, bool keep_path) {
+    AdamsSolver<D, O, Rhs> s(C, rhs, params, y0, t0, t1, dtmin, dtmax, tol);
+    Solution<D> sol;
+    drive<D>(s, max_attempts, keep_path, sol, [&](AdamsSolver<D, O, Rhs>& st) {
+        sol.path_t.push_back(st.out_t);
+        sol.path_y.push_back(st.out_y);
+    });
+    return sol;
+}
+
+// Euler: `dt` is what the builder arrives at (ivp.rs:396-421); the C API passes (dt_max + dt_min)/2 when both
+// were given, or the one that was.
+template <int D, class Rhs>
+inline Solution<D> solve_euler(Rhs rhs, const double* params, const double* y0, double t0, double t1, double dt,
+                               uint64_t max_attempts, bool keep_path) {
+    EulerSolver<D, Rhs> s(rhs, params, y0, t0, t1, dt);
+    Solution<D> sol;
+    drive<D>(s, max_attempts, keep_path, sol, [&](EulerSolver<D, Rhs>& st) {
         sol.path_t.push_back(st.out_t);
         sol.path_y.push_back(st.out_y);
     });

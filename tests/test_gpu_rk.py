@@ -274,3 +274,31 @@ def test_linear32_fast_within_band_and_matrix_exponential(cuda, engine, oracle):
     gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "anchors.json")))["linear32_seeded4_T4"]
     gold = np.array(gold).T  # (32, 4)
     assert rel_err(gpu.y_end[:, :4], gold).max() <= 1e-6  # global error of RKF45 at tol 1e-8 over T=4
+
+
+def test_pinned_and_zero_copy_host_paths_agree(cuda, engine):
+    """bacon_host_alloc buffers: staged (async H2D / kernel / D2H) and zero-copy (the kernel reads and writes
+    the pinned host buffers itself) give the same bits as pageable numpy inputs; the result arrays are pinned."""
+    from bacon_b200.ivp import pinned_empty
+    n = 5000
+    y0 = E.lorenz_y0(np.arange(n))
+    s = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.6, **LOR)
+    a = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+    y0p = pinned_empty(y0.shape)
+    y0p[...] = y0
+    pp = pinned_empty(LOR_P.shape)
+    pp[...] = LOR_P
+    b = s.solve_ivp_ensemble(y0p, pp, shared_params=True)
+    c = s.solve_ivp_ensemble(y0p, pp, shared_params=True, zero_copy=True)
+    assert (a.status == _abi.OK).all()
+    for k in ("y_end", "t_end", "dt_end", "status", "n_accept", "n_reject", "n_rhs"):
+        np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)
+        np.testing.assert_array_equal(getattr(a, k), getattr(c, k), err_msg=k)
+    assert c.launch["h2d_ms"] == 0 and c.launch["d2h_ms"] == 0 and c.launch["kernel_ms"] > 0
+    # zero_copy with a pageable input silently takes the staged path
+    d = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True, zero_copy=True)
+    np.testing.assert_array_equal(a.y_end, d.y_end)
+    # arrays outlive the result object (they own their pinned block)
+    ye = c.y_end
+    del a, b, c, d
+    assert np.isfinite(ye).all()
