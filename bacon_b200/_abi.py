@@ -1,12 +1,13 @@
 """ctypes mirror of include/bacon_ivp.h (structs, enums).  No logic here."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # bacon_method  (rk.rs:561, rk.rs:656, bdf.rs:706, bdf.rs:762)
-RK45, RK23, BDF6, BDF2 = 0, 1, 2, 3
-N_METHODS = 4
-METHOD_NAMES = {RK45: "RK45", RK23: "RK23", BDF6: "BDF6", BDF2: "BDF2"}
+RK45, RK23, BDF6, BDF2, ADAMS5, ADAMS3, EULER = 0, 1, 2, 3, 4, 5, 6
+N_METHODS = 7
+METHOD_NAMES = {RK45: "RK45", RK23: "RK23", BDF6: "BDF6", BDF2: "BDF2", ADAMS5: "Adams5", ADAMS3: "Adams3",
+                EULER: "Euler"}
 
 # bacon_status  (1..12 = IVPError, src/ivp.rs:50-76)
 OK = 0

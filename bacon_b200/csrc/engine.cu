@@ -269,6 +269,8 @@ struct bacon_solver {
     uint32_t flags;
     int history;
     uint64_t max_attempts;
+    bool has_euler_dt;  // Euler keeps ONE dt: the first bound given, then averaged with later ones (ivp.rs:396-421)
+    double euler_dt;
 };
 
 bacon_solver* bacon_solver_new(int method, int dim) {
@@ -290,6 +292,7 @@ void bacon_solver_free(bacon_solver* s) { delete s; }
 
 int bacon_solver_with_tolerance(bacon_solver* s, double tol) {
     if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
+    if (s->method == BACON_EULER) return 0;  // "Unused for Euler, call is a no-op" (ivp.rs:389-392)
     if (tol <= 0.0) return fail(BACON_E_TOLERANCE_OOB, "tolerance must be > 0");  // rk.rs:169-171
     s->tol = tol;
     s->has_tol = true;
@@ -298,6 +301,11 @@ int bacon_solver_with_tolerance(bacon_solver* s, double tol) {
 int bacon_solver_with_maximum_dt(bacon_solver* s, double max) {
     if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
     if (max <= 0.0) return fail(BACON_E_TIME_DELTA_OOB, "maximum dt must be > 0");  // rk.rs:180-182
+    if (s->method == BACON_EULER) {  // ivp.rs:396-406
+        s->euler_dt = s->has_euler_dt ? (s->euler_dt + max) / 2.0 : max;
+        s->has_euler_dt = true;
+        return 0;
+    }
     s->dt_max = max;
     s->has_max = true;
     if (s->has_min && s->dt_min > max) s->dt_min = max;  // rk.rs:185-189
@@ -306,6 +314,11 @@ int bacon_solver_with_maximum_dt(bacon_solver* s, double max) {
 int bacon_solver_with_minimum_dt(bacon_solver* s, double min) {
     if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
     if (min <= 0.0) return fail(BACON_E_TIME_DELTA_OOB, "minimum dt must be > 0");  // rk.rs:198-200
+    if (s->method == BACON_EULER) {  // ivp.rs:411-421
+        s->euler_dt = s->has_euler_dt ? (s->euler_dt + min) / 2.0 : min;
+        s->has_euler_dt = true;
+        return 0;
+    }
     s->dt_min = min;
     s->has_min = true;
     if (s->has_max && s->dt_max < min) s->dt_max = min;  // rk.rs:203-207
@@ -348,6 +361,22 @@ int bacon_solver_with_max_attempts(bacon_solver* s, uint64_t cap) {
 }
 int bacon_solver_config(const bacon_solver* s, bacon_ivp_config* out) {
     if (!s || !out) return fail(BACON_E_BAD_ARGUMENT, "NULL argument");
+    if (s->method == BACON_EULER) {  // ivp.rs:451-459: dt, initial time, ending time
+        if (!s->has_euler_dt || !s->has_t0 || !s->has_t1)
+            return fail(BACON_E_MISSING_PARAMETERS, "a time step (with_maximum_dt / with_minimum_dt), initial time and ending time are required");
+        std::memset(out, 0, sizeof(*out));
+        out->method = s->method;
+        out->dim = s->dim;
+        out->semantics = s->semantics;
+        out->flags = s->flags;
+        out->history_capacity = s->history;
+        out->dt_min = out->dt_max = s->euler_dt;
+        out->tol = 1.0;  // unused
+        out->t_start = s->t0;
+        out->t_end = s->t1;
+        out->max_attempts = s->max_attempts;
+        return 0;
+    }
     // rk.rs:250-254, in the reference's order
     if (!s->has_max || !s->has_min || !s->has_tol || !s->has_t0 || !s->has_t1)
         return fail(BACON_E_MISSING_PARAMETERS, "dt_max, dt_min, tolerance, initial time and ending time are all required");

@@ -9,6 +9,7 @@
 
 #include <cstdlib>
 
+#include "adams.cuh"
 #include "bdf.cuh"
 #include "drive.cuh"
 #include "rk_fast.cuh"
@@ -84,6 +85,15 @@ template <class Rhs, class Coef, bool STRICT, int MINB = 2> int launch_bdf(bacon
     return launch_stepper<BdfStepper<Rhs, Coef, STRICT, false>, MINB>(a);
 }
 
+// ---- Adams predictor-corrector and Euler.  No D1-D9 defect on these paths:
+// both semantics run the same kernel.
+template <class Rhs, class Coef, bool STRICT, int MINB = 2> int launch_adams(bacon_launch_args* a) {
+    return launch_stepper<AdamsStepper<Rhs, Coef, STRICT>, MINB>(a);
+}
+template <class Rhs, bool STRICT, int MINB = 4> int launch_euler(bacon_launch_args* a) {
+    return launch_stepper<EulerStepper<Rhs, STRICT>, MINB>(a);
+}
+
 // ---- registration: fills the launcher table of one RHS for THIS translation unit's build
 // flavour (fast, or strict when compiled with -DBACON_STRICT_FP -fmad=false) and hands it
 // to the engine through the C ABI (bacon_rhs_register merges the two flavours by name).
@@ -112,6 +122,9 @@ template <class Rhs> int register_rhs(const char* name) {
 #ifndef BACON_SKIP_BDF
     d.launch[S][BACON_BDF6] = &launch_bdf<Rhs, CoefBDF6, S != 0>;
     d.launch[S][BACON_BDF2] = &launch_bdf<Rhs, CoefBDF2, S != 0>;
+    d.launch[S][BACON_ADAMS5] = &launch_adams<Rhs, CoefAdams5, S != 0>;
+    d.launch[S][BACON_ADAMS3] = &launch_adams<Rhs, CoefAdams3, S != 0>;
+    d.launch[S][BACON_EULER] = &launch_euler<Rhs, S != 0>;
 #endif
     return bacon_rhs_register(&d);
 }

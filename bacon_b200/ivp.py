@@ -380,5 +380,62 @@ class BDF2(_Solver):
     METHOD = _abi.BDF2
 
 
+class Adams5(_Solver):
+    """Adams-Bashforth-Moulton predictor-corrector, order 5 (src/ivp/adams.rs:633)."""
+    METHOD = _abi.ADAMS5
+
+
+class Adams3(_Solver):
+    """Adams-Bashforth-Moulton predictor-corrector, order 3 (src/ivp/adams.rs:693)."""
+    METHOD = _abi.ADAMS3
+
+
+class Euler(_Solver):
+    """Explicit Euler, fixed step (src/ivp.rs:269-485).  `with_tolerance` is a no-op; each of
+    `with_maximum_dt` / `with_minimum_dt` sets the step, or averages it with the one already set
+    (ivp.rs:389-421).  The path starts with the initial condition and never holds the final state
+    (every step yields the OLD point, ivp.rs:331-337); `y_end` is the final state."""
+    METHOD = _abi.EULER
+
+
 RK45 = RungeKutta45  # README.md:24
 RK23 = RungeKutta23
+
+
+def solve_ivp(rhs, y0, params=None, *, t_span, dt_min, dt_max, tolerance, shared_params=False, params_aos=False,
+              n_gpus=1, chain=(Adams5, RungeKutta45, BDF6)):
+    """The README's free function `ivp::solve_ivp` (README.md:45-47: "tries a fifth-order predictor-corrector
+    followed by the Runge-Kutta-Fehlberg method followed by BDF6"), per trajectory of an ensemble: every
+    trajectory a solver failed on (status != Ok) is handed to the next solver of the chain, restarted from its
+    initial condition.  Returns the merged EnsembleResult with `.method` = index into `chain` of the solver
+    that produced each trajectory (the last one tried if all failed)."""
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    dim, n = y0.shape
+    todo = np.arange(n)
+    merged = None
+    method = np.zeros(n, dtype=np.int32)
+    for k, cls in enumerate(chain):
+        if todo.size == 0:
+            break
+        s = (cls.new(dim).with_minimum_dt(dt_min).with_maximum_dt(dt_max).with_tolerance(tolerance)
+             .with_initial_time(t_span[0]).with_ending_time(t_span[1]).with_derivative(rhs))
+        sub_p = params
+        if params is not None and not shared_params:
+            pa = np.asarray(params, dtype=np.float64)
+            sub_p = pa[todo] if params_aos else pa[:, todo]
+        res = s.solve_ivp_ensemble(np.ascontiguousarray(y0[:, todo]), sub_p, shared_params=shared_params,
+                                   params_aos=params_aos, n_gpus=n_gpus)
+        if merged is None:
+            merged = res
+        else:
+            merged.y_end[:, todo] = res.y_end
+            for name in ("t_end", "dt_end", "status", "n_accept", "n_reject", "n_rhs"):
+                getattr(merged, name)[todo] = getattr(res, name)
+        method[todo] = k
+        todo = todo[res.status != _abi.OK]
+    if merged is None:  # n == 0
+        merged = chain[0].new(dim).with_minimum_dt(dt_min).with_maximum_dt(dt_max).with_tolerance(tolerance) \
+            .with_initial_time(t_span[0]).with_ending_time(t_span[1]).with_derivative(rhs) \
+            .solve_ivp_ensemble(y0, params, shared_params=shared_params, params_aos=params_aos)
+    merged.method = method
+    return merged

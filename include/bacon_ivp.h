@@ -1,8 +1,9 @@
 /* bacon_ivp.h — C ABI of the B200 ensemble IVP engine (libbacon_ivp.so).
  *
  * This is the drop-in boundary for ONE path of aftix/bacon (bacon-sci 0.16.2):
- * the adaptive solvers of `bacon_sci::ivp` (RungeKutta45, RungeKutta23, BDF6),
- * batched over N independent trajectories.  The reference has no FFI of its
+ * the solvers of `bacon_sci::ivp` (RungeKutta45, RungeKutta23, BDF6/BDF2, and the
+ * callers either side of them: Adams5/Adams3, Euler), batched over N independent
+ * trajectories.  The reference has no FFI of its
  * own (it is pure safe Rust); every entry point below names the reference
  * interface it replaces (file:line relative to the reference tree).
  *
@@ -22,16 +23,20 @@
 extern "C" {
 #endif
 
-#define BACON_IVP_ABI_VERSION 1
+#define BACON_IVP_ABI_VERSION 2
 
 /* ---- solver families: src/ivp/rk.rs:561 (RungeKutta45), rk.rs:656
- * (RungeKutta23), src/ivp/bdf.rs:706 (BDF6), bdf.rs:762 (BDF2) ------------- */
+ * (RungeKutta23), src/ivp/bdf.rs:706 (BDF6), bdf.rs:762 (BDF2),
+ * src/ivp/adams.rs:633 (Adams5), adams.rs:693 (Adams3), src/ivp.rs:269 (Euler) */
 typedef enum bacon_method {
     BACON_RK45 = 0,
     BACON_RK23 = 1,
     BACON_BDF6 = 2,
     BACON_BDF2 = 3,
-    BACON_N_METHODS = 4
+    BACON_ADAMS5 = 4,
+    BACON_ADAMS3 = 5,
+    BACON_EULER = 6, /* fixed step: config.dt_max carries the builder's dt, tol/dt_min unused */
+    BACON_N_METHODS = 7
 } bacon_method;
 
 /* ---- status codes.  1..12 mirror `IVPError` variant by variant

@@ -159,6 +159,9 @@ using RungeKutta45 = Solver<BACON_RK45>;  // rk.rs:561
 using RungeKutta23 = Solver<BACON_RK23>;  // rk.rs:656
 using BDF6 = Solver<BACON_BDF6>;          // bdf.rs:706
 using BDF2 = Solver<BACON_BDF2>;          // bdf.rs:762
+using Adams5 = Solver<BACON_ADAMS5>;      // adams.rs:633
+using Adams3 = Solver<BACON_ADAMS3>;      // adams.rs:693
+using Euler = Solver<BACON_EULER>;        // ivp.rs:269 (with_tolerance is a no-op, dt = average of the bounds given)
 using RK45 = RungeKutta45;                // README.md:24
 using RK23 = RungeKutta23;
 

@@ -31,6 +31,7 @@
 #pragma once
 #include <array>
 #include <cmath>
+#include <cstring>
 #include <cstdint>
 #include <deque>
 #include <utility>
@@ -41,7 +42,28 @@ namespace bacon_oracle {
 enum class Mode : int { Corrected = 0, Literal = 1 };
 
 // how (tol/error)^(1/4) is evaluated (rk.rs:401 calls f64::powf -> libm pow).
+// For the Adams path (adams.rs:527, :553: powf(1/order)) mode 1 selects det_root below.
 enum class PowMode : int { LibmPow = 0, SqrtSqrt = 1 };
+
+// x^(1/N) from correctly rounded +, *, / and integer arithmetic on the bit pattern only: reproducible
+// bit for bit on the GPU (bacon_b200/csrc/adams.cuh det_root), unlike libm pow.  8 Newton steps from a
+// linear-in-the-exponent guess; agrees with pow(x, 1/N) to a few ulp (tests/test_oracle.py).
+template <int N> inline double det_root(double x) {
+    if (!(x > 0.0)) return x;
+    if (x > 1.7976931348623157e308) return x;
+    const long long one = 0x3ff0000000000000ll;
+    long long bits;
+    std::memcpy(&bits, &x, 8);
+    const long long gb = one + (bits - one) / N;
+    double z;
+    std::memcpy(&z, &gb, 8);
+    for (int it = 0; it < 8; ++it) {
+        double zn1 = z;
+        for (int k = 2; k < N; ++k) zn1 = zn1 * z;
+        z = ((double)(N - 1) * z + x / zn1) / (double)N;
+    }
+    return z;
+}
 
 // status codes shared with include/bacon_ivp.h (bacon_status)
 enum : int {
@@ -711,7 +733,7 @@ inline AdamsCoefficients<3> coefficients_adams3() {
 
 // ------------------------------------------------------------------------
 // AdamsSolver (adams.rs:72-122 fields, :340-394 RK4 start-up, :398-566 step).
-// No defect of the D1-D9 kind on this path: Literal == Corrected.
+// One defect on this path (D10, see step()): Literal = as written, Corrected = D10 repaired.
 // ------------------------------------------------------------------------
 template <int D, int O, class Rhs> struct AdamsSolver {
     double dt_max, dt_min, time, end, tolerance;
@@ -726,6 +748,7 @@ template <int D, int O, class Rhs> struct AdamsSolver {
     Rhs rhs;
     const double* params;
     PowMode pow_mode;  // q = (tol / (2 error))^(1/order): libm pow, as f64::powf (adams.rs:527, :553)
+    Mode mode = Mode::Corrected;
     Counters cnt;
     int fail_code = 0;
     double out_t = 0.0;
@@ -733,9 +756,9 @@ template <int D, int O, class Rhs> struct AdamsSolver {
 
     // Adams::solve (adams.rs:249-337)
     AdamsSolver(const AdamsCoefficients<O>& C, Rhs f, const double* p, const double* y0, double t0, double t1,
-                double dtmin, double dtmax, double tol)
+                double dtmin, double dtmax, double tol, PowMode pm)
         : dt_max(dtmax), dt_min(dtmin), time(t0), end(t1), tolerance(tol), coef(C), rhs(f), params(p),
-          pow_mode(PowMode::LibmPow) {
+          pow_mode(pm) {
         two = 2.0;
         half = 1.0 / two;        // :259
         one_sixth = 1.0 / 6.0;   // :260-262
@@ -749,6 +772,9 @@ template <int D, int O, class Rhs> struct AdamsSolver {
     bool f(double t, const double* y, double* dy) {
         cnt.n_rhs++;
         return rhs(t, y, params, dy);
+    }
+    double root(double x) const {  // x.powf(order.recip()) (adams.rs:526-527, :544-545)
+        return pow_mode == PowMode::LibmPow ? std::pow(x, 1.0 / order) : det_root<O>(x);
     }
 
     // adams.rs:340-394: like bdf.rs:346-387, and additionally stores f(t, y) of every stored point
@@ -854,6 +880,15 @@ template <int D, int O, class Rhs> struct AdamsSolver {
             time += dt;
             if (yield_memory == (size_t)O) {  // :498-501
                 yield_memory -= 1;
+                // D10 (found while restating; not in SURVEY.md's table): the early return skips the push below,
+                // although the sentinel branch (:429-440) assumes "the derivatives memory deque already has the
+                // derivatives for this step".  As written the step after every warm-up block therefore
+                // extrapolates with derivatives that lag one step behind: an O(dt) error estimate, a reject,
+                // a smaller dt and a new warm-up — the step count grows like 1/tol.  Corrected = push it.
+                if (mode == Mode::Corrected) {
+                    prev_derivatives.push_back(implicit_derivs);
+                    prev_derivatives.pop_front();
+                }
                 return StepKind::Redo;
             }
             prev_derivatives.push_back(implicit_derivs);  // :503-509
@@ -862,7 +897,7 @@ template <int D, int O, class Rhs> struct AdamsSolver {
             prev_derivatives.pop_front();
 
             if (error < one_tenth * tolerance) {  // :511-529
-                const double q = std::pow(tolerance / (two * error), 1.0 / order);
+                const double q = root(tolerance / (two * error));
                 if (q > four) dt *= four;
                 else dt *= q;
                 if (dt > dt_max) dt = dt_max;
@@ -879,7 +914,7 @@ template <int D, int O, class Rhs> struct AdamsSolver {
             time -= dt * (order - 1.0);
             state = save_state;
         }
-        const double q = std::pow(tolerance / (two * error), 1.0 / order);  // :544-545
+        const double q = root(tolerance / (two * error));  // :544-545
         if (q < one_tenth) dt *= one_tenth;  // :547-551
         else dt *= q;
         if (dt < dt_min) {  // :553-555
@@ -997,9 +1032,10 @@ inline Solution<D> solve_bdf(const BdfCoefficients<O>& C, Rhs rhs, const double*
 
 template <int D, int O, class Rhs>
 inline Solution<D> solve_adams(const AdamsCoefficients<O>& C, Rhs rhs, const double* params, const double* y0,
-                               double t0, double t1, double dtmin, double dtmax, double tol,
-                               uint64_t max_attempts, bool keep_path) {
-    AdamsSolver<D, O, Rhs> s(C, rhs, params, y0, t0, t1, dtmin, dtmax, tol);
+                               double t0, double t1, double dtmin, double dtmax, double tol, PowMode pm,
+                               Mode mode, uint64_t max_attempts, bool keep_path) {
+    AdamsSolver<D, O, Rhs> s(C, rhs, params, y0, t0, t1, dtmin, dtmax, tol, pm);
+    s.mode = mode;
     Solution<D> sol;
     drive<D>(s, max_attempts, keep_path, sol, [&](AdamsSolver<D, O, Rhs>& st) {
         sol.path_t.push_back(st.out_t);

@@ -53,6 +53,8 @@ def lib():
         L.oracle_roots_secant.restype = C.c_int
         L.oracle_fourth_root.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.oracle_fourth_root.restype = None
+        L.oracle_nth_root.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+        L.oracle_nth_root.restype = None
         L.oracle_max_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -132,4 +134,12 @@ def fourth_root(x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     a, b = np.empty_like(x), np.empty_like(x)
     lib().oracle_fourth_root(x.ctypes.data, x.size, a.ctypes.data, b.ctypes.data)
+    return a, b
+
+
+def nth_root(x, n):
+    """x^(1/n) by libm pow and by the deterministic Newton root of the strict Adams kernels (n = 3 or 5)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    a, b = np.empty_like(x), np.empty_like(x)
+    lib().oracle_nth_root(x.ctypes.data, x.size, int(n), a.ctypes.data, b.ctypes.data)
     return a, b

@@ -1,7 +1,7 @@
 // oracle_capi.cpp — C entry points of the CPU ORACLE (test infrastructure only).
 //
-// Wraps bacon_oracle.hpp (the restatement of src/ivp/rk.rs, src/ivp/bdf.rs and
-// src/ivp.rs:220-238) behind the same structs as include/bacon_ivp.h so tests can
+// Wraps bacon_oracle.hpp (the restatement of src/ivp/rk.rs, src/ivp/bdf.rs, src/ivp/adams.rs,
+// the Euler stepper src/ivp.rs:306-344 and the drive loop src/ivp.rs:220-238) behind the same structs as include/bacon_ivp.h so tests can
 // run the oracle and the CUDA path on identical buffers.  OpenMP over
 // trajectories = the "rayon over trajectories" CPU baseline of BASELINE.md
 // (kind "port": the Rust reference cannot be compiled in this image).
@@ -176,9 +176,20 @@ template <class Rhs> static void run_one(const RunArgs& a, size_t i) {
             s = bo::solve_bdf<D, 7>(bo::coefficients_bdf6(), Rhs{}, p.data(), y0, c.t_start, c.t_end,
                                     c.dt_min, c.dt_max, c.tol, mode, c.max_attempts, keep, newton);
             break;
-        default:
+        case BACON_BDF2:
             s = bo::solve_bdf<D, 3>(bo::coefficients_bdf2(), Rhs{}, p.data(), y0, c.t_start, c.t_end,
                                     c.dt_min, c.dt_max, c.tol, mode, c.max_attempts, keep, newton);
+            break;
+        case BACON_ADAMS5:
+            s = bo::solve_adams<D, 5>(bo::coefficients_adams5(), Rhs{}, p.data(), y0, c.t_start, c.t_end,
+                                      c.dt_min, c.dt_max, c.tol, a.pm, mode, c.max_attempts, keep);
+            break;
+        case BACON_ADAMS3:
+            s = bo::solve_adams<D, 3>(bo::coefficients_adams3(), Rhs{}, p.data(), y0, c.t_start, c.t_end,
+                                      c.dt_min, c.dt_max, c.tol, a.pm, mode, c.max_attempts, keep);
+            break;
+        default:  // BACON_EULER: config.dt_max carries the builder's dt
+            s = bo::solve_euler<D>(Rhs{}, p.data(), y0, c.t_start, c.t_end, c.dt_max, c.max_attempts, keep);
             break;
     }
     store<D>(a, i, s);
@@ -274,6 +285,14 @@ int oracle_roots_secant(int which, const double* start, double h, double tol, in
     }
     if (iterations) *iterations = it;
     return rc;
+}
+
+// x^(1/n) by libm pow and by the deterministic Newton root the strict Adams kernels share (n = 3 or 5).
+void oracle_nth_root(const double* x, size_t n_values, int n, double* by_pow, double* by_det) {
+    for (size_t i = 0; i < n_values; ++i) {
+        by_pow[i] = std::pow(x[i], 1.0 / (double)n);
+        by_det[i] = n == 3 ? bo::det_root<3>(x[i]) : bo::det_root<5>(x[i]);
+    }
 }
 
 // x^(1/4) both ways, for the pow-vs-sqrt(sqrt) agreement test.

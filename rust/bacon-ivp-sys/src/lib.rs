@@ -6,6 +6,9 @@ pub const BACON_RK45: c_int = 0;
 pub const BACON_RK23: c_int = 1;
 pub const BACON_BDF6: c_int = 2;
 pub const BACON_BDF2: c_int = 3;
+pub const BACON_ADAMS5: c_int = 4;
+pub const BACON_ADAMS3: c_int = 5;
+pub const BACON_EULER: c_int = 6;
 
 pub const BACON_SEM_CORRECTED: i32 = 0;
 pub const BACON_SEM_LITERAL: i32 = 1;
@@ -13,6 +16,7 @@ pub const BACON_FLAG_STRICT_FP: u32 = 1;
 pub const BACON_FLAG_SHARED_PARAMS: u32 = 2;
 pub const BACON_FLAG_BDF_NEWTON: u32 = 4;
 pub const BACON_FLAG_PARAMS_AOS: u32 = 8;
+pub const BACON_FLAG_ZERO_COPY: u32 = 16;
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
@@ -93,4 +97,6 @@ extern "C" {
     pub fn bacon_status_name(status: c_int) -> *const c_char;
     pub fn bacon_fp64_peak_tflops(iters: c_int, stream: *mut c_void) -> c_double;
     pub fn bacon_device_sm_count() -> c_int;
+    pub fn bacon_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn bacon_host_free(p: *mut c_void);
 }

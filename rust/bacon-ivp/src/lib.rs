@@ -179,5 +179,8 @@ pub type RungeKutta45 = Solver<{ sys::BACON_RK45 }>;  // rk.rs:561
 pub type RungeKutta23 = Solver<{ sys::BACON_RK23 }>;  // rk.rs:656
 pub type BDF6 = Solver<{ sys::BACON_BDF6 }>;          // bdf.rs:706
 pub type BDF2 = Solver<{ sys::BACON_BDF2 }>;          // bdf.rs:762
+pub type Adams5 = Solver<{ sys::BACON_ADAMS5 }>;      // adams.rs:633
+pub type Adams3 = Solver<{ sys::BACON_ADAMS3 }>;      // adams.rs:693
+pub type Euler = Solver<{ sys::BACON_EULER }>;        // ivp.rs:269
 pub type RK45 = RungeKutta45;                         // README.md:24
 pub type RK23 = RungeKutta23;

@@ -4,12 +4,14 @@ import numpy as np
 
 from bacon_b200 import _abi
 
-METHODS = {"RK45": _abi.RK45, "RK23": _abi.RK23, "BDF6": _abi.BDF6, "BDF2": _abi.BDF2}
+METHODS = {"RK45": _abi.RK45, "RK23": _abi.RK23, "BDF6": _abi.BDF6, "BDF2": _abi.BDF2, "Adams5": _abi.ADAMS5,
+           "Adams3": _abi.ADAMS3, "Euler": _abi.EULER}
 
 
 def make_solver(engine, method, dim, *, dt_min, dt_max, tol, t_start, t_end, rhs, semantics=0, flags=0,
                 history=0, max_attempts=0):
-    cls = {"RK45": engine.RungeKutta45, "RK23": engine.RungeKutta23, "BDF6": engine.BDF6, "BDF2": engine.BDF2}[method]
+    cls = {"RK45": engine.RungeKutta45, "RK23": engine.RungeKutta23, "BDF6": engine.BDF6, "BDF2": engine.BDF2,
+           "Adams5": engine.Adams5, "Adams3": engine.Adams3, "Euler": engine.Euler}[method]
     s = (cls.new(dim).with_minimum_dt(dt_min).with_maximum_dt(dt_max).with_tolerance(tol)
          .with_initial_time(t_start).with_ending_time(t_end).with_derivative(rhs)
          .with_semantics(semantics).with_flags(flags).with_history(history).with_max_attempts(max_attempts))

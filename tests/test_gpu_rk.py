@@ -283,13 +283,14 @@ def test_pinned_and_zero_copy_host_paths_agree(cuda, engine):
     n = 5000
     y0 = E.lorenz_y0(np.arange(n))
     s = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.6, **LOR)
-    a = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+    a = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True, zero_copy=False)
     y0p = pinned_empty(y0.shape)
     y0p[...] = y0
     pp = pinned_empty(LOR_P.shape)
     pp[...] = LOR_P
-    b = s.solve_ivp_ensemble(y0p, pp, shared_params=True)
+    b = s.solve_ivp_ensemble(y0p, pp, shared_params=True, zero_copy=False)
     c = s.solve_ivp_ensemble(y0p, pp, shared_params=True, zero_copy=True)
+    assert b.launch["d2h_ms"] > 0
     assert (a.status == _abi.OK).all()
     for k in ("y_end", "t_end", "dt_end", "status", "n_accept", "n_reject", "n_rhs"):
         np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)

@@ -17,10 +17,11 @@ import pytest
 
 from bacon_b200 import _abi
 from bacon_b200 import ensembles as E
-from reference_cases import BDF_CASES, RK_CASES, bdf_cfg
+from reference_cases import ADAMS_CASES, BDF_CASES, EULER_CASES, RK_CASES, bdf_cfg
 
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "anchors.json")))
-M = {"RK45": _abi.RK45, "RK23": _abi.RK23, "BDF6": _abi.BDF6, "BDF2": _abi.BDF2}
+M = {"RK45": _abi.RK45, "RK23": _abi.RK23, "BDF6": _abi.BDF6, "BDF2": _abi.BDF2, "Adams5": _abi.ADAMS5,
+     "Adams3": _abi.ADAMS3, "Euler": _abi.EULER}
 
 
 @pytest.mark.parametrize("method", ["RK45", "RK23"])
@@ -168,3 +169,79 @@ def test_oracle_failure_statuses(oracle):
     y0[0, 3] = np.nan
     r = oracle.solve_ensemble(_abi.RK45, "lorenz", y0, p, shared_params=True, dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0, t_end=0.1)
     assert r["status"][3] == _abi.E_NONFINITE and (np.delete(r["status"], 3) == _abi.OK).all()
+
+
+@pytest.mark.parametrize("case", ADAMS_CASES, ids=[c[0] for c in ADAMS_CASES])
+def test_reference_adams_tests(oracle, case):
+    """adams.rs:714-922: the six live Adams tests (two of them on a y-dependent right-hand side), the
+    reference's assertion on every yielded point.  REF_LITERAL is the source as written (these tests pin it);
+    REF_CORRECTED repairs D10 (the speculative step's derivative never reaches the deque, adams.rs:498-501):
+    same assertion, far fewer steps on the y-dependent problems.  Both through both evaluations of x^(1/order)."""
+    name, method, rhs, y0, cfg, exact, eps, lit, cor = case
+    for sem, (n_yield, n_rej) in ((_abi.SEM_LITERAL, lit), (_abi.SEM_CORRECTED, cor)):
+        outs = []
+        for pm in (0, 1):  # libm pow (f64::powf) / the deterministic root of the strict device kernels
+            r = oracle.solve_ensemble(M[method], rhs, np.array([[y0]]), history_capacity=8000, pow_mode=pm, semantics=sem,
+                                      **cfg)
+            assert r["status"][0] == _abi.OK
+            m = int(r["hist_len"][0])
+            assert (m, int(r["n_reject"][0])) == (n_yield, n_rej) and m == r["n_accept"][0]
+            t, y = r["hist_t"][0, :m], r["hist_y"][0, :m, 0]
+            assert np.abs(y - exact(t)).max() <= eps  # the reference's assertion
+            assert np.all(np.diff(t) > 0) and t[0] > cfg["t_start"]  # the initial condition is not yielded
+            assert r["t_end"][0] >= cfg["t_end"]
+            outs.append(r)
+        np.testing.assert_allclose(outs[0]["y_end"], outs[1]["y_end"], rtol=1e-12)
+        assert np.array_equal(outs[0]["n_rhs"], outs[1]["n_rhs"])
+
+
+def test_adams_root_modes_agree(oracle):
+    """adams.rs:527,:553 call powf(x, 1/order); the strict kernels use a Newton root built from +,*,/ only."""
+    x = np.exp(np.random.default_rng(2).uniform(np.log(1e-300), np.log(1e300), 200000))
+    for n in (3, 5):
+        a, b = oracle.nth_root(x, n)
+        # powf's exponent is fl(1/n), not 1/n: the reference's own value is off the true root by |ln x|/n * 2^-53
+        assert (np.abs(a - b) <= 4 * np.spacing(a) + a * np.abs(np.log(x)) / n * 1.2e-16).all()
+        near = (x > 1e-6) & (x < 1e6)  # the range q is evaluated on in practice
+        assert (np.abs(a - b)[near] <= 4 * np.spacing(a[near])).all() or near.sum() == 0
+        a, b = oracle.nth_root(np.array([0.0, np.inf, 1.0, 32.0, 27.0]), n)
+        assert a[0] == b[0] == 0.0 and np.isinf(b[1]) and b[2] == 1.0
+    assert oracle.nth_root(np.array([32.0]), 5)[1][0] == 2.0 and oracle.nth_root(np.array([27.0]), 3)[1][0] == 3.0
+
+
+def test_adams_y_dependent_ensemble_against_closed_form(oracle):
+    """Harmonic oscillators with per-trajectory frequency (y-dependent, 2-dim): both Adams orders converge to the
+    closed form, and dropping the pending warm-up block at Done (the D9 analogue, adams.rs:442-463) only ever
+    loses yielded points, never the final state."""
+    n = 64
+    w = np.linspace(0.5, 3.0, n)
+    y0 = np.stack([np.ones(n), np.zeros(n)])
+    exact = np.stack([np.cos(3.0 * w), -w * np.sin(3.0 * w)])
+    for method, tol in (("Adams5", 1e-8), ("Adams3", 1e-6)):
+        r = oracle.solve_ensemble(M[method], "harmonic", y0, w[None, :], dt_min=1e-8, dt_max=0.05, tol=tol, t_start=0.0,
+                                  t_end=3.0)
+        assert (r["status"] == _abi.OK).all() and (r["t_end"] >= 3.0).all()
+        assert np.abs(r["y_end"] - exact).max() < 10 * tol and r["n_accept"].max() < 6000
+    # as written (D10): the same problem needs ~1/tol steps, and still converges
+    lit = oracle.solve_ensemble(M["Adams5"], "harmonic", y0[:, -4:], w[None, -4:], dt_min=1e-8, dt_max=0.05, tol=1e-5,
+                                t_start=0.0, t_end=3.0, semantics=_abi.SEM_LITERAL)
+    cor = oracle.solve_ensemble(M["Adams5"], "harmonic", y0[:, -4:], w[None, -4:], dt_min=1e-8, dt_max=0.05, tol=1e-5,
+                                t_start=0.0, t_end=3.0)
+    assert (lit["status"] == _abi.OK).all() and (lit["n_accept"] > 100 * cor["n_accept"]).all()
+    assert np.abs(lit["y_end"] - exact[:, -4:]).max() < 1e-3
+
+
+@pytest.mark.parametrize("case", EULER_CASES, ids=[c[0] for c in EULER_CASES])
+def test_reference_euler_tests(oracle, case):
+    """ivp.rs:539-653.  Euler yields the OLD point of every step: the path starts AT the initial condition and
+    never contains the final state (ivp.rs:331-337)."""
+    name, rhs, y0, dt, exact, eps = case
+    y0 = np.array(y0).reshape(-1, 1)
+    par = np.ones((1, 1)) if rhs == "harmonic" else None
+    r = oracle.solve_ensemble(_abi.EULER, rhs, y0, par, dt_min=dt, dt_max=dt, tol=1.0, t_start=0.0, t_end=1.0,
+                              history_capacity=400)
+    m = int(r["hist_len"][0])
+    assert r["status"][0] == _abi.OK and m == round(1.0 / dt) == r["n_accept"][0] == r["n_rhs"][0]
+    t, y = r["hist_t"][0, :m], r["hist_y"][0, :m, 0]
+    assert np.abs(y - exact(t)).max() <= eps  # the reference's assertion
+    assert t[0] == 0.0 and y[0] == y0[0, 0] and t[-1] < 1.0 and r["t_end"][0] >= 1.0
