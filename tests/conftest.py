@@ -12,6 +12,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    # a runaway kernel (a trajectory that never retires) must fail one test, not eat the GPU call:
+    # the "thread" method ends the process even while a C call is blocking
+    for it in items:
+        if "gpu" in it.keywords and not any(m.name == "timeout" for m in it.iter_markers()):
+            it.add_marker(pytest.mark.timeout(300, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """The CPU oracle (oracle/liboracle.so), compiled on demand. Test infrastructure only."""

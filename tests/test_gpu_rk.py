@@ -303,3 +303,27 @@ def test_pinned_and_zero_copy_host_paths_agree(cuda, engine):
     ye = c.y_end
     del a, b, c, d
     assert np.isfinite(ye).all()
+
+
+def test_multi_gpu_host_entry_matches_single_gpu(cuda, engine):
+    """bacon_ivp_solve_ensemble_multi: trajectories dealt i mod G over the GPUs of this process,
+    bit-identical with the single-GPU solve, ragged n, per-trajectory parameters and dense output included."""
+    g = cuda.cuda.device_count()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    g = min(g, 4)
+    n = 10007
+    y0 = E.lorenz_y0(np.arange(n))
+    s = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.5, **LOR)
+    one = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+    many = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True, n_gpus=g)
+    for k in ("y_end", "t_end", "dt_end", "status", "n_accept", "n_reject", "n_rhs"):
+        np.testing.assert_array_equal(getattr(one, k), getattr(many, k), err_msg=k)
+    assert many.launch["n_kernels"] == g
+    idx = np.arange(1001)
+    y0v, mu = E.vdp_problem(idx * 4000, 1 << 22)
+    sv = make_solver(engine, "RK23", 2, rhs="vdp", dt_min=1e-12, dt_max=0.1, tol=1e-8, t_start=0.0, t_end=0.05, history=64)
+    a = sv.solve_ivp_ensemble(y0v, mu)
+    b = sv.solve_ivp_ensemble(y0v, mu, n_gpus=g)
+    for k in ("y_end", "status", "n_accept", "hist_len", "hist_t", "hist_y"):
+        np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)
