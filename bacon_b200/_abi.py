@@ -1,7 +1,7 @@
 """ctypes mirror of include/bacon_ivp.h (structs, enums).  No logic here."""
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # bacon_method  (rk.rs:561, rk.rs:656, bdf.rs:706, bdf.rs:762)
 RK45, RK23, BDF6, BDF2, ADAMS5, ADAMS3, EULER = 0, 1, 2, 3, 4, 5, 6
@@ -57,8 +57,7 @@ class Result(C.Structure):
     _fields_ = [
         ("y_end", C.c_void_p), ("t_end", C.c_void_p), ("dt_end", C.c_void_p),
         ("status", C.c_void_p), ("n_accept", C.c_void_p), ("n_reject", C.c_void_p),
-        ("n_rhs", C.c_void_p), ("hist_t", C.c_void_p), ("hist_y", C.c_void_p),
-        ("hist_len", C.c_void_p),
+        ("n_rhs", C.c_void_p), ("hist", C.c_void_p), ("hist_len", C.c_void_p),
     ]
 
 

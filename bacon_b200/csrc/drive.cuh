@@ -22,10 +22,9 @@ constexpr int ENSEMBLE_BLOCK = 128;
 template <class Stepper, bool HIST, int MINB>
 __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB) ensemble_kernel(const __grid_constant__ bacon_launch_args a) {
     constexpr int D = Stepper::D;
-    extern __shared__ __align__(16) unsigned char smem[];
 
     Stepper s(a);
-    HistStage<D, HIST> hist(a, smem);
+    HistStage<D, HIST> hist(a);
     const unsigned long long n = a.n;
 
     unsigned long long idx = warp_fetch(a.work_counter, true);
@@ -53,7 +52,6 @@ __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB) ensemble_kernel(const __
             if (fin) {
                 idx = nxt;
                 live = idx < n;
-                hist.begin();
                 s.reset(a, idx, live);
             }
             if (!__any_sync(FULL_MASK, live)) return;  // the warp can only run dry right after a retirement

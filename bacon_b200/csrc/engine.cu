@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -179,8 +180,7 @@ ShardLayout layout_shard(void* base, const bacon_ivp_config& cfg, size_t n, bool
     L.out.n_reject = want.n_reject ? c.take<uint32_t>(n) : nullptr;
     L.out.n_rhs = want.n_rhs ? c.take<uint32_t>(n) : nullptr;
     const size_t cap = cfg.history_capacity > 0 ? (size_t)cfg.history_capacity : 0;
-    L.out.hist_t = cap ? c.take<double>(n * cap) : nullptr;
-    L.out.hist_y = cap ? c.take<double>(n * cap * (size_t)cfg.dim) : nullptr;
+    L.out.hist = cap ? c.take<double>(n * cap * (size_t)(1 + cfg.dim)) : nullptr;
     L.out.hist_len = (cap && want.hist_len) ? c.take<uint32_t>(n) : nullptr;
     L.bytes = c.off;
     return L;
@@ -204,8 +204,8 @@ int check_common(const bacon_ivp_config* cfg, int rhs_id, const double* y0, cons
                     entry->name.c_str(), entry->n_params);
     if (!y0 || !out->y_end || !out->status) return fail(BACON_E_BAD_ARGUMENT, "y0, out.y_end and out.status are required");
     if (entry->n_params > 0 && !params) return fail(BACON_E_BAD_ARGUMENT, "rhs '%s' needs params", entry->name.c_str());
-    if (cfg->history_capacity > 0 && (!out->hist_t || !out->hist_y))
-        return fail(BACON_E_BAD_ARGUMENT, "history_capacity > 0 needs out.hist_t and out.hist_y");
+    if (cfg->history_capacity > 0 && !out->hist)
+        return fail(BACON_E_BAD_ARGUMENT, "history_capacity > 0 needs out.hist ([n][capacity][1 + dim])");
     // REF_LITERAL is the source as written, operation order included: only the strict kernels implement it
     const int strict = ((cfg->flags & BACON_FLAG_STRICT_FP) || cfg->semantics == BACON_SEM_LITERAL) ? 1 : 0;
     *fn = entry->launch[strict][cfg->method];
@@ -463,6 +463,8 @@ int bacon_ivp_solve_ensemble_device(const bacon_ivp_config* cfg, int rhs_id, siz
     bacon_launch_fn fn = nullptr;
     int rc = check_common(cfg, rhs_id, d_y0, d_params, d_out, &entry, &fn);
     if (rc != 0) return rc;
+    if (cfg->history_capacity > 0 && (reinterpret_cast<uintptr_t>(d_out->hist) & 31u))
+        return fail(BACON_E_BAD_ARGUMENT, "d_out.hist must be 32-byte aligned (records are written with 256-bit stores)");
     g_last_launch = bacon_ivp_launch_info{};
     if (n == 0) return 0;
     int dev = 0;
@@ -637,10 +639,8 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
             a.work_counter = s.ctx->counters + s.ctx->next_counter;
             s.ctx->next_counter = (s.ctx->next_counter + 1) % kCounterSlots;
             CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
-            if (cap) {  // slots beyond hist_len read as zero on the host (the staging buffer is reused between calls)
-                CUDA_TRY(cudaMemsetAsync(s.dl.out.hist_t, 0, sizeof(double) * s.n * cap, st));
-                CUDA_TRY(cudaMemsetAsync(s.dl.out.hist_y, 0, sizeof(double) * s.n * cap * D, st));
-            }
+            if (cap)  // slots beyond hist_len read as zero on the host (the staging buffer is reused between calls)
+                CUDA_TRY(cudaMemsetAsync(s.dl.out.hist, 0, sizeof(double) * s.n * cap * (D + 1), st));
             CUDA_TRY(cudaEventRecord(s.ctx->ev[1], st));
             rc = fn(&a);
             if (rc != 0) return fail(rc, "kernel launch failed on device %d: %s", s.dev, cudaGetErrorString(cudaGetLastError()));
@@ -660,8 +660,7 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
         D2H(n_reject, uint32_t, s.n);
         D2H(n_rhs, uint32_t, s.n);
         if (cap) {
-            D2H(hist_t, double, s.n * cap);
-            D2H(hist_y, double, s.n * cap * D);
+            D2H(hist, double, s.n * cap * (D + 1));
             D2H(hist_len, uint32_t, s.n);
         }
 #undef D2H
@@ -696,10 +695,9 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
             SCATTER(n_rhs);
             if (cap) {
                 SCATTER(hist_len);
-                for (size_t k = 0; k < s.n; ++k) {
-                    std::memcpy(out->hist_t + (g + k * G) * cap, h.hist_t + k * cap, sizeof(double) * cap);
-                    std::memcpy(out->hist_y + (g + k * G) * cap * D, h.hist_y + k * cap * D, sizeof(double) * cap * D);
-                }
+                const size_t path = cap * (size_t)(D + 1);  // doubles per trajectory
+                for (size_t k = 0; k < s.n; ++k)
+                    std::memcpy(out->hist + (g + k * G) * path, h.hist + k * path, sizeof(double) * path);
             }
 #undef SCATTER
         }

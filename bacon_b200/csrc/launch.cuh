@@ -47,11 +47,7 @@ template <class K> inline int launch_persistent(K kernel, bacon_launch_args* a, 
 }
 
 template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* a) {
-    constexpr int D = Stepper::D;
-    if (a->cfg.history_capacity > 0 && a->out.hist_t && a->out.hist_y) {
-        const size_t smem = HistStage<D, true>::smem_bytes(ENSEMBLE_BLOCK / 32);
-        return launch_persistent(ensemble_kernel<Stepper, true, MINB>, a, smem);
-    }
+    if (a->cfg.history_capacity > 0 && a->out.hist) return launch_persistent(ensemble_kernel<Stepper, true, MINB>, a, 0);
     return launch_persistent(ensemble_kernel<Stepper, false, MINB>, a, 0);
 }
 

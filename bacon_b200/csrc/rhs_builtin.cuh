@@ -2,6 +2,8 @@
 // `Derivative` closures (src/ivp.rs:34-48).  A RHS is a stateless device functor
 //   static constexpr int DIM, NPARAM;
 //   __device__ void operator()(double t, const double (&y)[DIM], const double* p, double (&dy)[DIM]) const;
+//   (optional, fast RK path)     __device__ void scaled(double h, double t, const double (&y)[DIM], const double* p,
+//                                                       double (&k)[DIM]) const;   k = h * f(t, y)
 //   (optional, BDF Newton path)  __device__ void jac(double t, const double (&y)[DIM], const double* p,
 //                                                    double (&J)[DIM][DIM]) const;   J[r][c] = d f_r / d y_c
 // The per-trajectory parameter block `p` is read-only: the reference clones the
@@ -19,6 +21,14 @@ struct RhsLorenz {  // p = (sigma, rho, beta)
         dy[0] = p[0] * (y[1] - y[0]);
         dy[1] = y[0] * (p[1] - y[2]) - y[1];
         dy[2] = y[0] * y[1] - p[2] * y[2];
+    }
+    // k = h * f: the first component is linear in sigma, so h*sigma (the same for all stages of an attempt) replaces
+    // a multiplication per stage
+    __device__ __forceinline__ void scaled(double h, double, const double (&y)[3], const double* p, double (&k)[3]) const {
+        const double hs = h * p[0];
+        k[0] = hs * (y[1] - y[0]);
+        k[1] = h * (y[0] * (p[1] - y[2]) - y[1]);
+        k[2] = h * (y[0] * y[1] - p[2] * y[2]);
     }
     __device__ __forceinline__ void jac(double, const double (&y)[3], const double* p, double (&J)[3][3]) const {
         J[0][0] = -p[0];       J[0][1] = p[0];  J[0][2] = 0.0;

@@ -71,6 +71,11 @@ __device__ __forceinline__ double inv_eighth_root(double x) {
     return fma(z * 0.125, r, z);        // Newton on z^-8 = x
 }
 
+// optional member of a RHS functor:  void scaled(double h, double t, const double (&y)[D], const double* p,
+// double (&k)[D]) const  ->  k = h * f(t, y).  Only the fast (non-strict) RK kernels use it.
+template <class Rhs, class = void> struct has_scaled { static constexpr bool value = false; };
+template <class Rhs> struct has_scaled<Rhs, decltype(void(&Rhs::scaled))> { static constexpr bool value = true; };
+
 template <class Tab, int I> __host__ __device__ constexpr int first_nz_a() {
     for (int j = 0; j < I; ++j)
         if (Tab::a(I, j) != 0.0) return j;
@@ -165,10 +170,18 @@ template <class Rhs, class Tab> struct RkFastStepper {
                 });
                 Y[d] = s;
             }
-            if constexpr (i == 0) rhs(t, Y, p, fi);
-            else rhs(fma(Tab::cv(i), h, t), Y, p, fi);
+            if constexpr (has_scaled<Rhs>::value) {
+                // the functor returns h * f itself (it can fold h into a linear term: Lorenz saves a DMUL per stage)
+                if constexpr (i == 0) rhs.scaled(h, t, Y, p, fi);
+                else rhs.scaled(h, fma(Tab::cv(i), h, t), Y, p, fi);
 #pragma unroll
-            for (int d = 0; d < D; ++d) k[i][d] = stage_used<Tab>(i) ? h * fi[d] : 0.0;
+                for (int d = 0; d < D; ++d) k[i][d] = stage_used<Tab>(i) ? fi[d] : 0.0;
+            } else {
+                if constexpr (i == 0) rhs(t, Y, p, fi);
+                else rhs(fma(Tab::cv(i), h, t), Y, p, fi);
+#pragma unroll
+                for (int d = 0; d < D; ++d) k[i][d] = stage_used<Tab>(i) ? h * fi[d] : 0.0;
+            }
         });
 
         // embedded error, squared: q = || sum_j e_j k_j ||^2   (rk.rs:386-390 is sqrt(q)/h)

@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
             if (accepted) {
                 if (HIST && n_acc < hcap) {  // the yielded point (rk.rs:418-419): one coalesced row
                     const size_t row = (size_t)idx * hcap + n_acc;
-                    a.out.hist_y[row * N + lane] = y;
-                    if (lane == 0) a.out.hist_t[row] = t;
+                    double* rec = a.out.hist + row * (N + 1);  // (t, y[0..N)) record, 264 contiguous bytes per point
+                    rec[1 + lane] = y;
+                    if (lane == 0) rec[0] = t;
                 }
                 n_acc++;
             } else {
@@ -240,7 +241,7 @@ template <class Tab, bool STRICT> int launch_rk_warp_linear32(bacon_launch_args*
     } else if (a->cfg.semantics != BACON_SEM_CORRECTED) {
         return BACON_E_UNSUPPORTED;
     }
-    if (a->cfg.history_capacity > 0 && a->out.hist_t && a->out.hist_y)
+    if (a->cfg.history_capacity > 0 && a->out.hist)
         return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, true, 4>, a);
     return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, false, 4>, a);
 }

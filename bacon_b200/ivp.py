@@ -37,6 +37,9 @@ def _check(rc):
         raise IVPError(rc, last_error())
 
 
+_RESULT_FIELDS = {name for name, _ in _abi.Result._fields_}
+
+
 class PinnedBlock:
     """One page-locked host block from `bacon_host_alloc`, carved into numpy arrays.  The arrays keep the
     block alive (ndarray.base -> ctypes view -> this object); it returns to the library's cache when the
@@ -87,8 +90,9 @@ class EnsembleResult:
         self.n_accept = arrays["n_accept"]
         self.n_reject = arrays["n_reject"]
         self.n_rhs = arrays["n_rhs"]
-        self.hist_t = arrays.get("hist_t")    # (n, cap)
-        self.hist_y = arrays.get("hist_y")    # (n, cap, dim)
+        self.hist = arrays.get("hist")        # (n, cap, 1 + dim): (t, y) records, one Path per trajectory
+        self.hist_t = None if self.hist is None else self.hist[:, :, 0]    # views of the record array
+        self.hist_y = None if self.hist is None else self.hist[:, :, 1:]
         self.hist_len = arrays.get("hist_len")
         self.launch = launch                  # dict: kernel_ms, h2d_ms, d2h_ms, grid, block, regs_per_thread
 
@@ -284,8 +288,7 @@ class _Solver:
                  "status": ((n,), np.int32), "n_accept": ((n,), np.uint32), "n_reject": ((n,), np.uint32),
                  "n_rhs": ((n,), np.uint32)}
         if cap > 0:
-            specs.update({"hist_t": ((n, cap), np.float64), "hist_y": ((n, cap, dim), np.float64),
-                          "hist_len": ((n,), np.uint32)})
+            specs.update({"hist": ((n, cap, 1 + dim), np.float64), "hist_len": ((n,), np.uint32)})
         if n == 0:
             arrays = {k: np.zeros(sh, dtype=dt) for k, (sh, dt) in specs.items()}
         else:
@@ -339,10 +342,12 @@ class _Solver:
                 "n_rhs": torch.zeros(n, dtype=torch.int32, device=dev),
             }
             if cap > 0:
-                out["hist_t"] = torch.zeros((n, cap), dtype=torch.float64, device=dev)
-                out["hist_y"] = torch.zeros((n, cap, dim), dtype=torch.float64, device=dev)
+                out["hist"] = torch.zeros((n, cap, 1 + dim), dtype=torch.float64, device=dev)
                 out["hist_len"] = torch.zeros(n, dtype=torch.int32, device=dev)
-        res = _abi.Result(**{k: v.data_ptr() for k, v in out.items()})
+        res = _abi.Result(**{k: v.data_ptr() for k, v in out.items() if k in _RESULT_FIELDS})
+        if cap > 0:  # views of the record array
+            out["hist_t"] = out["hist"][:, :, 0]
+            out["hist_y"] = out["hist"][:, :, 1:]
         with torch.cuda.device(dev):
             s = torch.cuda.current_stream(dev) if stream is None else stream
             _check(lib().bacon_ivp_solve_ensemble_device(C.byref(cfg), rid, n, y0.data_ptr(), pptr, C.byref(res),

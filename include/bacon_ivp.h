@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BACON_IVP_ABI_VERSION 2
+#define BACON_IVP_ABI_VERSION 3
 
 /* ---- solver families: src/ivp/rk.rs:561 (RungeKutta45), rk.rs:656
  * (RungeKutta23), src/ivp/bdf.rs:706 (BDF6), bdf.rs:762 (BDF2),
@@ -97,9 +97,12 @@ typedef struct bacon_ivp_config {
 
 /* Output block.  Any pointer may be NULL (that output is skipped) except
  * y_end and status.  Layouts (n = number of trajectories):
- *   y_end   [dim][n]        SoA, trajectory index fastest
- *   hist_t  [n][cap]        accepted times, trajectory-major (one `Path` each, ivp.rs:203)
- *   hist_y  [n][cap][dim]   accepted states, same order as the reference yields them
+ *   y_end   [dim][n]           SoA, trajectory index fastest
+ *   hist    [n][cap][1 + dim]  dense output: one contiguous `Path` per trajectory, one (t, y[0..dim))
+ *                              record per accepted point, in the order the reference yields them — the
+ *                              memory image of its `Vec<(f64, SVector<f64, D>)>` (ivp.rs:203).  A record is
+ *                              32 bytes for dim = 3: the kernel writes it with ONE 256-bit store (a whole
+ *                              DRAM sector), no staging.  Device pointers must be 32-byte aligned.
  * For the host entry points these are host pointers, for *_device device
  * pointers. */
 typedef struct bacon_ivp_result {
@@ -110,9 +113,8 @@ typedef struct bacon_ivp_result {
     uint32_t* n_accept;  /* [n] points yielded (`Ok`, ivp.rs:229)                               */
     uint32_t* n_reject;  /* [n] rejected step attempts                                          */
     uint32_t* n_rhs;     /* [n] derivative evaluations                                          */
-    double* hist_t;
-    double* hist_y;
-    uint32_t* hist_len;  /* [n] points written (<= history_capacity)                            */
+    double* hist;        /* [n][cap][1 + dim], required when history_capacity > 0               */
+    uint32_t* hist_len;  /* [n] records written (<= history_capacity)                           */
 } bacon_ivp_result;
 
 /* Launch record filled by the last solve on this thread (timing + totals). */

@@ -33,7 +33,7 @@ using Path = std::vector<std::pair<double, std::vector<double>>>;
 struct EnsembleResult {
     size_t n = 0;
     int dim = 0, capacity = 0;
-    std::vector<double> y_end, t_end, dt_end, hist_t, hist_y;  // layouts of bacon_ivp_result
+    std::vector<double> y_end, t_end, dt_end, hist;  // layouts of bacon_ivp_result; hist = [n][capacity][1 + dim]
     std::vector<int32_t> status;
     std::vector<uint32_t> n_accept, n_reject, n_rhs, hist_len;
     bacon_ivp_launch_info launch{};
@@ -41,8 +41,8 @@ struct EnsembleResult {
     Path path(size_t i) const {
         Path p;
         for (uint32_t k = 0; k < hist_len[i]; ++k) {
-            const double* row = &hist_y[(i * capacity + k) * dim];
-            p.emplace_back(hist_t[i * capacity + k], std::vector<double>(row, row + dim));
+            const double* rec = &hist[(i * capacity + k) * (size_t)(1 + dim)];  // (t, y[0..dim))
+            p.emplace_back(rec[0], std::vector<double>(rec + 1, rec + 1 + dim));
         }
         return p;
     }
@@ -129,11 +129,9 @@ template <int METHOD> class Solver {
         o.n_reject = r.n_reject.data();
         o.n_rhs = r.n_rhs.data();
         if (c.history_capacity > 0) {
-            r.hist_t.resize(n * c.history_capacity);
-            r.hist_y.resize(n * c.history_capacity * c.dim);
+            r.hist.resize(n * c.history_capacity * (size_t)(1 + c.dim));
             r.hist_len.resize(n);
-            o.hist_t = r.hist_t.data();
-            o.hist_y = r.hist_y.data();
+            o.hist = r.hist.data();
             o.hist_len = r.hist_len.data();
         }
         check(bacon_ivp_solve_ensemble_multi(&c, rhs_, n, y0, params, &o, n_gpus));

@@ -108,10 +108,12 @@ def solve_ensemble(method, rhs, y0, params=None, *, dt_min, dt_max, tol, t_start
         "n_reject": np.zeros(n, dtype=np.uint32), "n_rhs": np.zeros(n, dtype=np.uint32),
     }
     if history_capacity > 0:
-        out["hist_t"] = np.zeros((n, history_capacity))
-        out["hist_y"] = np.zeros((n, history_capacity, dim))
+        out["hist"] = np.zeros((n, history_capacity, 1 + dim))
         out["hist_len"] = np.zeros(n, dtype=np.uint32)
     res = _abi.Result(**{k: v.ctypes.data for k, v in out.items()})
+    if history_capacity > 0:  # the two columns of the record array, as views
+        out["hist_t"] = out["hist"][:, :, 0]
+        out["hist_y"] = out["hist"][:, :, 1:]
     rc = L.oracle_ivp_solve_ensemble(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res),
                                      pow_mode, n_threads)
     if rc != 0:

@@ -129,12 +129,13 @@ static void store(const RunArgs& a, size_t i, const bo::Solution<D>& s) {
     const bacon_ivp_result& o = *a.out;
     int status = s.status;
     const int cap = a.cfg->history_capacity;
-    if (cap > 0 && o.hist_t && o.hist_y) {
+    if (cap > 0 && o.hist) {
         const size_t np = s.path_t.size();
         const size_t keep = np < (size_t)cap ? np : (size_t)cap;
-        for (size_t k = 0; k < keep; ++k) {
-            o.hist_t[i * cap + k] = s.path_t[k];
-            for (int d = 0; d < D; ++d) o.hist_y[(i * cap + k) * D + d] = s.path_y[k][d];
+        for (size_t k = 0; k < keep; ++k) {  // one (t, y) record per yielded point: Vec<(f64, BVector)> (ivp.rs:203)
+            double* rec = o.hist + (i * cap + k) * (size_t)(D + 1);
+            rec[0] = s.path_t[k];
+            for (int d = 0; d < D; ++d) rec[1 + d] = s.path_y[k][d];
         }
         if (o.hist_len) o.hist_len[i] = (uint32_t)keep;
         if (np > (size_t)cap && status == bo::ST_OK) status = bo::ST_HISTORY_OVERFLOW;

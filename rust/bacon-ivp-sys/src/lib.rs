@@ -45,8 +45,7 @@ pub struct bacon_ivp_result {
     pub n_accept: *mut u32,
     pub n_reject: *mut u32,
     pub n_rhs: *mut u32,
-    pub hist_t: *mut c_double,
-    pub hist_y: *mut c_double,
+    pub hist: *mut c_double,
     pub hist_len: *mut u32,
 }
 

@@ -59,8 +59,7 @@ pub struct EnsembleResult {
     pub n_accept: Vec<u32>,
     pub n_reject: Vec<u32>,
     pub n_rhs: Vec<u32>,
-    pub hist_t: Vec<f64>,  // [n][cap]
-    pub hist_y: Vec<f64>,  // [n][cap][dim]
+    pub hist: Vec<f64>,    // [n][cap][1 + dim]: (t, y) records, the image of Vec<(f64, SVector<f64, D>)>
     pub hist_len: Vec<u32>,
     pub capacity: usize,
 }
@@ -69,8 +68,8 @@ impl EnsembleResult {
     pub fn path(&self, i: usize) -> Path {
         (0..self.hist_len[i] as usize)
             .map(|k| {
-                let row = (i * self.capacity + k) * self.dim;
-                (self.hist_t[i * self.capacity + k], self.hist_y[row..row + self.dim].to_vec())
+                let rec = (i * self.capacity + k) * (1 + self.dim);
+                (self.hist[rec], self.hist[rec + 1..rec + 1 + self.dim].to_vec())
             })
             .collect()
     }
@@ -149,14 +148,13 @@ impl<const METHOD: i32> Solver<METHOD> {
             n, dim: self.dim, capacity: cap,
             y_end: vec![0.0; self.dim * n], t_end: vec![0.0; n], dt_end: vec![0.0; n], status: vec![-1; n],
             n_accept: vec![0; n], n_reject: vec![0; n], n_rhs: vec![0; n],
-            hist_t: vec![0.0; n * cap], hist_y: vec![0.0; n * cap * self.dim], hist_len: vec![0; n],
+            hist: vec![0.0; n * cap * (1 + self.dim)], hist_len: vec![0; n],
         };
         let out = sys::bacon_ivp_result {
             y_end: r.y_end.as_mut_ptr(), t_end: r.t_end.as_mut_ptr(), dt_end: r.dt_end.as_mut_ptr(),
             status: r.status.as_mut_ptr(), n_accept: r.n_accept.as_mut_ptr(), n_reject: r.n_reject.as_mut_ptr(),
             n_rhs: r.n_rhs.as_mut_ptr(),
-            hist_t: if cap > 0 { r.hist_t.as_mut_ptr() } else { std::ptr::null_mut() },
-            hist_y: if cap > 0 { r.hist_y.as_mut_ptr() } else { std::ptr::null_mut() },
+            hist: if cap > 0 { r.hist.as_mut_ptr() } else { std::ptr::null_mut() },
             hist_len: if cap > 0 { r.hist_len.as_mut_ptr() } else { std::ptr::null_mut() },
         };
         let pptr = if params.is_empty() { std::ptr::null() } else { params.as_ptr() };

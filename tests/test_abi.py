@@ -35,10 +35,10 @@ def test_library_exports_every_declared_symbol(engine):
 
 
 def test_struct_layouts_match_header():
-    # bacon_ivp_config: 6 x 4-byte fields, 5 doubles, one u64; bacon_ivp_result: 10 pointers
+    # bacon_ivp_config: 6 x 4-byte fields, 5 doubles, one u64; bacon_ivp_result: 9 pointers
     assert C.sizeof(_abi.Config) == 6 * 4 + 5 * 8 + 8
     assert _abi.Config.dt_min.offset == 24 and _abi.Config.max_attempts.offset == 64
-    assert C.sizeof(_abi.Result) == 10 * C.sizeof(C.c_void_p)
+    assert C.sizeof(_abi.Result) == 9 * C.sizeof(C.c_void_p)
     assert C.sizeof(_abi.LaunchInfo) == 3 * 4 + 4 * 4
 
 
