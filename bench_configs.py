@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--broyden", action="store_true", help="config 5 with the reference's Broyden iteration instead of Newton+LU")
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hist", action="store_true", help="configs 2 and 4 without dense output (what the history costs)")
+    ap.add_argument("--n", type=int, default=0, help="override the trajectory count")
     args = ap.parse_args()
 
     import torch
@@ -51,7 +53,7 @@ def main():
     torch.cuda.set_device(dev)
     kw_dev = {}
     if args.config == 2:
-        w = dict(E.LORENZ, n=1 << 18)
+        w = dict(E.LORENZ, n=args.n or (1 << 18))
         n = max(1024, int(w["n"] * args.scale))
         y0 = E.lorenz_y0(np.arange(n))
         par = np.tile(np.array(w["params"])[:, None], (1, n))
@@ -78,6 +80,8 @@ def main():
         y0, par = E.robertson_problem(np.arange(n))
         make = B.BDF6
         flags, hist = (0 if args.broyden else _abi.FLAG_BDF_NEWTON), 0
+    if args.no_hist:
+        hist = 0
     dim = w["dim"]
     s = (make.new(dim).with_minimum_dt(w["dt_min"]).with_maximum_dt(w["dt_max"]).with_tolerance(w["tol"])
          .with_initial_time(w["t_start"]).with_ending_time(w["t_end"]).with_derivative(w["rhs"]).with_flags(flags)
