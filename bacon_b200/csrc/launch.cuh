@@ -52,10 +52,16 @@ template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* 
 }
 
 // ---- fast (FMA, compile-time tableau), REF_CORRECTED only
-#ifndef BACON_RK_MINB
-#define BACON_RK_MINB 4  // resident 128-thread CTAs per SM the fast RK kernels are compiled for (register budget)
+// resident 128-thread CTAs per SM the fast RK kernels are compiled for (register budget): 6 (80 registers) when the
+// state y, the stages k and the parameters fit (Lorenz/RKF45 needs 74), else 4 (128 registers)
+template <class Rhs, class Tab> constexpr int rk_fast_minb() {
+#ifdef BACON_RK_MINB
+    return BACON_RK_MINB;
+#else
+    return Rhs::DIM * (Tab::O + 1) + Rhs::NPARAM <= 28 ? 6 : 4;
 #endif
-template <class Rhs, class Tab, int MINB = BACON_RK_MINB> int launch_rk_fast(bacon_launch_args* a) {
+}
+template <class Rhs, class Tab, int MINB = rk_fast_minb<Rhs, Tab>()> int launch_rk_fast(bacon_launch_args* a) {
     if (a->cfg.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;
     return launch_stepper<RkFastStepper<Rhs, Tab>, MINB>(a);
 }

@@ -41,22 +41,45 @@ namespace bacon {
 __device__ __forceinline__ bool pos_le(double a, double b) { return __double_as_longlong(a) <= __double_as_longlong(b); }
 __device__ __forceinline__ bool pos_lt(double a, double b) { return __double_as_longlong(a) < __double_as_longlong(b); }
 
-// clamp(safety * (num/den)^(1/8), 0.1, 4) as a double; num, den >= 0.  SFU, log domain: the exponent
-// difference is integer arithmetic on the high words, the mantissas (top 20 bits rebuilt as floats in
-// [1, 2)) go through MUFU.LG2, the result through MUFU.EX2.  den = 0 -> 4, den = inf -> 0.1.
-// Relative accuracy ~3e-7 (the clamp bounds are the floats nearest 0.1 and 4).
-__device__ __forceinline__ double step_factor(double num, double den, float safety) {
+// the float 1.m built from the top 20 mantissa bits of a double's high word: two instructions (mask, shift-add).
+// Inline PTX because the compiler otherwise rewrites the expression as shift / and / or.
+__device__ __forceinline__ float mantissa_as_float(int hi) {
+    unsigned m;
+    asm("and.b32 %0, %1, 0x000fffff;\n\tmad.lo.u32 %0, %0, 8, 0x3f800000;" : "=r"(m) : "r"(hi));
+    return __uint_as_float(m);
+}
+
+// The step-size factor clamp(safety * (num/den)^(1/8), 0.1, 4), num, den >= 0, on the SFU in the log domain.
+// step_factor_log2: log2(safety * (num/den)^(1/8)), unclamped — the exponent difference is integer arithmetic on
+// the high words, the mantissas (top 20 bits rebuilt as floats in [1, 2)) go through MUFU.LG2.  den = 0 -> large
+// positive, den = inf -> large negative.  exp2_as_double: MUFU.EX2 and a float -> double conversion on the integer
+// pipe (the argument is inside [-3.33, 2], so the result is a normal float).  Relative accuracy ~3e-7.
+__device__ __forceinline__ float lg2_approx(float x) {
+    asm("lg2.approx.ftz.f32 %0, %0;" : "+f"(x));
+    return x;
+}
+__device__ __forceinline__ float step_factor_log2(double num, double den, float log2_safety) {
     const int hn = __double2hiint(num), hd = __double2hiint(den);
     const int de = (hn >> 20) - (hd >> 20);
-    float mn = __uint_as_float(0x3f800000u | (((unsigned)hn << 3) & 0x007ffff8u));
-    float md = __uint_as_float(0x3f800000u | (((unsigned)hd << 3) & 0x007ffff8u));
+    float mn = mantissa_as_float(hn), md = mantissa_as_float(hd);
     asm("lg2.approx.ftz.f32 %0, %0;" : "+f"(mn));
     asm("lg2.approx.ftz.f32 %0, %0;" : "+f"(md));
-    float l = 0.125f * ((float)de + (mn - md));
+    return fmaf(0.125f, (float)de + (mn - md), log2_safety);
+}
+__device__ __forceinline__ double exp2_as_double(float l) {
     asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(l));
-    const float d = fminf(fmaxf(safety * l, 0.1f), 4.0f);
-    const unsigned fb = __float_as_uint(d);  // float -> double on the integer pipe (d is a normal float)
+    const unsigned fb = __float_as_uint(l);
     return __hiloint2double((int)((fb >> 3) + (896u << 20)), (int)(fb << 29));
+}
+constexpr float LOG2_TENTH = -3.3219280949f;  // log2(0.1); log2(4) = 2
+
+// A positive double as a float scaled by a power of two chosen per ensemble (only RATIOS of such values are used):
+// bits = ((hi << 3) | (lo >> 29)) - (C << 23).  The funnel shift leaves the low 9 exponent bits in the top 9 bits
+// and 23 mantissa bits below; the subtraction re-biases the exponent.  Two integer instructions, no conversion on the
+// FP64 pipe.  Inside the window (resulting exponent field 1..254) the result is exact up to truncation (2^-23); see
+// RkFastStepper::attempt for what happens outside.
+__device__ __forceinline__ float scaled_float(double x, int c_shifted) {
+    return __int_as_float((int)__funnelshift_l((unsigned)__double2loint(x), (unsigned)__double2hiint(x), 3) - c_shifted);
 }
 
 // x^(-1/8), x in [1e-6, 1e8]: SFU seed + one Newton step in fp64 (used by the warp-per-trajectory kernel)
@@ -100,7 +123,8 @@ template <class Tab> __host__ __device__ constexpr bool stage_used(int j) {
 
 // Stepper concept used by ensemble_kernel (drive.cuh):
 //   D;  ctor(args);  reset(args, idx, live);  int attempt(bool& yielded)  (-1 = keep going, else a
-//   bacon_status);  t, dt, n_acc, n_rej, n_rhs();  out_t()/out_y() = the yielded point;  end_y().
+//   bacon_status);  t, dt, n_rej, n_rhs();  accepted count: field n_acc, or acc_running() / acc_of(raw) + status_of(raw)
+//   when attempt() returns an encoded status (StepperCodec, drive.cuh);  out_t()/out_y() = the yielded point;  end_y().
 template <class Rhs, class Tab> struct RkFastStepper {
     static constexpr int D = Rhs::DIM;
     static constexpr int P = Rhs::NPARAM;
@@ -108,12 +132,18 @@ template <class Rhs, class Tab> struct RkFastStepper {
 
     // ensemble-wide constants (registers / uniform registers)
     double t_start, t_end, dt_min, dt_max, tol, dt0;
-    uint32_t cap;
+    uint32_t cap;  // max_attempts
+    int c_shifted;   // exponent re-bias of scaled_float() for this ensemble's (tol dt)^2 range, << 23
+    int hi_dt_max;   // high word of dt_max — or INT_MIN (every attempt takes the exact path) if that range has no window
+    float eighth;    // 0.125f pinned in a register (ptxas otherwise re-materialises it every attempt)
     // one trajectory
     double y[D], p[P > 0 ? P : 1];
     double t, dt;
-    uint32_t n_acc, n_att;
-    uint32_t n_rej;  // valid once attempt() has returned a status (>= 0)
+    // attempts that ran their stages / attempts reported as rejected.  Accepted = n_att - n_rej (- 1 when the
+    // trajectory failed in an attempt that counts neither way: see attempt()); not a counter of its own, so the
+    // accepted path carries one increment.
+    uint32_t n_att, n_rej;
+    static constexpr int VOID_ATTEMPT = 0x100;  // ORed into the status attempt() returns: the last attempt counts neither way
 
     __device__ __forceinline__ explicit RkFastStepper(const bacon_launch_args& a) {
         t_start = a.cfg.t_start;
@@ -122,16 +152,28 @@ template <class Rhs, class Tab> struct RkFastStepper {
         dt_max = a.cfg.dt_max;
         tol = a.cfg.tol;
         dt0 = (dt_max + dt_min) * 0.5;  // rk.rs:315
+        {
+            // Window of scaled_float(): (tol dt_max)^2 maps to exponent field 250; (tol dt_min)^2 / 16 (a clamped last
+            // step h in [dt_min/4, dt_min) still lands inside; a smaller h fails the dt_min test below whatever the
+            // factor) must stay above field 24, so that everything below the window is < th2 * 2^-20, where the factor
+            // is clamped to 4 anyway.  Anchoring the top keeps the 9-bit exponent field free of aliases down to 2^-1020.
+            const double lo2 = (tol * dt_min) * (tol * dt_min), hi2 = (tol * dt_max) * (tol * dt_max);
+            const int e_lo = (__double2hiint(lo2) >> 20) & 0x7ff, e_hi = (__double2hiint(hi2) >> 20) & 0x7ff;
+            const bool ok = e_lo >= 1 && e_hi <= 1022 && e_hi - e_lo <= 250 - 28;
+            c_shifted = (int)((unsigned)(e_hi - 512 - 250) << 23);
+            hi_dt_max = ok ? __double2hiint(dt_max) : (int)0x80000000;
+            eighth = __int_as_float(0x3e000000 + (a.cfg.dim >> 30));  // + 0, but not a constant ptxas can see
+        }
         cap = (a.cfg.max_attempts == 0 || a.cfg.max_attempts > 0xFFFFFFFEull) ? 0xFFFFFFFEu
                                                                                : (uint32_t)a.cfg.max_attempts;
         t = t_start;
         dt = dt0;
-        n_acc = n_rej = n_att = 0;
+        n_rej = n_att = 0;
     }
     __device__ __forceinline__ void reset(const bacon_launch_args& a, unsigned long long idx, bool live) {
         t = t_start;
         dt = dt0;
-        n_acc = n_rej = n_att = 0;
+        n_rej = n_att = 0;
         if (live) load_problem<D, P>(a, idx, y, p);
     }
     __device__ __forceinline__ uint32_t n_rhs() const { return n_att * (uint32_t)O; }
@@ -139,21 +181,22 @@ template <class Rhs, class Tab> struct RkFastStepper {
     __device__ __forceinline__ const double (&out_y() const)[D] { return y; }
     __device__ __forceinline__ const double (&end_y() const)[D] { return y; }
 
-    // one IVPStepper::step call (rk.rs:361-423).  Exits (return >= 0) set n_rej = attempts that were
-    // rejected and reported as such; on the hot path it is implied by n_att - n_acc.
+    // one IVPStepper::step call (rk.rs:361-423).  The common case — not the last step, accepted, new dt strictly
+    // inside (dt_min, dt_max) — is proven by 32-bit compares of the HIGH words (a positive double's high word is
+    // monotone in its value, so hi(a) < hi(b) proves a < b); everything else, including every case the high words
+    // cannot decide, goes to one of two rare blocks that run the reference's own tests exactly.  Exits (return >= 0)
+    // return the bacon_status, ORed with VOID_ATTEMPT when the failing attempt is reported neither as accepted nor as
+    // rejected (status_of / acc_of decode it for the driver).
     __device__ __forceinline__ int attempt(bool& yielded) {
         const Rhs rhs{};
-        yielded = false;
-        // rk.rs:362-368.  rem <= 0 (Done) and rem <= dt (clamp the last step) are ONE signed compare of bit
-        // patterns: dt > 0, and a negative or zero double is <= every positive one as a signed integer.
+        // rk.rs:362-368.  rem <= 0 (Done) and rem <= dt (clamp the last step) both imply hi(rem) <= hi(dt) as signed
+        // integers (dt > 0).
         const double rem = t_end - t;
         double h = dt;
-        const bool last = __double_as_longlong(rem) <= __double_as_longlong(dt);
-        if (n_att >= cap || last) {
-            n_rej = n_att - n_acc;
+        if (__builtin_expect((n_att >= cap) | (__double2hiint(rem) <= __double2hiint(dt)), 0)) {  // rare
             if (n_att >= cap) return BACON_E_MAX_ATTEMPTS;
             if (!(t < t_end)) return BACON_OK;  // rk.rs:362-364
-            if (t + dt >= t_end) h = rem;       // rk.rs:366-368, the reference's own test on this rare path
+            if (t + dt >= t_end) h = rem;       // rk.rs:366-368, the reference's own test
         }
 
         // stages: k_i = h * f(t + c_i h, y + sum_j a_ij k_j)   (rk.rs:370-384)
@@ -166,7 +209,7 @@ template <class Rhs, class Tab> struct RkFastStepper {
                 double s = y[d];
                 static_for<0, i>([&](auto J) {
                     constexpr int j = decltype(J)::value;
-                    if constexpr (Tab::a(i, j) != 0.0) s = fma(Tab::av(i, j), k[j][d], s);
+                    if constexpr (Tab::a(i, j) != 0.0) s = fma(coef_a<i, j>(), k[j][d], s);
                 });
                 Y[d] = s;
             }
@@ -198,42 +241,72 @@ template <class Rhs, class Tab> struct RkFastStepper {
         }
         const double th = tol * h;
         const double th2 = th * th;
-
         n_att++;
-        // error <= tol  <=>  q <= (tol h)^2   (rk.rs:392).  A NaN q has a bit pattern above every finite
-        // value: it is "not accepted" and diagnosed on the reject path.
-        const bool accepted = pos_le(q, th2);
-        // rk.rs:400-412: (tol/error)^(1/4) = (th2/q)^(1/8)
-        double dtn = h * step_factor(th2, q, (float)Tab::safety);
-        dtn = pos_lt(dt_max, dtn) ? dt_max : dtn;
-        dt = dtn;
-        if (accepted) {
-            t += h;
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                double s = y[d];
-                static_for<0, O>([&](auto J) {
-                    constexpr int j = decltype(J)::value;
-                    if constexpr (Tab::b(j) != 0.0) s = fma(Tab::bv(j), k[j][d], s);
-                });
-                y[d] = s;
+        // rk.rs:400-408: (tol/error)^(1/4) = (th2/q)^(1/8), on the SFU in the log domain.  An accepted step has a factor
+        // >= safety > 0.1, so the lower clamp, like the clamp to dt_max (:410-412), is left to the rare block.
+        // q and th2 are turned into floats by scaled_float().  th2 is always inside the window (ctor).  q below the
+        // window (or +0) gives NaN or -inf from LG2, hence lf = NaN or +inf, and fminf(., 2) = 2: the factor 4 that such
+        // a q deserves.  q above the window is > th2: the rare block recomputes the factor from the doubles.
+        const float lf = fmaf(eighth, lg2_approx(scaled_float(th2, c_shifted)) - lg2_approx(scaled_float(q, c_shifted)),
+                              Tab::log2_safety);
+        double dtn = h * exp2_as_double(fminf(lf, 2.0f));
+
+        // error <= tol  <=>  q <= (tol h)^2   (rk.rs:392).  q >= +0 or NaN (either sign): as UNSIGNED integers a NaN
+        // orders above every finite value, so it is never "accepted".
+        const unsigned hq = (unsigned)__double2hiint(q), hth = (unsigned)__double2hiint(th2);
+        const int hdn = __double2hiint(dtn);
+        if (__builtin_expect((hq >= hth) | (hdn >= hi_dt_max) | (hdn <= __double2hiint(dt_min)), 0)) {
+            // rare: the exact tests
+            const bool accepted =
+                (unsigned long long)__double_as_longlong(q) <= (unsigned long long)__double_as_longlong(th2);
+            dtn = h * exp2_as_double(fminf(fmaxf(step_factor_log2(th2, q, Tab::log2_safety), LOG2_TENTH), 2.0f));
+            dtn = pos_lt(dt_max, dtn) ? dt_max : dtn;  // rk.rs:410-412
+            dt = dtn;
+            if (!accepted) {
+                if (q != q) return BACON_E_NONFINITE | VOID_ATTEMPT;  // the reference would Redo forever (D8)
+                n_rej++;
+                if (pos_lt(dtn, dt_min) && t < t_end) return BACON_E_MIN_DT_EXCEEDED;  // rk.rs:414-416
+                return -1;
             }
-        }
-        if (!accepted || pos_lt(dtn, dt_min)) {  // rare
-            if (!accepted && q != q) {           // the reference would Redo forever (D8)
-                n_rej = n_att - n_acc - 1;
-                return BACON_E_NONFINITE;
-            }
-            if (pos_lt(dtn, dt_min) && t < t_end) {  // rk.rs:414-416: fails before the point is yielded
-                n_rej = n_att - n_acc - (accepted ? 1u : 0u);
-                return BACON_E_MIN_DT_EXCEEDED;
-            }
-        }
-        if (accepted) {
-            n_acc++;
+            advance(h, k);
+            // rk.rs:414-416: fails before the point is yielded (the attempt is counted neither way)
+            if (pos_lt(dtn, dt_min) && t < t_end) return BACON_E_MIN_DT_EXCEEDED | VOID_ATTEMPT;
             yielded = true;
+            return -1;
         }
+        dt = dtn;
+        advance(h, k);
+        yielded = true;
         return -1;
+    }
+
+    __device__ __forceinline__ static int status_of(int raw) { return raw & (VOID_ATTEMPT - 1); }
+    __device__ __forceinline__ uint32_t acc_of(int raw) const { return n_att - n_rej - ((raw & VOID_ATTEMPT) ? 1u : 0u); }
+    __device__ __forceinline__ uint32_t acc_running() const { return n_att - n_rej; }
+
+    // rk.rs:393-398: t += dt, y += sum_j b_j k_j
+    __device__ __forceinline__ void advance(double h, const double (&k)[O][D]) {
+        t += h;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            double s = y[d];
+            static_for<0, O>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                if constexpr (Tab::b(j) != 0.0) s = fma(Tab::bv(j), k[j][d], s);
+            });
+            y[d] = s;
+        }
+    }
+
+    // a_ij as a DFMA operand: entries whose low word is zero (1/4, 2, -8, 3/4 ...) are encodable as an immediate and
+    // stay literals; the others are read from __constant__ memory into uniform registers once, outside the loop
+    // (RKF45 has 24 distinct coefficients: with all of them in uniform registers ptxas runs out and re-loads one
+    // per attempt).
+    template <int I, int J> __device__ __forceinline__ static double coef_a() {
+        constexpr double v = Tab::a(I, J);
+        constexpr double s = v * 1048576.0;
+        if constexpr (s == (double)(long long)s && (v >= 1.0 / 1024 || v <= -1.0 / 1024) && v <= 1024.0 && v >= -1024.0) return v;
+        else return Tab::av(I, J);
     }
 };
 

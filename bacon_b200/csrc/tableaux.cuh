@@ -61,6 +61,7 @@ struct TabRKF45 {
         return v[i];
     }
     static constexpr double safety = 84.0 / 100.0;  // rk.rs:266-268 (intent)
+    static constexpr float log2_safety = -0.2515387670f;  // log2(0.84)
 #ifdef __CUDACC__
     __device__ __forceinline__ static double cv(int i) { return kRKF45_c[i]; }
     __device__ __forceinline__ static double av(int i, int j) { return kRKF45_a[i][j]; }
@@ -92,6 +93,7 @@ struct TabBS23 {
         return v[i];
     }
     static constexpr double safety = 84.0 / 100.0;
+    static constexpr float log2_safety = -0.2515387670f;  // log2(0.84)
 #ifdef __CUDACC__
     __device__ __forceinline__ static double cv(int i) { return kBS23_c[i]; }
     __device__ __forceinline__ static double av(int i, int j) { return kBS23_a[i][j]; }

@@ -199,6 +199,55 @@ def test_failure_statuses_never_abort_the_batch(cuda, engine, oracle):
     assert rel_err(gpu.y_end[:, ok], ref["y_end"][:, ok]).max() <= band(1e-8)
 
 
+def test_fast_controller_corner_cases(cuda, engine, oracle):
+    """The fast stepper decides "common case" from high words and evaluates the step-size factor on floats re-biased
+    into a per-ensemble exponent window (rk_fast.cuh).  Everything outside that window must still take the
+    reference's decisions: compare step COUNTS with the oracle on problems built to leave it."""
+    def counts_match(gpu, ref, slack=1):
+        np.testing.assert_array_equal(gpu.status, ref["status"])
+        d_acc = np.abs(gpu.n_accept.astype(np.int64) - ref["n_accept"].astype(np.int64))
+        d_rej = np.abs(gpu.n_reject.astype(np.int64) - ref["n_reject"].astype(np.int64))
+        assert d_acc.max() <= slack and d_rej.max() <= slack, (d_acc.max(), d_rej.max())
+
+    one = np.ones((1, 64))
+    # (a) error estimate exactly zero (RK45 integrates y' = -2t exactly): factor 4 until dt_max, then pinned there
+    for method in ("RK45", "RK23"):
+        gpu, ref = run_both(engine, oracle, method, "quadratic", one, dt_min=1e-6, dt_max=0.1, tol=1e-6, t_start=0.0,
+                            t_end=3.0)
+        counts_match(gpu, ref, slack=0 if method == "RK45" else 1)
+        assert rel_err(gpu.y_end, ref["y_end"]).max() <= band(1e-6)
+    # (b) the solution decays to 1e-130: the squared error estimate (~1e-280) is far below the window -> factor 4
+    gpu, ref = run_both(engine, oracle, "RK45", "decay", one, dt_min=1e-6, dt_max=0.5, tol=1e-8, t_start=0.0, t_end=300.0)
+    counts_match(gpu, ref)
+    # (the error test is absolute, rk.rs:386-392: at 5e-131 the two solutions agree to ~1e-4 relative, 1e-134 absolute)
+    assert (gpu.status == _abi.OK).all() and np.abs(gpu.y_end - ref["y_end"]).max() <= 1e-8
+    # (c) no window: (tol dt_max)^2 >= 1, and (tol dt_min)^2 underflows -> every attempt takes the exact path
+    y0 = E.lorenz_y0(np.arange(64))
+    gpu, ref = run_both(engine, oracle, "RK45", "harmonic", np.vstack([one, 0 * one]), np.full((1, 64), 2.0),
+                        dt_min=1e-6, dt_max=4.0, tol=0.5, t_start=0.0, t_end=50.0)
+    counts_match(gpu, ref)
+    gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, dt_min=1e-200, dt_max=0.1,
+                        tol=1e-8, t_start=0.0, t_end=1.0)
+    counts_match(gpu, ref, slack=3)
+    assert rel_err(gpu.y_end, ref["y_end"]).max() <= band(1e-8)
+    # (d) a narrow dt range that pins dt at dt_min's edge and at dt_max in turn (both clamps live on the exact path)
+    gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, dt_min=1e-3, dt_max=2e-3,
+                        tol=1e-6, t_start=0.0, t_end=1.0)
+    counts_match(gpu, ref, slack=3)
+    # (e) an infinity in the state: inf - inf inside the RHS GENERATES a NaN (sign bit set on this hardware) -> NonFinite
+    y0b = y0.copy()
+    y0b[0, 5] = np.inf
+    gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0b, LOR_P, shared_params=True, t_end=0.2, **LOR)
+    assert gpu.status[5] == _abi.E_NONFINITE and ref["status"][5] == _abi.E_NONFINITE
+    assert (np.delete(gpu.status, 5) == _abi.OK).all()
+    # (f) a time axis that ends exactly where a step lands, negative start time
+    gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, dt_min=1e-9, dt_max=0.1, tol=1e-8,
+                        t_start=-2.0, t_end=-1.0)
+    counts_match(gpu, ref, slack=3)
+    np.testing.assert_array_equal(gpu.t_end, ref["t_end"])
+    assert rel_err(gpu.y_end, ref["y_end"]).max() <= band(1e-8)
+
+
 def test_edge_sizes(cuda, engine, oracle):
     """n = 1, ragged n around warp/block multiples, and n = 0."""
     for n in (1, 31, 33, 127, 129, 1025):
