@@ -17,7 +17,8 @@
 
 namespace bacon {
 
-template <class K> inline int launch_persistent(K kernel, bacon_launch_args* a, size_t smem) {
+// grid of a persistent launch: resident CTAs per SM (occupancy of `kernel`) x SM count, capped by the work
+template <class K> inline int persistent_grid(K kernel, bacon_launch_args* a, size_t smem) {
     cudaError_t e;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -41,14 +42,66 @@ template <class K> inline int launch_persistent(K kernel, bacon_launch_args* a, 
     a->grid = (int)grid;
     a->block = ENSEMBLE_BLOCK;
     a->regs_per_thread = fa.numRegs;
+    return 0;
+}
+
+template <class K> inline int launch_persistent(K kernel, bacon_launch_args* a, size_t smem) {
+    if (const int rc = persistent_grid(kernel, a, smem)) return rc;
     a->n_kernels = 1;
-    kernel<<<(unsigned)grid, ENSEMBLE_BLOCK, smem, (cudaStream_t)a->stream>>>(*a);
+    kernel<<<(unsigned)a->grid, ENSEMBLE_BLOCK, smem, (cudaStream_t)a->stream>>>(*a);
     return cudaGetLastError() == cudaSuccess ? 0 : BACON_E_CUDA;
 }
 
+// stream-ordered scratch for the suspended trajectories of the tail (drive.cuh): the pool keeps its memory between
+// launches (release threshold raised once per device), so this is a free-list lookup, not a cudaMalloc
+inline cudaError_t tail_scratch_alloc(double** p, size_t bytes, cudaStream_t st) {
+    static bool pool_ready[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_ready[dev] = true;
+    }
+    return cudaMallocAsync((void**)p, bytes, st);
+}
+
+template <class Stepper, bool HIST, int MINB> inline int launch_stepper_hist(bacon_launch_args* a) {
+    auto kernel = ensemble_kernel<Stepper, HIST, MINB>;
+    if (const int rc = persistent_grid(kernel, a, 0)) return rc;
+    cudaStream_t st = (cudaStream_t)a->stream;
+    double* tail = nullptr;
+    if constexpr (StepperMigrates<Stepper>::value) {
+        // a tail only exists when lanes take more than one trajectory; BACON_IVP_NO_TAIL=1 switches it off (A/B)
+        static const bool no_tail = getenv("BACON_IVP_NO_TAIL") != nullptr;
+        if (!no_tail && a->n > (unsigned long long)a->grid * ENSEMBLE_BLOCK) {
+            const size_t bytes = sizeof(double) * (Stepper::STATE_DOUBLES + 1) * (size_t)a->grid * ENSEMBLE_BLOCK;
+            if (tail_scratch_alloc(&tail, bytes, st) != cudaSuccess) {
+                (void)cudaGetLastError();
+                tail = nullptr;  // no scratch: the main kernel runs every trajectory to its end itself
+            }
+        }
+    }
+    a->n_kernels = 1;
+    kernel<<<(unsigned)a->grid, ENSEMBLE_BLOCK, 0, st>>>(*a, tail);
+    if (cudaGetLastError() != cudaSuccess) return BACON_E_CUDA;
+    if constexpr (StepperMigrates<Stepper>::value) {
+        if (tail) {
+            ensemble_tail_kernel<Stepper, HIST, MINB><<<(unsigned)a->grid, ENSEMBLE_BLOCK, 0, st>>>(*a, tail);
+            if (cudaGetLastError() != cudaSuccess) return BACON_E_CUDA;
+            a->n_kernels = 2;
+            if (cudaFreeAsync(tail, st) != cudaSuccess) return BACON_E_CUDA;
+        }
+    }
+    return 0;
+}
+
 template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* a) {
-    if (a->cfg.history_capacity > 0 && a->out.hist) return launch_persistent(ensemble_kernel<Stepper, true, MINB>, a, 0);
-    return launch_persistent(ensemble_kernel<Stepper, false, MINB>, a, 0);
+    if (a->cfg.history_capacity > 0 && a->out.hist) return launch_stepper_hist<Stepper, true, MINB>(a);
+    return launch_stepper_hist<Stepper, false, MINB>(a);
 }
 
 // ---- fast (FMA, compile-time tableau), REF_CORRECTED only

@@ -139,10 +139,15 @@ template <class Rhs, class Tab> struct RkFastStepper {
     // one trajectory
     double y[D], p[P > 0 ? P : 1];
     double t, dt;
-    // attempts that ran their stages / attempts reported as rejected.  Accepted = n_att - n_rej (- 1 when the
-    // trajectory failed in an attempt that counts neither way: see attempt()); not a counter of its own, so the
-    // accepted path carries one increment.
-    uint32_t n_att, n_rej;
+    // Counters.  `tick` counts attempt() CALLS and is the only counter the common path touches.  Every lane of a warp
+    // makes the same calls, so the lanes' ticks stay equal, and every CHECK_EVERY calls the whole warp takes the rare
+    // block together, rewinds tick to 0 and returns RAW_CHECKPOINT to the driver (which uses it to notice that the
+    // work counter ran dry without polling anything per attempt).  `tick0` is the trajectory's origin on that axis:
+    // attempts that ran their stages = tick - tick0 (calls that ran none move tick0 along).  The same compare,
+    // tick > next_check, enforces max_attempts.  Accepted = attempts - n_rej (- 1 when the trajectory failed in an
+    // attempt that counts neither way: see attempt()).
+    static constexpr uint32_t CHECK_EVERY = 64;
+    uint32_t tick, tick0, next_check, n_rej;
     static constexpr int VOID_ATTEMPT = 0x100;  // ORed into the status attempt() returns: the last attempt counts neither way
 
     __device__ __forceinline__ explicit RkFastStepper(const bacon_launch_args& a) {
@@ -166,17 +171,26 @@ template <class Rhs, class Tab> struct RkFastStepper {
         }
         cap = (a.cfg.max_attempts == 0 || a.cfg.max_attempts > 0xFFFFFFFEull) ? 0xFFFFFFFEu
                                                                                : (uint32_t)a.cfg.max_attempts;
+        tick = 0;
         t = t_start;
         dt = dt0;
-        n_rej = n_att = 0;
+        rearm(0);
     }
+    // the trajectory has made n attempts so far: place it on the tick axis
+    __device__ __forceinline__ void rearm(uint32_t n) {
+        tick0 = tick - n;
+        const uint32_t left = cap - n, room = CHECK_EVERY - tick;
+        next_check = tick + (left < room ? left : room);
+    }
+    __device__ __forceinline__ uint32_t n_att() const { return tick - tick0; }
     __device__ __forceinline__ void reset(const bacon_launch_args& a, unsigned long long idx, bool live) {
         t = t_start;
         dt = dt0;
-        n_rej = n_att = 0;
+        n_rej = 0;
+        rearm(0);
         if (live) load_problem<D, P>(a, idx, y, p);
     }
-    __device__ __forceinline__ uint32_t n_rhs() const { return n_att * (uint32_t)O; }
+    __device__ __forceinline__ uint32_t n_rhs() const { return n_att() * (uint32_t)O; }
     __device__ __forceinline__ double out_t() const { return t; }
     __device__ __forceinline__ const double (&out_y() const)[D] { return y; }
     __device__ __forceinline__ const double (&end_y() const)[D] { return y; }
@@ -193,10 +207,21 @@ template <class Rhs, class Tab> struct RkFastStepper {
         // integers (dt > 0).
         const double rem = t_end - t;
         double h = dt;
-        if (__builtin_expect((n_att >= cap) | (__double2hiint(rem) <= __double2hiint(dt)), 0)) {  // rare
-            if (n_att >= cap) return BACON_E_MAX_ATTEMPTS;
-            if (!(t < t_end)) return BACON_OK;  // rk.rs:362-364
-            if (t + dt >= t_end) h = rem;       // rk.rs:366-368, the reference's own test
+        tick++;
+        if (__builtin_expect((tick > next_check) | (__double2hiint(rem) <= __double2hiint(dt)), 0)) {  // rare
+            if (tick > next_check) {
+                tick0++;  // this call runs no stages
+                if (n_att() >= cap) return BACON_E_MAX_ATTEMPTS;
+                const uint32_t n = n_att();  // a checkpoint: the whole warp is here
+                tick = 0;
+                rearm(n);
+                return -2;  // RAW_CHECKPOINT
+            }
+            if (!(t < t_end)) {  // rk.rs:362-364
+                tick0++;
+                return BACON_OK;
+            }
+            if (t + dt >= t_end) h = rem;  // rk.rs:366-368, the reference's own test
         }
 
         // stages: k_i = h * f(t + c_i h, y + sum_j a_ij k_j)   (rk.rs:370-384)
@@ -241,7 +266,6 @@ template <class Rhs, class Tab> struct RkFastStepper {
         }
         const double th = tol * h;
         const double th2 = th * th;
-        n_att++;
         // rk.rs:400-408: (tol/error)^(1/4) = (th2/q)^(1/8), on the SFU in the log domain.  An accepted step has a factor
         // >= safety > 0.1, so the lower clamp, like the clamp to dt_max (:410-412), is left to the rare block.
         // q and th2 are turned into floats by scaled_float().  th2 is always inside the window (ctor).  q below the
@@ -280,9 +304,32 @@ template <class Rhs, class Tab> struct RkFastStepper {
         return -1;
     }
 
+    // suspend / resume (tail compaction, drive.cuh): everything that belongs to the trajectory
+    static constexpr int STATE_DOUBLES = D + (P > 0 ? P : 0) + 3;
+    __device__ __forceinline__ double remaining() const { return t_end - t; }
+    __device__ __forceinline__ void save(double (&st)[STATE_DOUBLES + 1]) const {
+#pragma unroll
+        for (int d = 0; d < D; ++d) st[d] = y[d];
+#pragma unroll
+        for (int k = 0; k < P; ++k) st[D + k] = p[k];
+        st[D + P] = t;
+        st[D + P + 1] = dt;
+        st[D + P + 2] = __hiloint2double((int)n_att(), (int)n_rej);
+    }
+    __device__ __forceinline__ void load(const double (&st)[STATE_DOUBLES + 1]) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[d] = st[d];
+#pragma unroll
+        for (int k = 0; k < P; ++k) p[k] = st[D + k];
+        t = st[D + P];
+        dt = st[D + P + 1];
+        n_rej = (uint32_t)__double2loint(st[D + P + 2]);
+        tick = 0;  // the lanes of the new warp start a common tick axis
+        rearm((uint32_t)__double2hiint(st[D + P + 2]));
+    }
     __device__ __forceinline__ static int status_of(int raw) { return raw & (VOID_ATTEMPT - 1); }
-    __device__ __forceinline__ uint32_t acc_of(int raw) const { return n_att - n_rej - ((raw & VOID_ATTEMPT) ? 1u : 0u); }
-    __device__ __forceinline__ uint32_t acc_running() const { return n_att - n_rej; }
+    __device__ __forceinline__ uint32_t acc_of(int raw) const { return n_att() - n_rej - ((raw & VOID_ATTEMPT) ? 1u : 0u); }
+    __device__ __forceinline__ uint32_t acc_running() const { return n_att() - n_rej; }
 
     // rk.rs:393-398: t += dt, y += sum_j b_j k_j
     __device__ __forceinline__ void advance(double h, const double (&k)[O][D]) {
