@@ -43,10 +43,48 @@ template <class S> struct StepperMigrates<S, decltype(void(S::STATE_DOUBLES))> {
 };
 #endif
 
+// Work hand-out: per-warp blocks of consecutive trajectories.  Why blocks: with dense output every lane stores into its
+// own trajectory's history, and ONE store instruction whose 32 lanes touch 32 different 2 MB pages is 4 times slower
+// than one whose lanes stay within a few pages (address translation; tools/hist_compute_probe.cu: 1.16 against 4.4
+// TB/s).  Lanes that each take "the next index" from one global counter end up with 32 unrelated trajectories per
+// warp; lanes that take it from their WARP's block of <= 32 consecutive indices stay neighbours (a trajectory's history
+// is cap * 8(1+D) bytes: 147 KB in config 2, so a block is 2-3 pages).  Block sizes shrink towards the end of the
+// ensemble (guided self-scheduling) so that no warp sits on unstarted work while others idle.
+// One 64-bit word per warp in shared memory: base << 16 | size << 8 | used.  Loop-free and safe under divergence: the
+// lane whose atomicAdd finds the block exactly exhausted refills it from the global counter; a lane that arrives while
+// that refill is in flight takes a single index from the global counter instead.
+struct WarpQueue {
+    unsigned long long* word;       // shared memory
+    unsigned long long* global;     // the launch's work counter
+    unsigned long long n;
+    unsigned long long per_block;   // 8 x warps of the grid: remaining / per_block = next block size
+
+    __device__ __noinline__ unsigned long long fetch() {
+        const unsigned long long s = atomicAdd(word, 1ull);
+        const unsigned used = (unsigned)(s & 0xff), size = (unsigned)((s >> 8) & 0xff);
+        if (used < size) return (s >> 16) + used;
+        if (used > size) return atomicAdd(global, 1ull);  // a refill is in flight (rare): take a single index instead
+        // used == size: this lane refills
+        const unsigned long long seen = *(volatile unsigned long long*)global;
+        const unsigned long long rem = seen < n ? n - seen : 0;
+        unsigned long long b = rem / per_block;
+        b = b < 1 ? 1 : (b > 32 ? 32 : b);
+        const unsigned long long nb = atomicAdd(global, b);
+        // (a block may reach past n, or start there when the counter is dry: callers test idx < n, and every later
+        // fetch from such a block returns an index >= n as well)
+        atomicExch(word, (nb << 16) | (b << 8) | 1ull);
+        return nb;
+    }
+    // nothing left to start in this warp's block and nothing left in the global counter
+    __device__ __forceinline__ bool dry() const {
+        const unsigned long long v = *(volatile unsigned long long*)word;
+        return (unsigned)(v & 0xff) >= (unsigned)((v >> 8) & 0xff) && *(volatile unsigned long long*)global >= n;
+    }
+};
+
 // Main kernel.  No vote and no liveness test in the loop: a lane whose trajectory ends leaves the common path on its own
-// (the branch is inside attempt()), stores its record, takes the next trajectory index with its own atomicAdd (one per
-// trajectory: ~3e7/s for the whole GPU, and the compiler aggregates lanes that arrive together) and rejoins its warp at
-// the next attempt.  A lane that finds the counter dry is done.
+// (the branch is inside attempt()), stores its record, takes the next trajectory index from its warp's block (WarpQueue)
+// and rejoins its warp at the next attempt.  A lane that finds the queue dry is done.
 //
 // Tail (steppers that migrate, `tail` != nullptr).  The lanes decohere over the run, so when the counter runs dry the
 // remaining work per lane is spread evenly between nothing and a whole trajectory; left alone, each warp would run
@@ -84,35 +122,44 @@ __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB)
         }
     };
 
+    __shared__ unsigned long long wq_words[ENSEMBLE_BLOCK / 32];
+    WarpQueue wq{&wq_words[threadIdx.x >> 5], a.work_counter, n, 8ull * (ENSEMBLE_BLOCK / 32) * gridDim.x};
+    // the first 32 trajectories of the warp: one aggregated fetch; the queue starts as an exhausted block
     unsigned long long idx = warp_fetch(a.work_counter, true);
+    if ((threadIdx.x & 31) == 0) *wq.word = (1ull << 8) | 1ull;
+    __syncwarp();
+
     if (idx >= n) {
         leave(false, 0);
         return;
     }
     s.reset(a, idx, true);
+    hist.begin(idx);
     for (;;) {
         bool yielded = false;
         const uint32_t n_acc_before = HIST ? Codec::acc_running(s) : 0u;
         const int raw = s.attempt(yielded);
-        hist.push(yielded, n_acc_before, idx, s.out_t(), s.out_y());
+        hist.push(yielded, n_acc_before, s.out_t(), s.out_y());
         if (raw != RAW_RUNNING) {  // rare
             if (raw == RAW_CHECKPOINT) {
-                if (MIGRATE && tail && *(volatile unsigned long long*)a.work_counter >= n) {
+                if (MIGRATE && tail && (HIST ? wq.dry() : *(volatile unsigned long long*)a.work_counter >= n)) {
                     leave(true, idx);  // suspend
                     return;
                 }
             } else {
                 const uint32_t n_acc = Codec::acc(s, raw);
-                hist.retire(true, idx, n_acc);
+                hist.retire(idx, n_acc);
                 int st = Codec::status(s, raw);
                 if (HIST && st == BACON_OK && n_acc > (uint32_t)a.cfg.history_capacity) st = BACON_E_HISTORY_OVERFLOW;
                 store_result<D>(a.out, n, idx, s.end_y(), s.t, s.dt, st, n_acc, s.n_rej, s.n_rhs());
-                idx = atomicAdd(a.work_counter, 1ull);
+                // (final state only: which trajectory a lane runs next does not matter — one global atomicAdd)
+                idx = HIST ? wq.fetch() : atomicAdd(a.work_counter, 1ull);
                 if (idx >= n) {
                     leave(false, 0);
                     return;
                 }
                 s.reset(a, idx, true);
+                hist.begin(idx);
             }
         }
     }
@@ -177,15 +224,16 @@ __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB)
     if (moved < 0) return;
     const unsigned long long idx = (unsigned long long)moved;
     s.load(st);
+    hist.begin(idx);
 
     for (;;) {
         bool yielded = false;
         const uint32_t n_acc_before = HIST ? Codec::acc_running(s) : 0u;
         const int raw = s.attempt(yielded);
-        hist.push(yielded, n_acc_before, idx, s.out_t(), s.out_y());
+        hist.push(yielded, n_acc_before, s.out_t(), s.out_y());
         if (raw >= 0) {
             const uint32_t n_acc = Codec::acc(s, raw);
-            hist.retire(true, idx, n_acc);
+            hist.retire(idx, n_acc);
             int stt = Codec::status(s, raw);
             if (HIST && stt == BACON_OK && n_acc > (uint32_t)a.cfg.history_capacity) stt = BACON_E_HISTORY_OVERFLOW;
             store_result<D>(a.out, a.n, idx, s.end_y(), s.t, s.dt, stt, n_acc, s.n_rej, s.n_rhs());

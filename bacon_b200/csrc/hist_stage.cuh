@@ -8,15 +8,21 @@
 // Lanes of a warp sit at different trajectories and different step counts, so nothing a warp writes in one
 // step is contiguous ACROSS lanes; what is contiguous is each lane's own record.  For D = 3 a record is
 // 32 bytes = one DRAM sector, written by the lane with a single 256-bit store (STG.E.256, sm_100): every
-// store instruction fills 32 whole sectors, no read-modify-write, no staging, one instruction per accepted
-// step.  Other dimensions use the widest stores the record's alignment allows (128-bit when 1 + D is even,
-// else 64-bit); consecutive records of a trajectory complete each other's sectors in L2 before eviction.
+// store instruction fills 32 whole sectors, and the four sectors of a 128-byte line arrive within a few
+// microseconds of each other, which is young enough for L2 to merge them into one line write.  Other
+// dimensions use the widest stores the record's alignment allows (128-bit when 1 + D is even, else 64-bit).
 //
-// History of this file: round 1 first staged 8 points per lane in shared memory (pair-interleaved layout)
-// and copied full lane buffers out warp-cooperatively into separate hist_t[n][cap] / hist_y[n][cap][D]
-// arrays.  Measured on B200 (bench_configs.py --config 2, profiles/): the copy-out loop serialised over
-// full lanes (about 100 extra warp instructions per warp step against 195 for the integrator) and capped
-// dense output at 1.2 TB/s; the record layout removes the loop altogether.
+// What decides the speed is not the store but what comes AFTER it (measured, profiles/r01i_dense_output.md).
+// Under load a store waits ~1000 cycles in the SM's memory queue before it reads its operands, and whatever
+// instruction next WRITES one of its operand registers waits with it.  The data registers are the stepper's
+// state (t, y): rewritten an attempt later, no problem.  The ADDRESS used to be a temporary computed from
+// (idx, n_acc) right before the store and recycled by the very next instruction: half of all issue slots of
+// the kernel went into that one stall (1.6 TB/s).  Now the address is a per-lane pointer that is advanced
+// right BEFORE each store, i.e. one whole attempt after the previous store was queued.  tools/
+// hist_compute_probe.cu is the synthetic twin that shows the ceiling: 128 DFMA + one such store per step
+// runs at 96 % of the FP64 rate while writing 4.4 TB/s; staging whole 128-byte lines in shared memory or
+// registers (tools/hist_write_probe.cu: needed when NOTHING separates the stores) buys nothing here and
+// was dropped, like the round-1 staging of 8 points per lane with a warp-cooperative copy-out.
 #pragma once
 #include "ivp_common.cuh"
 
@@ -26,8 +32,9 @@ template <int D, bool ENABLED> struct HistStage;
 
 template <int D> struct HistStage<D, false> {
     __device__ __forceinline__ explicit HistStage(const bacon_launch_args&) {}
-    __device__ __forceinline__ void push(bool, uint32_t, unsigned long long, double, const double (&)[D]) {}
-    __device__ __forceinline__ void retire(bool, unsigned long long, uint32_t) {}
+    __device__ __forceinline__ void begin(unsigned long long) {}
+    __device__ __forceinline__ void push(bool, uint32_t, double, const double (&)[D]) {}
+    __device__ __forceinline__ void retire(unsigned long long, uint32_t) {}
 };
 
 template <int D> struct HistStage<D, true> {
@@ -36,39 +43,41 @@ template <int D> struct HistStage<D, true> {
     double* hist;
     uint32_t* hist_len;
     uint32_t cap;
+    double* base;  // the current trajectory's first record
 
     __device__ __forceinline__ explicit HistStage(const bacon_launch_args& a) {
         hist = a.out.hist;
         hist_len = a.out.hist_len;
         cap = (uint32_t)a.cfg.history_capacity;
+        base = hist;
     }
+    // this lane now runs trajectory idx
+    __device__ __forceinline__ void begin(unsigned long long idx) { base = hist + (size_t)idx * cap * R; }
 
     // called by every lane once per step() call; lanes that yielded a point write its record
-    __device__ __forceinline__ void push(bool yielded, uint32_t n_acc_before, unsigned long long idx, double t,
-                                         const double (&y)[D]) {
+    __device__ __forceinline__ void push(bool yielded, uint32_t n_acc_before, double t, const double (&y)[D]) {
         if (!(yielded && n_acc_before < cap)) return;
-        double* dst = hist + ((size_t)idx * cap + n_acc_before) * R;
-        double rec[R];
-        rec[0] = t;
+        double* dst = base + (size_t)n_acc_before * R;
+        double r[R];
+        r[0] = t;
 #pragma unroll
-        for (int d = 0; d < D; ++d) rec[1 + d] = y[d];
+        for (int d = 0; d < D; ++d) r[1 + d] = y[d];
         if constexpr (R % 4 == 0) {  // 32-byte records: whole sectors
 #pragma unroll
             for (int j = 0; j < R; j += 4)
-                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "d"(rec[j]), "d"(rec[j + 1]),
-                             "d"(rec[j + 2]), "d"(rec[j + 3])
-                             : "memory");
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "d"(r[j]), "d"(r[j + 1]),
+                             "d"(r[j + 2]), "d"(r[j + 3]));
         } else if constexpr (R % 2 == 0) {
 #pragma unroll
-            for (int j = 0; j < R; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(rec[j], rec[j + 1]);
+            for (int j = 0; j < R; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(r[j], r[j + 1]);
         } else {
 #pragma unroll
-            for (int j = 0; j < R; ++j) dst[j] = rec[j];
+            for (int j = 0; j < R; ++j) dst[j] = r[j];
         }
     }
 
-    __device__ __forceinline__ void retire(bool fin, unsigned long long idx, uint32_t n_acc) {
-        if (fin && hist_len) hist_len[idx] = n_acc < cap ? n_acc : cap;
+    __device__ __forceinline__ void retire(unsigned long long idx, uint32_t n_acc) {
+        if (hist_len) hist_len[idx] = n_acc < cap ? n_acc : cap;
     }
 };
 

@@ -100,7 +100,12 @@ template <class Stepper, bool HIST, int MINB> inline int launch_stepper_hist(bac
 }
 
 template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* a) {
-    if (a->cfg.history_capacity > 0 && a->out.hist) return launch_stepper_hist<Stepper, true, MINB>(a);
+    // Dense output: one resident CTA fewer when the budget is tight (6 -> 5: 80 -> 96 registers).  At 80 registers
+    // ptxas re-loads launch constants (t_end, dt bounds, capacity) from the constant bank inside the loop; those loads
+    // queue behind the history stores in the SM's memory pipeline and the instructions that need them wait ~1000
+    // cycles: 1.6 TB/s of history instead of 3+ (profiles/r01i_dense_output.md).
+    constexpr int MINB_HIST = MINB >= 6 ? MINB - 1 : MINB;
+    if (a->cfg.history_capacity > 0 && a->out.hist) return launch_stepper_hist<Stepper, true, MINB_HIST>(a);
     return launch_stepper_hist<Stepper, false, MINB>(a);
 }
 
@@ -129,13 +134,15 @@ template <class Rhs, class Tab, int MINB = 1> int launch_rk_strict(bacon_launch_
 }
 
 // ---- BDF (Broyden as in the reference, or Newton + in-register LU with BACON_FLAG_BDF_NEWTON)
-template <class Rhs, class Coef, bool STRICT, int MINB = 2> int launch_bdf(bacon_launch_args* a) {
+// Resident CTAs per SM the kernels are compiled for: Newton + in-register LU fits 3 (168 registers, 8 bytes spilled);
+// the reference's Broyden iteration keeps two D x D matrices alive and stays at 2.
+template <class Rhs, class Coef, bool STRICT, int MINB = 2, int MINB_NEWTON = 3> int launch_bdf(bacon_launch_args* a) {
     if (a->cfg.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;  // REF_LITERAL BDF: CPU oracle only
     if (a->cfg.flags & BACON_FLAG_BDF_NEWTON) {
         // the strict build is the reference's own (Broyden) iteration.  `if constexpr`: a strict translation
         // unit (-fmad=false) must not instantiate a kernel that a fast one also defines under the same name.
         if constexpr (STRICT) return BACON_E_UNSUPPORTED;
-        else return launch_stepper<BdfStepper<Rhs, Coef, false, true>, MINB>(a);
+        else return launch_stepper<BdfStepper<Rhs, Coef, false, true>, MINB_NEWTON>(a);
     }
     return launch_stepper<BdfStepper<Rhs, Coef, STRICT, false>, MINB>(a);
 }

@@ -207,22 +207,24 @@ template <class Rhs, class Tab> struct RkFastStepper {
         // integers (dt > 0).
         const double rem = t_end - t;
         double h = dt;
-        tick++;
-        if (__builtin_expect((tick > next_check) | (__double2hiint(rem) <= __double2hiint(dt)), 0)) {  // rare
-            if (tick > next_check) {
-                tick0++;  // this call runs no stages
-                if (n_att() >= cap) return BACON_E_MAX_ATTEMPTS;
-                const uint32_t n = n_att();  // a checkpoint: the whole warp is here
+        if (__builtin_expect((tick >= next_check) | (__double2hiint(rem) <= __double2hiint(dt)), 0)) {  // rare
+            if (tick >= next_check) {
+                if (n_att() >= cap) {
+                    tick++, tick0++;  // a call that runs no stages
+                    return BACON_E_MAX_ATTEMPTS;
+                }
+                const uint32_t n = n_att();  // a checkpoint: the whole warp is here; the tick axis restarts
                 tick = 0;
                 rearm(n);
                 return -2;  // RAW_CHECKPOINT
             }
             if (!(t < t_end)) {  // rk.rs:362-364
-                tick0++;
+                tick++, tick0++;
                 return BACON_OK;
             }
             if (t + dt >= t_end) h = rem;  // rk.rs:366-368, the reference's own test
         }
+        tick++;
 
         // stages: k_i = h * f(t + c_i h, y + sum_j a_ij k_j)   (rk.rs:370-384)
         double k[O][D];

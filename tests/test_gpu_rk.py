@@ -174,6 +174,45 @@ def test_dense_output_matches_oracle_path(cuda, engine, oracle):
             np.testing.assert_array_equal(gpu.hist_y[np.arange(n)[ok], last[ok]], gpu.y_end[:, ok].T)
 
 
+def test_tail_kernel_and_dense_output_do_not_change_a_trajectory(cuda, engine):
+    """Scheduling must be invisible: a trajectory's numbers depend on its inputs only.  150 000 trajectories take more
+    than one per lane, so the work counter runs dry, warps suspend at a checkpoint and ensemble_tail_kernel finishes
+    them on other lanes (drive.cuh), each trajectory's history written partly by one kernel and partly by the other
+    (hist_stage.cuh); lanes take their trajectories from per-warp blocks (WarpQueue).  The same trajectories solved in
+    three smaller launches (at most one per lane: no tail) must give the same bits: final states, counters and every
+    history record."""
+    n, cap = 150_000, 512
+    y0 = E.lorenz_y0(np.arange(n))
+    s = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.15, history=cap, **LOR)
+    a = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+    assert engine.last_launch()["n_kernels"] == 2
+    assert (a.status == _abi.OK).all() and len(set(a.hist_len % 4)) == 4
+    for lo in range(0, n, 50_000):
+        b = s.solve_ivp_ensemble(np.ascontiguousarray(y0[:, lo:lo + 50_000]), LOR_P, shared_params=True)
+        assert engine.last_launch()["n_kernels"] == 1
+        sl = slice(lo, lo + 50_000)
+        for k in ("y_end", "t_end", "dt_end"):
+            assert np.array_equal(getattr(a, k)[..., sl].view(np.uint64), getattr(b, k).view(np.uint64)), k
+        for k in ("n_accept", "n_reject", "n_rhs", "hist_len"):
+            np.testing.assert_array_equal(getattr(a, k)[sl], getattr(b, k), err_msg=k)
+        assert np.array_equal(a.hist_t[sl].view(np.uint64), b.hist_t.view(np.uint64))
+        assert np.array_equal(a.hist_y[sl].view(np.uint64), b.hist_y.view(np.uint64))
+    mask = np.arange(cap)[None, :] < a.hist_len[:, None]
+    assert (a.hist_t[~mask] == 0).all() and (np.diff(a.hist_t, axis=1)[mask[:, 1:]] > 0).all()
+    last = a.hist_len.astype(np.int64) - 1
+    np.testing.assert_array_equal(a.hist_y[np.arange(n), last], a.y_end.T)
+    # final state only, and a history overflow that ends inside the tail kernel
+    s0 = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.15, **LOR)
+    c = s0.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+    assert np.array_equal(c.y_end.view(np.uint64), a.y_end.view(np.uint64))
+    s1 = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.15, history=64, **LOR)
+    d = s1.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+    over = a.n_accept > 64
+    assert over.sum() > n // 2 and (d.status[over] == _abi.E_HISTORY_OVERFLOW).all() and (d.status[~over] == _abi.OK).all()
+    np.testing.assert_array_equal(d.hist_len, np.minimum(a.n_accept, 64))
+    assert np.array_equal(d.hist_y.view(np.uint64), a.hist_y[:, :64].view(np.uint64))
+
+
 def test_failure_statuses_never_abort_the_batch(cuda, engine, oracle):
     """Per-trajectory failures land in status[i] (the reference aborts one trajectory, ivp.rs:232-235)."""
     n = 256
