@@ -57,7 +57,7 @@ struct WarpQueue {
     unsigned long long* word;       // shared memory
     unsigned long long* global;     // the launch's work counter
     unsigned long long n;
-    unsigned long long per_block;   // 8 x warps of the grid: remaining / per_block = next block size
+    unsigned long long per_block;   // BACON_WQ_DIV x warps of the grid: remaining / per_block = next block size
 
     __device__ __noinline__ unsigned long long fetch() {
         const unsigned long long s = atomicAdd(word, 1ull);
@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB)
     };
 
     __shared__ unsigned long long wq_words[ENSEMBLE_BLOCK / 32];
-    WarpQueue wq{&wq_words[threadIdx.x >> 5], a.work_counter, n, 8ull * (ENSEMBLE_BLOCK / 32) * gridDim.x};
+#ifndef BACON_WQ_DIV
+#define BACON_WQ_DIV 1  // block size = remaining / (BACON_WQ_DIV x warps of the grid), clamped to [1, 32]
+#endif
+    WarpQueue wq{&wq_words[threadIdx.x >> 5], a.work_counter, n, (unsigned long long)BACON_WQ_DIV * (ENSEMBLE_BLOCK / 32) * gridDim.x};
     // the first 32 trajectories of the warp: one aggregated fetch; the queue starts as an exhausted block
     unsigned long long idx = warp_fetch(a.work_counter, true);
     if ((threadIdx.x & 31) == 0) *wq.word = (1ull << 8) | 1ull;

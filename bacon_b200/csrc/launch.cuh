@@ -104,7 +104,10 @@ template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* 
     // ptxas re-loads launch constants (t_end, dt bounds, capacity) from the constant bank inside the loop; those loads
     // queue behind the history stores in the SM's memory pipeline and the instructions that need them wait ~1000
     // cycles: 1.6 TB/s of history instead of 3+ (profiles/r01i_dense_output.md).
-    constexpr int MINB_HIST = MINB >= 6 ? MINB - 1 : MINB;
+#ifndef BACON_HIST_MINB_DROP
+#define BACON_HIST_MINB_DROP 1
+#endif
+    constexpr int MINB_HIST = MINB >= 6 ? MINB - BACON_HIST_MINB_DROP : MINB;
     if (a->cfg.history_capacity > 0 && a->out.hist) return launch_stepper_hist<Stepper, true, MINB_HIST>(a);
     return launch_stepper_hist<Stepper, false, MINB>(a);
 }

@@ -23,3 +23,14 @@ PY
 done
 python bench_configs.py --config 5 --broyden --steps 2 --no-cpu-baseline > gpurun_out/${T}_cfg5_broyden.json 2>/dev/null
 python bench_configs.py --config 2 --steps 2 --no-cpu-baseline > gpurun_out/${T}_cfg2hist.json 2>/dev/null
+python bench_configs.py --config 2 --steps 2 --no-cpu-baseline --n 1048576 > gpurun_out/${T}_cfg2hist1m.json 2>/dev/null
+python - "$T" <<'PY'
+import json, sys
+for c in ("cfg5_broyden", "cfg2hist", "cfg2hist1m"):
+    try:
+        d = json.load(open(f"gpurun_out/{sys.argv[1]}_{c}.json"))
+        print(f"{c}: {d['value']:.4e} steps/s  {d['ms_per_pass']:.2f} ms  fp64 frac {d['roofline']['frac']:.3f}  dense {d.get('dense_output',{}).get('achieved_GBs')}")
+    except Exception as e:
+        print(c, "FAILED", e)
+PY
+ncu --set full --clock-control none --import-source on -k regex:ensemble_kernel -s 1 -c 1 -o gpurun_out/prof_cfg2hist_${T} -f python bench_configs.py --config 2 --n 1048576 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/${T}_ncu_hist.log 2>&1
