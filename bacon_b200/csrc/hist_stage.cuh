@@ -12,17 +12,14 @@
 // microseconds of each other, which is young enough for L2 to merge them into one line write.  Other
 // dimensions use the widest stores the record's alignment allows (128-bit when 1 + D is even, else 64-bit).
 //
-// What decides the speed is not the store but what comes AFTER it (measured, profiles/r01i_dense_output.md).
-// Under load a store waits ~1000 cycles in the SM's memory queue before it reads its operands, and whatever
-// instruction next WRITES one of its operand registers waits with it.  The data registers are the stepper's
-// state (t, y): rewritten an attempt later, no problem.  The ADDRESS used to be a temporary computed from
-// (idx, n_acc) right before the store and recycled by the very next instruction: half of all issue slots of
-// the kernel went into that one stall (1.6 TB/s).  Now the address is a per-lane pointer that is advanced
-// right BEFORE each store, i.e. one whole attempt after the previous store was queued.  tools/
+// What decides the speed is WHERE the 32 lanes of one store instruction write (profiles/r01i_dense_output.md):
+// 32 different 2 MB pages cost four times as much as a few pages (address translation), so the driver hands
+// trajectories out in per-warp blocks of consecutive indices (WarpQueue, drive.cuh).  tools/
 // hist_compute_probe.cu is the synthetic twin that shows the ceiling: 128 DFMA + one such store per step
-// runs at 96 % of the FP64 rate while writing 4.4 TB/s; staging whole 128-byte lines in shared memory or
-// registers (tools/hist_write_probe.cu: needed when NOTHING separates the stores) buys nothing here and
-// was dropped, like the round-1 staging of 8 points per lane with a warp-cooperative copy-out.
+// runs at 96 % of the FP64 rate while writing 4.4 TB/s when the lanes of a warp are neighbours, 1.16 TB/s
+// when they are not.  Staging whole 128-byte lines per lane in shared memory or registers (needed when
+// NOTHING separates the stores: tools/hist_write_probe.cu) buys nothing here and was dropped, like the
+// round-1 staging of 8 points per lane with a warp-cooperative copy-out into separate t / y arrays.
 #pragma once
 #include "ivp_common.cuh"
 

@@ -45,13 +45,6 @@ template <class K> inline int persistent_grid(K kernel, bacon_launch_args* a, si
     return 0;
 }
 
-template <class K> inline int launch_persistent(K kernel, bacon_launch_args* a, size_t smem) {
-    if (const int rc = persistent_grid(kernel, a, smem)) return rc;
-    a->n_kernels = 1;
-    kernel<<<(unsigned)a->grid, ENSEMBLE_BLOCK, smem, (cudaStream_t)a->stream>>>(*a);
-    return cudaGetLastError() == cudaSuccess ? 0 : BACON_E_CUDA;
-}
-
 // stream-ordered scratch for the suspended trajectories of the tail (drive.cuh): the pool keeps its memory between
 // launches (release threshold raised once per device), so this is a free-list lookup, not a cudaMalloc
 inline cudaError_t tail_scratch_alloc(double** p, size_t bytes, cudaStream_t st) {
@@ -100,10 +93,8 @@ template <class Stepper, bool HIST, int MINB> inline int launch_stepper_hist(bac
 }
 
 template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* a) {
-    // Dense output: one resident CTA fewer when the budget is tight (6 -> 5: 80 -> 96 registers).  At 80 registers
-    // ptxas re-loads launch constants (t_end, dt bounds, capacity) from the constant bank inside the loop; those loads
-    // queue behind the history stores in the SM's memory pipeline and the instructions that need them wait ~1000
-    // cycles: 1.6 TB/s of history instead of 3+ (profiles/r01i_dense_output.md).
+    // Dense output: one resident CTA fewer when the budget is tight (6 -> 5: 80 -> 96 registers, no re-loads of launch
+    // constants inside the loop).  Measured 1-2 % faster than 6 (profiles/r01i_dense_output.md).
 #ifndef BACON_HIST_MINB_DROP
 #define BACON_HIST_MINB_DROP 1
 #endif
