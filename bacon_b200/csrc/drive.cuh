@@ -39,7 +39,7 @@ constexpr int RAW_CHECKPOINT = -2;  // attempt(): nothing was computed, the whol
 template <class S, class = void> struct StepperMigrates { static constexpr bool value = false; };
 #ifndef BACON_NO_MIGRATE  // (A/B switch for measurements)
 template <class S> struct StepperMigrates<S, decltype(void(S::STATE_DOUBLES))> {
-    static constexpr bool value = (S::STATE_DOUBLES + 1) * 8 * ENSEMBLE_BLOCK <= 40 * 1024;
+    static constexpr bool value = (S::STATE_DOUBLES + 1) * 8 * (2 * ENSEMBLE_BLOCK) <= 40 * 1024;  // the tail CTA's exchange buffer
 };
 #endif
 
@@ -168,38 +168,40 @@ __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB)
     }
 }
 
-// Which quartile of the CTA's sorted trajectories a warp takes in the tail.  Measured with tools/smsp_probe.cu on
-// B200: a warp runs on sub-partition %warpid % 4 (two warps with the same value share one FP64 pipe), a 128-thread
-// CTA holds hardware warp slots 4k..4k+3 (k = %warpid / 4 = the CTA's slot on its SM), and the hardware already
-// rotates which warp of the CTA starts on sub-partition 0.  Slots 0..3 give every sub-partition each quartile once;
-// the next two slots pair quartile q with 3 - q, so with 6 resident CTAs every sub-partition gets the same work.
-__device__ __forceinline__ int tail_quartile() {
+// Which eighth of the CTA's sorted trajectories a warp takes in the tail.  Measured with tools/smsp_probe.cu on B200:
+// a warp runs on sub-partition %warpid % 4 (two warps with the same value share one FP64 pipe), a 256-thread CTA holds
+// hardware warp slots 8k..8k+7 (k = %warpid / 8 = the CTA's slot on its SM; its warps w and w+4 share a
+// sub-partition), and the hardware already rotates which warp of the CTA starts on sub-partition 0.  The two warps of
+// a CTA on sub-partition j take the octiles o and 7 - o, o = (j + k) mod 4: every sub-partition holds the same amount
+// of work whatever the number of resident CTAs, and its warps retire at evenly spread times.
+constexpr int TAIL_BLOCK = 2 * ENSEMBLE_BLOCK;
+__device__ __forceinline__ int tail_octile() {
     unsigned hw;
     asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw));
-    const int j = hw & 3, k = (hw >> 2);
-    if ((k & 7) < 4) return (j + k) & 3;
-    return (k & 1) ? 3 - j : j;
+    const int j = hw & 3, second = (hw >> 2) & 1, k = hw >> 3;
+    const int o = (j + k) & 3;
+    return second ? 7 - o : o;
 }
 
-// Tail kernel (same grid as the main kernel): the CTA sorts the 128 suspended trajectories of its slots by remaining
-// time and deals them so that each warp holds one quartile — warps retire one after the other and the sub-partitions
-// thin out — then runs them to their end, no refills.
+// Tail kernel (one CTA of 256 lanes per two CTAs of the main kernel): the CTA sorts the 256 suspended trajectories of its
+// slots by remaining time and deals them so that each warp holds one octile — warps retire one after the other and
+// the sub-partitions thin out — then runs them to their end, no refills.
 template <class Stepper, bool HIST, int MINB>
-__global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB)
-    ensemble_tail_kernel(const __grid_constant__ bacon_launch_args a, const double* __restrict__ tail) {
+__global__ void __launch_bounds__(TAIL_BLOCK, (MINB + 1) / 2)
+    ensemble_tail_kernel(const __grid_constant__ bacon_launch_args a, const double* __restrict__ tail, unsigned long long lanes) {
     constexpr int D = Stepper::D;
     using Codec = StepperCodec<Stepper>;
     constexpr int W = Stepper::STATE_DOUBLES + 1;
-    __shared__ double slots[W][ENSEMBLE_BLOCK];
-    __shared__ int keys[ENSEMBLE_BLOCK];
+    __shared__ double slots[W][TAIL_BLOCK];
+    __shared__ int keys[TAIL_BLOCK];
 
     Stepper s(a);
     HistStage<D, HIST> hist(a);
-    const size_t lanes = (size_t)gridDim.x * ENSEMBLE_BLOCK, g = (size_t)blockIdx.x * ENSEMBLE_BLOCK + threadIdx.x;
+    const size_t g = (size_t)blockIdx.x * TAIL_BLOCK + threadIdx.x;  // slot written by lane g of the main kernel
     const int me = threadIdx.x;
 
     double st[W];
-    st[W - 1] = tail[(size_t)(W - 1) * lanes + g];
+    st[W - 1] = g < lanes ? tail[(size_t)(W - 1) * lanes + g] : __longlong_as_double(-1ll);
     const bool had = __double_as_longlong(st[W - 1]) >= 0;
 #pragma unroll
     for (int w = 0; w < W - 1; ++w) st[w] = had ? tail[(size_t)w * lanes + g] : 0.0;
@@ -213,14 +215,14 @@ __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB)
     keys[me] = key;
     __syncthreads();
     int rank = 0;
-    for (int j = 0; j < ENSEMBLE_BLOCK; ++j) {
+    for (int j = 0; j < TAIL_BLOCK; ++j) {
         const int kj = keys[j];
         rank += (kj < key || (kj == key && j < me)) ? 1 : 0;
     }
 #pragma unroll
     for (int w = 0; w < W; ++w) slots[w][rank] = st[w];
     __syncthreads();
-    const int src = tail_quartile() * 32 + (me & 31);
+    const int src = tail_octile() * 32 + (me & 31);
 #pragma unroll
     for (int w = 0; w < W; ++w) st[w] = slots[w][src];
     const long long moved = __double_as_longlong(st[W - 1]);

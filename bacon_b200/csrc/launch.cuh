@@ -83,7 +83,9 @@ template <class Stepper, bool HIST, int MINB> inline int launch_stepper_hist(bac
     if (cudaGetLastError() != cudaSuccess) return BACON_E_CUDA;
     if constexpr (StepperMigrates<Stepper>::value) {
         if (tail) {
-            ensemble_tail_kernel<Stepper, HIST, MINB><<<(unsigned)a->grid, ENSEMBLE_BLOCK, 0, st>>>(*a, tail);
+            const unsigned long long lanes = (unsigned long long)a->grid * ENSEMBLE_BLOCK;
+            const unsigned tail_grid = (unsigned)((lanes + TAIL_BLOCK - 1) / TAIL_BLOCK);
+            ensemble_tail_kernel<Stepper, HIST, MINB><<<tail_grid, TAIL_BLOCK, 0, st>>>(*a, tail, lanes);
             if (cudaGetLastError() != cudaSuccess) return BACON_E_CUDA;
             a->n_kernels = 2;
             if (cudaFreeAsync(tail, st) != cudaSuccess) return BACON_E_CUDA;
