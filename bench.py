@@ -36,9 +36,10 @@ def parse():
     ap.add_argument("--t-end", type=float, default=0.0)
     ap.add_argument("--cpu-sample", type=int, default=0, help="trajectories in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-mode", default="zero_copy", choices=["staged", "zero_copy"],
+    ap.add_argument("--e2e-mode", default="auto", choices=["auto", "staged", "zero_copy"],
                     help="host-buffer C-ABI call: staged = async H2D, kernel, async D2H; zero_copy = the kernel reads/"
-                         "writes the pinned host buffers itself")
+                         "writes the pinned host buffers itself; auto = zero_copy on one GPU, staged when several ranks "
+                         "share the host (8 kernels issuing per-trajectory PCIe writes at once: 45 ms against 31.5)")
     return ap.parse_args()
 
 
@@ -234,7 +235,8 @@ def ours(args):
 
     # ---- end to end through the host-buffer C-ABI call: pinned host in, host out, copies inside the timed region
     y0_np, p_np = y0_host.numpy(), p_host.numpy()
-    zc = args.e2e_mode == "zero_copy"
+    e2e_mode = args.e2e_mode if args.e2e_mode != "auto" else ("zero_copy" if world == 1 else "staged")
+    zc = e2e_mode == "zero_copy"
     for _ in range(2):
         r = solver.solve_ivp_ensemble(y0_np, p_np, shared_params=True, zero_copy=zc)
     barrier()
@@ -298,7 +300,7 @@ def ours(args):
         "accepted_steps_per_step": acc_total, "rejected_steps_per_step": rej_total, "wall_s": t_wall,
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * float(t_e2e[0]) / args.steps, "mode": args.e2e_mode,
+                "ms_per_step": 1e3 * float(t_e2e[0]) / args.steps, "mode": e2e_mode,
                 "how": "bacon_ivp_solve_ensemble (C ABI, host buffers): pinned y0/params in, pinned result arrays "
                        "out, wall clock around the blocking calls"},
         "gpu_launches": args.steps * world * launch["n_kernels"], "clocks": sampler.summary(),
