@@ -3,9 +3,10 @@
 // One trajectory = one `solve(data)` + `IVPIterator::collect_vec` of the
 // reference (src/ivp.rs:209-238).  A kernel owns a grid of persistent lanes; a
 // lane integrates one trajectory at a time with its whole stepper state in
-// registers, and when the trajectory retires (Done / Failure) the warp ballots,
-// stores the results and pulls the next trajectory indices from a global work
-// counter with ONE atomicAdd per warp (warp-aggregated fetch).
+// registers, and when the trajectory retires (Done / Failure) the lane stores
+// its record and pulls the next trajectory index from the launch's work counter
+// (drive.cuh; the first 32 indices of a warp come from ONE warp-aggregated
+// atomicAdd, warp_fetch below; rk_warp_linear.cuh uses it throughout).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
