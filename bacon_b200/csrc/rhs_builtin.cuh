@@ -43,12 +43,6 @@ struct RhsVdp {  // Van der Pol, p = (mu)
         dy[0] = y[1];
         dy[1] = (p[0] * (1.0 - y[0] * y[0])) * y[1] - y[0];
     }
-    // k = h * f with h*mu folded once per attempt: 5 FP64 instructions per stage instead of 6
-    __device__ __forceinline__ void scaled(double h, double, const double (&y)[2], const double* p, double (&k)[2]) const {
-        const double hm = h * p[0];
-        k[0] = h * y[1];
-        k[1] = fma(hm * fma(-y[0], y[0], 1.0), y[1], -(h * y[0]));
-    }
     __device__ __forceinline__ void jac(double, const double (&y)[2], const double* p, double (&J)[2][2]) const {
         J[0][0] = 0.0;                               J[0][1] = 1.0;
         J[1][0] = -2.0 * p[0] * y[0] * y[1] - 1.0;   J[1][1] = p[0] * (1.0 - y[0] * y[0]);

@@ -213,6 +213,21 @@ def test_tail_kernel_and_dense_output_do_not_change_a_trajectory(cuda, engine):
     assert np.array_equal(d.hist_y.view(np.uint64), a.hist_y[:, :64].view(np.uint64))
 
 
+def test_work_queue_blocks_strict_history_bit_exact(cuda, engine, oracle):
+    """More trajectories than lanes with dense output: lanes refill from their warp's block of consecutive indices
+    (WarpQueue, drive.cuh), blocks shrink towards the end of the ensemble, and a ragged n leaves partial blocks.  The
+    strict kernels (no tail kernel: they do not migrate) must still match the oracle bit for bit, every record."""
+    for n in (130_001, 114_000):  # just above the 113 664 resident lanes: most lanes refill once, from small blocks
+        y0 = E.lorenz_y0(np.arange(n))
+        gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, strict=True, history=48,
+                            t_end=0.03, **LOR)
+        _assert_bit_exact(gpu, ref)
+        np.testing.assert_array_equal(gpu.hist_len, ref["hist_len"])
+        mask = np.arange(48)[None, :] < gpu.hist_len[:, None]
+        assert np.array_equal(gpu.hist_t[mask], ref["hist_t"][mask]) and np.array_equal(gpu.hist_y[mask], ref["hist_y"][mask])
+        assert (gpu.hist_t[~mask] == 0).all()
+
+
 def test_failure_statuses_never_abort_the_batch(cuda, engine, oracle):
     """Per-trajectory failures land in status[i] (the reference aborts one trajectory, ivp.rs:232-235)."""
     n = 256
