@@ -38,6 +38,10 @@ template <class K> inline int persistent_grid(K kernel, bacon_launch_args* a, si
     const long long need = (long long)((a->n + ENSEMBLE_BLOCK - 1) / ENSEMBLE_BLOCK);
     if (grid > need) grid = need;
     if (a->grid_override > 0) grid = a->grid_override;
+    if (const char* env = getenv("BACON_IVP_GRID")) {  // a small grid makes small ensembles refill, run dry and suspend
+        const int want = atoi(env);                     // (tests, compute-sanitizer runs)
+        if (want >= 1 && want < grid) grid = want;
+    }
     if (grid < 1) grid = 1;
     a->grid = (int)grid;
     a->block = ENSEMBLE_BLOCK;

@@ -228,6 +228,27 @@ def test_work_queue_blocks_strict_history_bit_exact(cuda, engine, oracle):
         assert (gpu.hist_t[~mask] == 0).all()
 
 
+def test_tiny_grid_refill_dry_suspend_tail(cuda, engine, oracle, monkeypatch):
+    """BACON_IVP_GRID caps the grid: 5 CTAs for 3000 trajectories make every lane refill several times, the counter run
+    dry, warps suspend and the tail kernel finish them — on sizes where the oracle checks every record."""
+    n = 3000
+    y0 = E.lorenz_y0(np.arange(n))
+    ref_fast = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, history=160, t_end=0.15, **LOR)[0]
+    monkeypatch.setenv("BACON_IVP_GRID", "5")
+    gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, strict=True, history=160,
+                        t_end=0.15, **LOR)
+    assert engine.last_launch()["grid"] == 5
+    _assert_bit_exact(gpu, ref)
+    mask = np.arange(160)[None, :] < gpu.hist_len[:, None]
+    assert np.array_equal(gpu.hist_t[mask], ref["hist_t"][mask]) and np.array_equal(gpu.hist_y[mask], ref["hist_y"][mask])
+    fast = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, history=160, t_end=0.15, **LOR)[0]
+    assert engine.last_launch()["n_kernels"] == 2 and engine.last_launch()["grid"] == 5
+    for k in ("y_end", "t_end", "dt_end"):  # the same bits as on the full grid, where no lane ever refilled
+        assert np.array_equal(getattr(fast, k).view(np.uint64), getattr(ref_fast, k).view(np.uint64)), k
+    np.testing.assert_array_equal(fast.n_accept, ref_fast.n_accept)
+    assert np.array_equal(fast.hist_y.view(np.uint64), ref_fast.hist_y.view(np.uint64))
+
+
 def test_failure_statuses_never_abort_the_batch(cuda, engine, oracle):
     """Per-trajectory failures land in status[i] (the reference aborts one trajectory, ivp.rs:232-235)."""
     n = 256
