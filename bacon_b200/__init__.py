@@ -6,4 +6,5 @@ solver front end over that ABI.
 """
 from . import _abi  # noqa: F401
 from .ivp import (BDF2, BDF6, RK23, RK45, Adams3, Adams5, EnsembleResult, Euler, IVPError,  # noqa: F401
-                  RungeKutta23, RungeKutta45, fp64_peak_tflops, last_launch, pinned_empty, solve_ivp)
+                  RungeKutta23, RungeKutta45, fp64_peak_tflops, last_launch, pinned_empty, register_rhs_source,
+                  solve_ivp)

@@ -1,7 +1,7 @@
 """ctypes mirror of include/bacon_ivp.h (structs, enums).  No logic here."""
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # bacon_method  (rk.rs:561, rk.rs:656, bdf.rs:706, bdf.rs:762)
 RK45, RK23, BDF6, BDF2, ADAMS5, ADAMS3, EULER = 0, 1, 2, 3, 4, 5, 6
@@ -76,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "bacon_solver_with_maximum_dt", "bacon_solver_with_minimum_dt", "bacon_solver_with_initial_time",
     "bacon_solver_with_ending_time", "bacon_solver_with_semantics", "bacon_solver_with_flags",
     "bacon_solver_with_history", "bacon_solver_with_max_attempts", "bacon_solver_config",
-    "bacon_ivp_validate", "bacon_rhs_register", "bacon_rhs_lookup", "bacon_rhs_count",
+    "bacon_ivp_validate", "bacon_rhs_register", "bacon_rhs_register_source", "bacon_rhs_lookup", "bacon_rhs_count",
     "bacon_rhs_info", "bacon_ivp_solve_ensemble", "bacon_ivp_solve_ensemble_device",
     "bacon_ivp_solve_ensemble_multi", "bacon_ivp_last_launch", "bacon_last_error",
     "bacon_status_name", "bacon_fp64_peak_tflops", "bacon_device_sm_count", "bacon_host_alloc", "bacon_host_free",

@@ -46,6 +46,7 @@ def lib():
         "bacon_ivp_validate": (i32, [cfgp]),
         "bacon_rhs_register": (i32, [vp]),
         "bacon_rhs_lookup": (i32, [C.c_char_p]),
+        "bacon_rhs_register_source": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, i32, i32]),
         "bacon_rhs_count": (i32, []),
         "bacon_rhs_info": (i32, [i32, C.POINTER(C.c_char_p), C.POINTER(i32), C.POINTER(i32)]),
         "bacon_ivp_solve_ensemble": (i32, [cfgp, i32, sz, vp, vp, resp]),

@@ -46,6 +46,10 @@ int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                    \
     } while (0)
 
+}  // namespace
+namespace bacon_internal { void set_last_error(const char* msg) { g_last_error = msg; } }  // for rtc.cu
+namespace {
+
 // ---------------------------------------------------------------- RHS registry
 struct RhsEntry {
     std::string name;

@@ -8,8 +8,10 @@
 // (drive.cuh; the first 32 indices of a warp come from ONE warp-aggregated
 // atomicAdd, warp_fetch below; rk_warp_linear.cuh uses it throughout).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "../../include/bacon_ivp.h"
 

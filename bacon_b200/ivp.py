@@ -355,6 +355,19 @@ class _Solver:
         return out
 
 
+def register_rhs_source(name, type_name, source, dim, n_params=0):
+    """A user right-hand side as CUDA C++ source text (a functor `type_name` with DIM, NPARAM and operator(), optionally
+    jac / scaled: include/bacon_ivp_rhs.cuh), compiled by the library with NVRTC and inlined into the kernels like a
+    built-in.  The device form of `with_derivative(closure)` (src/ivp.rs:186) for callers without nvcc.  Returns the
+    rhs id; afterwards `with_derivative(name)` works.  A source that does not compile raises IVPError(UserError) with
+    the compiler log."""
+    rid = lib().bacon_rhs_register_source(str(name).encode(), str(type_name).encode(), str(source).encode(), int(dim),
+                                          int(n_params))
+    if rid < 0:
+        _check(-rid)
+    return rid
+
+
 def last_launch():
     info = _abi.LaunchInfo()
     _check(lib().bacon_ivp_last_launch(C.byref(info)))

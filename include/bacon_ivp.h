@@ -16,14 +16,22 @@
 #ifndef BACON_IVP_H
 #define BACON_IVP_H
 
+#ifdef __CUDACC_RTC__ /* NVRTC has no system headers (bacon_rhs_register_source compiles user functors with it) */
+typedef signed int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+#else
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define BACON_IVP_ABI_VERSION 3
+#define BACON_IVP_ABI_VERSION 4
 
 /* ---- solver families: src/ivp/rk.rs:561 (RungeKutta45), rk.rs:656
  * (RungeKutta23), src/ivp/bdf.rs:706 (BDF6), bdf.rs:762 (BDF2),
@@ -170,6 +178,14 @@ typedef struct bacon_rhs_desc {
 
 int bacon_rhs_register(const bacon_rhs_desc*); /* returns rhs id >= 0, or -bacon_status */
 int bacon_rhs_lookup(const char* name);        /* rhs id >= 0, or -1                     */
+/* The same plug-in without nvcc on the caller's side: `source` is CUDA C++ text that defines the functor type
+ * `type_name` (contract: include/bacon_ivp_rhs.cuh); the library compiles it with NVRTC together with its own kernel
+ * headers — the right-hand side is inlined into the stage loops exactly like a built-in — one program per (method,
+ * strict/fast, dense output) actually used, cached per device.  Replaces `with_derivative(closure)` (src/ivp.rs:186)
+ * for callers that cannot run a CUDA compiler at build time.  Returns the rhs id >= 0, or -bacon_status:
+ * BACON_E_USER with the compiler log in bacon_last_error() when the source does not compile, BACON_E_UNSUPPORTED when
+ * libnvrtc / the driver are not there. */
+int bacon_rhs_register_source(const char* name, const char* type_name, const char* source, int dim, int n_params);
 int bacon_rhs_count(void);
 int bacon_rhs_info(int rhs_id, const char** name, int* dim, int* n_params);
 

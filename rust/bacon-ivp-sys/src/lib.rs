@@ -1,4 +1,4 @@
-//! Raw bindings to `include/bacon_ivp.h` (ABI version 1).  UNVERIFIED: no Rust toolchain in the build image.
+//! Raw bindings to `include/bacon_ivp.h` (ABI version 4).  UNVERIFIED: no Rust toolchain in the build image.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_double, c_int, c_void};
 
@@ -82,6 +82,9 @@ extern "C" {
     pub fn bacon_solver_config(s: *const bacon_solver, out: *mut bacon_ivp_config) -> c_int;
     pub fn bacon_ivp_validate(cfg: *const bacon_ivp_config) -> c_int;
     pub fn bacon_rhs_lookup(name: *const c_char) -> c_int;
+    /// A user right-hand side as CUDA C++ source text, compiled by the library with NVRTC (no nvcc at build time).
+    pub fn bacon_rhs_register_source(name: *const c_char, type_name: *const c_char, source: *const c_char,
+                                     dim: c_int, n_params: c_int) -> c_int;
     pub fn bacon_rhs_count() -> c_int;
     pub fn bacon_rhs_info(id: c_int, name: *mut *const c_char, dim: *mut c_int, n_params: *mut c_int) -> c_int;
     pub fn bacon_ivp_solve_ensemble(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, y0: *const c_double,

@@ -193,3 +193,32 @@ def test_every_kernel_exists_in_exactly_one_object(engine):
     assert len(entries) > 100
     dup = sorted({e for e in entries if entries.count(e) > 1})
     assert not dup, dup[:4]
+
+
+def test_runtime_compiled_rhs_is_checked_at_registration():
+    """bacon_rhs_register_source (NVRTC): a good functor registers and can be looked up, a broken one is rejected with
+    the compiler's log as IVPError(UserError) — the analogue of a `Derivative` closure that does not type-check.  No GPU
+    needed: compiling is not launching."""
+    import bacon_b200 as B
+    from bacon_b200 import _abi
+    from bacon_b200._lib import lib
+    good = """
+    struct Brusselator {
+        static constexpr int DIM = 2, NPARAM = 2;
+        __device__ void operator()(double, const double (&y)[2], const double* p, double (&dy)[2]) const {
+            dy[0] = p[0] + y[0] * y[0] * y[1] - (p[1] + 1.0) * y[0];
+            dy[1] = p[1] * y[0] - y[0] * y[0] * y[1];
+        }
+    };"""
+    try:
+        rid = B.register_rhs_source("brusselator_rtc_abi", "Brusselator", good, 2, 2)
+    except B.IVPError as e:
+        if e.code == _abi.E_UNSUPPORTED:
+            pytest.skip(f"no libnvrtc here: {e}")
+        raise
+    assert rid >= 0 and lib().bacon_rhs_lookup(b"brusselator_rtc_abi") == rid
+    with pytest.raises(B.IVPError) as bad:
+        B.register_rhs_source("broken_rtc_abi", "Broken", good.replace("Brusselator", "Broken").replace("p[1] * y[0]", "q[1] * y[0]"), 2, 2)
+    assert bad.value.code == _abi.E_USER and "q" in str(bad.value) and "undefined" in str(bad.value)
+    with pytest.raises(B.IVPError):  # DIM of the functor and of the registration must agree
+        B.register_rhs_source("wrongdim_rtc_abi", "Brusselator", good, 3, 2)

@@ -81,3 +81,69 @@ def test_single_trajectory_solve_is_the_reference_call(cuda, engine):
     with pytest.raises(engine.IVPError) as e:
         s.solve_ivp("exp")
     assert e.value.variant == "MinimumTimeDeltaExceeded" and len(e.value.path) == 1
+
+
+LORENZ_SRC = """
+struct LorenzRtc {  // p = (sigma, rho, beta): the same expression trees as the built-in
+    static constexpr int DIM = 3, NPARAM = 3;
+    __device__ void operator()(double, const double (&y)[3], const double* p, double (&dy)[3]) const {
+        dy[0] = p[0] * (y[1] - y[0]);
+        dy[1] = y[0] * (p[1] - y[2]) - y[1];
+        dy[2] = y[0] * y[1] - p[2] * y[2];
+    }
+    __device__ void scaled(double h, double, const double (&y)[3], const double* p, double (&k)[3]) const {
+        const double hs = h * p[0];
+        k[0] = hs * (y[1] - y[0]);
+        k[1] = h * (y[0] * (p[1] - y[2]) - y[1]);
+        k[2] = h * (y[0] * y[1] - p[2] * y[2]);
+    }
+    __device__ void jac(double, const double (&y)[3], const double* p, double (&J)[3][3]) const {
+        J[0][0] = -p[0];       J[0][1] = p[0];  J[0][2] = 0.0;
+        J[1][0] = p[1] - y[2]; J[1][1] = -1.0;  J[1][2] = -y[0];
+        J[2][0] = y[1];        J[2][1] = y[0];  J[2][2] = -p[2];
+    }
+};
+"""
+
+
+def test_runtime_compiled_rhs_equals_the_built_in(cuda, engine, oracle, monkeypatch):
+    """bacon_rhs_register_source: the Lorenz functor handed over as source text and compiled by NVRTC with the library's
+    own kernel headers must behave like the built-in compiled by nvcc — bit for bit with the oracle in the strict
+    kernels (history included), bit for bit with the built-in in the fast ones (same templates, same front end), through
+    every stepper family, with the tail kernel, and a source error must surface as UserError."""
+    from bacon_b200 import ensembles as E
+    from parity import run_both
+    rid = engine.register_rhs_source("lorenz_rtc", "LorenzRtc", LORENZ_SRC, 3, 3)
+    assert rid >= 0
+    P = np.array(E.LORENZ["params"])
+    LOR = dict(dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0.0)
+    n = 4000
+    y0 = E.lorenz_y0(np.arange(n))
+    # strict: oracle parity (the oracle knows the problem as "lorenz")
+    for method in ("RK45", "RK23"):
+        s = make_solver(engine, method, 3, rhs="lorenz_rtc", flags=_abi.FLAG_STRICT_FP, history=96, t_end=0.1, **LOR)
+        g = s.solve_ivp_ensemble(y0, P, shared_params=True)
+        r = oracle.solve_ensemble(getattr(_abi, method), "lorenz", y0, P, shared_params=True, history_capacity=96, pow_mode=1,
+                                  t_end=0.1, **LOR)
+        assert np.array_equal(g.y_end.view(np.uint64), r["y_end"].view(np.uint64)), method
+        np.testing.assert_array_equal(g.n_accept, r["n_accept"])
+        mask = np.arange(96)[None, :] < g.hist_len[:, None]
+        assert np.array_equal(g.hist_y[mask], r["hist_y"][mask])
+    # fast, on a tiny grid so that lanes refill and the tail kernel runs: the same bits as the built-in
+    monkeypatch.setenv("BACON_IVP_GRID", "6")
+    for method, extra in (("RK45", {}), ("RK23", {}), ("BDF6", dict(flags=_abi.FLAG_BDF_NEWTON)), ("BDF2", {}), ("Adams5", {}),
+                          ("Euler", {})):
+        cfg = dict(LOR, t_end=0.05)
+        if method.startswith("BDF") or method == "Euler":
+            cfg.update(dt_max=1e-3, tol=1e-6)
+        a = make_solver(engine, method, 3, rhs="lorenz_rtc", **extra, **cfg).solve_ivp_ensemble(y0, P, shared_params=True)
+        launch = engine.last_launch()
+        b = make_solver(engine, method, 3, rhs="lorenz", **extra, **cfg).solve_ivp_ensemble(y0, P, shared_params=True)
+        assert launch["n_kernels"] == engine.last_launch()["n_kernels"] == (2 if method.startswith("RK") else 1), method
+        np.testing.assert_array_equal(a.status, b.status, err_msg=method)
+        np.testing.assert_array_equal(a.n_accept, b.n_accept, err_msg=method)
+        assert np.array_equal(a.y_end.view(np.uint64), b.y_end.view(np.uint64)), method
+    # a functor that does not compile
+    with pytest.raises(engine.IVPError) as e:
+        engine.register_rhs_source("broken_rtc", "LorenzRtc", LORENZ_SRC.replace("p[2] * y[2];\n    }\n    __device__ void scaled", "p[2] * z;\n    }\n    __device__ void scaled"), 3, 3)
+    assert e.value.variant == "UserError" and "z" in str(e.value)
