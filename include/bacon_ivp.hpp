@@ -82,6 +82,15 @@ template <int METHOD> class Solver {
         if (rhs_ < 0) throw IVPError(BACON_E_BAD_ARGUMENT, "no right-hand side named '" + rhs_name + "'");
         return *this;
     }
+    // the closest thing to `with_derivative(closure)`: the functor as CUDA C++ source text, compiled by the library
+    // (NVRTC) and inlined into the kernels; throws IVPError(UserError) with the compiler log if it does not compile
+    Solver& with_derivative_source(const std::string& name, const std::string& type_name, const std::string& source,
+                                   int n_params) {
+        const int id = bacon_rhs_register_source(name.c_str(), type_name.c_str(), source.c_str(), dim_, n_params);
+        if (id < 0) check(-id);
+        rhs_ = id;
+        return *this;
+    }
     // README.md:33-39
     Solver& with_dt_max(double v) { return with_maximum_dt(v); }
     Solver& with_dt_min(double v) { return with_minimum_dt(v); }
