@@ -38,6 +38,13 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+// a launcher returned rc: keep the message it left (a runtime-compiled right-hand side reports the compiler log that way)
+int launch_failed(int rc, int dev) {
+    if (!g_last_error.empty()) return rc;
+    if (dev >= 0) return fail(rc, "kernel launch failed on device %d: %s", dev, cudaGetErrorString(cudaGetLastError()));
+    return fail(rc, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+
 #define CUDA_TRY(expr)                                                                          \
     do {                                                                                        \
         cudaError_t e__ = (expr);                                                               \
@@ -239,8 +246,9 @@ int launch_on_device(const bacon_ivp_config* cfg, bacon_launch_fn fn, size_t n, 
     (void)dev;
     CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     if (ev_start) CUDA_TRY(cudaEventRecord(ev_start, stream));
+    g_last_error.clear();
     const int rc = fn(&a);
-    if (rc != 0) return fail(rc, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != 0) return launch_failed(rc, -1);
     if (ev_stop) CUDA_TRY(cudaEventRecord(ev_stop, stream));
     if (filled) *filled = a;
     return 0;
@@ -571,8 +579,9 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
             ctx->next_counter = (ctx->next_counter + 1) % kCounterSlots;
             CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
             CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
+            g_last_error.clear();
             rc = fn(&a);
-            if (rc != 0) return fail(rc, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (rc != 0) return launch_failed(rc, -1);
             CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
             CUDA_TRY(cudaStreamSynchronize(st));
             float ms = 0.f;
@@ -646,8 +655,9 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
             if (cap)  // slots beyond hist_len read as zero on the host (the staging buffer is reused between calls)
                 CUDA_TRY(cudaMemsetAsync(s.dl.out.hist, 0, sizeof(double) * s.n * cap * (D + 1), st));
             CUDA_TRY(cudaEventRecord(s.ctx->ev[1], st));
+            g_last_error.clear();
             rc = fn(&a);
-            if (rc != 0) return fail(rc, "kernel launch failed on device %d: %s", s.dev, cudaGetErrorString(cudaGetLastError()));
+            if (rc != 0) return launch_failed(rc, s.dev);
             CUDA_TRY(cudaEventRecord(s.ctx->ev[2], st));
             s.filled = a;
         }

@@ -61,9 +61,17 @@ template <int D> struct HistStage<D, true> {
         for (int d = 0; d < D; ++d) r[1 + d] = y[d];
         if constexpr (R % 4 == 0) {  // 32-byte records: whole sectors
 #pragma unroll
-            for (int j = 0; j < R; j += 4)
+            for (int j = 0; j < R; j += 4) {
+#if defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ < 1209)
+                // 256-bit vector stores need PTX ISA 8.8 (CUDA 12.9): an older NVRTC (bacon_rhs_register_source picks up
+                // whatever libnvrtc.so.12 the process has) gets the same sector as two 128-bit halves
+                asm volatile("st.global.v2.f64 [%0], {%1, %2};\n\tst.global.v2.f64 [%0+16], {%3, %4};" ::"l"(dst + j), "d"(r[j]),
+                             "d"(r[j + 1]), "d"(r[j + 2]), "d"(r[j + 3]));
+#else
                 asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "d"(r[j]), "d"(r[j + 1]),
                              "d"(r[j + 2]), "d"(r[j + 3]));
+#endif
+            }
         } else if constexpr (R % 2 == 0) {
 #pragma unroll
             for (int j = 0; j < R; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(r[j], r[j + 1]);
