@@ -80,6 +80,7 @@ struct DeviceCtx {
     unsigned long long* counters = nullptr;  // ring of work counters, one per in-flight launch
     int next_counter = 0;
     cudaStream_t stream = nullptr;           // used by the host-buffer entry points
+    cudaStream_t copy_stream = nullptr;      // background DMA of the late inputs (zero-copy path)
     cudaEvent_t ev[4] = {};
     // grow-only device staging for the host-buffer entry points
     void* d_buf = nullptr;
@@ -98,6 +99,7 @@ int get_ctx(int dev, DeviceCtx** out) {
         CUDA_TRY(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, dev));
         CUDA_TRY(cudaMalloc(&c.counters, sizeof(unsigned long long) * kCounterSlots));
         CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
         for (auto& e : c.ev) CUDA_TRY(cudaEventCreate(&e));
         c.ready = true;
     }
@@ -578,12 +580,31 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
             a.work_counter = ctx->counters + ctx->next_counter;
             ctx->next_counter = (ctx->next_counter + 1) % kCounterSlots;
             CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+            // A refill over the host link costs a lane ~2 us and its 31 warp-mates wait at the loop's latch, ~9 times per
+            // lane: 0.6 ms of a 31 ms launch.  So only the FIRST trajectory of every lane is read from the caller's
+            // memory (nothing to wait for); meanwhile a DMA copies all inputs into device memory on a second stream
+            // and then raises a flag the refills check.
+            const size_t y0_bytes = sizeof(double) * (size_t)D * n, p_bytes = (shared || P == 0) ? 0 : sizeof(double) * (size_t)P * n;
+            rc = ensure_device_buf(*ctx, y0_bytes + p_bytes + 256);
+            if (rc != 0) return rc;
+            char* dbuf = (char*)ctx->d_buf;
+            unsigned int* flag = (unsigned int*)(dbuf + y0_bytes + p_bytes);
+            CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
+            CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[3], 0));
+            CUDA_TRY(cudaMemcpyAsync(dbuf, y0, y0_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (p_bytes) CUDA_TRY(cudaMemcpyAsync(dbuf + y0_bytes, params, p_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CUDA_TRY(cudaMemsetAsync(flag, 1, sizeof(unsigned int), ctx->copy_stream));
+            a.y0_late = (const double*)dbuf;
+            a.params_late = p_bytes ? (const double*)(dbuf + y0_bytes) : nullptr;
+            a.late_ready = flag;
             CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
             g_last_error.clear();
             rc = fn(&a);
             if (rc != 0) return launch_failed(rc, -1);
             CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
             CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
             float ms = 0.f;
             CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
             g_last_launch.kernel_ms = ms;

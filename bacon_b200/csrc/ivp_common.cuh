@@ -29,6 +29,13 @@ struct bacon_launch_args {
     int32_t grid_override;             // >0: force this grid (tests)
     // filled by the launcher
     int32_t grid, block, regs_per_thread, n_kernels;
+    // Late inputs (zero-copy host path): trajectories >= late_from are read from y0_late / params_late (a device copy
+    // that a DMA fills while the first trajectories, read straight from the caller's pinned memory, already run)
+    // once *late_ready != 0.  All NULL / 0 otherwise.  late_from is set by the launcher (= the lanes of the grid).
+    const double* y0_late;
+    const double* params_late;
+    const unsigned int* late_ready;
+    unsigned long long late_from;
 };
 
 namespace bacon {
@@ -84,17 +91,31 @@ __device__ __forceinline__ void store_result(const bacon_ivp_result& o, unsigned
     if (o.n_rhs) o.n_rhs[i] = n_rhs;
 }
 
+// (not inlined: a loop inside the persistent loop's body makes ptxas re-load the tableau from the constant bank on every
+// attempt instead of keeping it in uniform registers)
+static __device__ __noinline__ void wait_until_set(const unsigned int* flag) {
+    while (*(volatile const unsigned int*)flag == 0) {
+    }
+}
+
 template <int D, int P>
 __device__ __forceinline__ void load_problem(const bacon_launch_args& a, unsigned long long i,
                                              double (&y)[D], double (&p)[(P > 0 ? P : 1)]) {
+    const double* y0 = a.y0;
+    const double* params = a.params;
+    if (a.y0_late && i >= a.late_from) {  // a refill on the zero-copy host path: the DMA-ed copy, not the host link
+        wait_until_set(a.late_ready);
+        y0 = a.y0_late;
+        if (a.params_late) params = a.params_late;
+    }
 #pragma unroll
-    for (int d = 0; d < D; ++d) y[d] = a.y0[(size_t)d * a.n + i];
+    for (int d = 0; d < D; ++d) y[d] = y0[(size_t)d * a.n + i];
     if constexpr (P > 0) {
         const bool shared = (a.cfg.flags & BACON_FLAG_SHARED_PARAMS) != 0;
         const bool aos = (a.cfg.flags & BACON_FLAG_PARAMS_AOS) != 0;
 #pragma unroll
         for (int k = 0; k < P; ++k)
-            p[k] = shared ? a.params[k] : (aos ? a.params[(size_t)i * P + k] : a.params[(size_t)k * a.n + i]);
+            p[k] = shared ? params[k] : (aos ? params[(size_t)i * P + k] : params[(size_t)k * a.n + i]);
     }
 }
 

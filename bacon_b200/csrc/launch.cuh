@@ -46,6 +46,7 @@ template <class K> inline int persistent_grid(K kernel, bacon_launch_args* a, si
     a->grid = (int)grid;
     a->block = ENSEMBLE_BLOCK;
     a->regs_per_thread = fa.numRegs;
+    a->late_from = (unsigned long long)grid * ENSEMBLE_BLOCK;  // the first trajectory of every lane comes before this
     return 0;
 }
 

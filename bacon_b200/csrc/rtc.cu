@@ -284,6 +284,7 @@ int rtc_launch(int slot, bacon_launch_args* a) {
     a->block = BLOCK;
     a->regs_per_thread = regs;
     a->n_kernels = 1;
+    a->late_from = (unsigned long long)grid * BLOCK;
     CUstream st = (CUstream)a->stream;
     if (v.tableau) {  // strict RK: the tableau as the stepper's row_iter() sees it, either semantics (launch_rk_strict)
         bacon::RkTableauRt T;
