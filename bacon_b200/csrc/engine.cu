@@ -228,25 +228,33 @@ int check_common(const bacon_ivp_config* cfg, int rhs_id, const double* y0, cons
     return 0;
 }
 
+// What every launch needs: the problem, the stream, and a zeroed work counter from the context's ring.  The caller
+// holds g_ctx_mu.
+int fill_args_locked(bacon_launch_args& a, const bacon_ivp_config* cfg, size_t n, const double* y0, const double* params,
+                     const bacon_ivp_result& out, cudaStream_t stream, DeviceCtx& ctx) {
+    a = bacon_launch_args{};
+    a.cfg = *cfg;
+    a.n = n;
+    a.y0 = y0;
+    a.params = params;
+    a.out = out;
+    a.stream = stream;
+    a.sm_count = ctx.sm_count;
+    a.work_counter = ctx.counters + ctx.next_counter;
+    ctx.next_counter = (ctx.next_counter + 1) % kCounterSlots;
+    CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
+    return 0;
+}
+
 int launch_on_device(const bacon_ivp_config* cfg, bacon_launch_fn fn, size_t n, const double* d_y0,
                      const double* d_params, const bacon_ivp_result* d_out, cudaStream_t stream, int dev,
                      DeviceCtx& ctx, cudaEvent_t ev_start, cudaEvent_t ev_stop, bacon_launch_args* filled) {
-    bacon_launch_args a{};
-    a.cfg = *cfg;
-    a.n = n;
-    a.y0 = d_y0;
-    a.params = d_params;
-    a.out = *d_out;
-    a.stream = stream;
-    a.sm_count = ctx.sm_count;
-    a.grid_override = 0;
+    bacon_launch_args a;
     {
         std::lock_guard<std::mutex> lk(g_ctx_mu);
-        a.work_counter = ctx.counters + ctx.next_counter;
-        ctx.next_counter = (ctx.next_counter + 1) % kCounterSlots;
+        if (const int rc = fill_args_locked(a, cfg, n, d_y0, d_params, *d_out, stream, ctx)) return rc;
     }
     (void)dev;
-    CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), stream));
     if (ev_start) CUDA_TRY(cudaEventRecord(ev_start, stream));
     g_last_error.clear();
     const int rc = fn(&a);
@@ -569,17 +577,9 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
             rc = get_ctx(dev0, &ctx);
             if (rc != 0) return rc;
             cudaStream_t st = ctx->stream;
-            bacon_launch_args a{};
-            a.cfg = *cfg;
-            a.n = n;
-            a.y0 = (const double*)zy0;
-            a.params = (const double*)zp;
-            a.out = z;
-            a.stream = st;
-            a.sm_count = ctx->sm_count;
-            a.work_counter = ctx->counters + ctx->next_counter;
-            ctx->next_counter = (ctx->next_counter + 1) % kCounterSlots;
-            CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+            bacon_launch_args a;
+            rc = fill_args_locked(a, cfg, n, (const double*)zy0, (const double*)zp, z, st, *ctx);
+            if (rc != 0) return rc;
             // A refill over the host link costs a lane ~2 us and its 31 warp-mates wait at the loop's latch, ~9 times per
             // lane: 0.6 ms of a 31 ms launch.  So only the FIRST trajectory of every lane is read from the caller's
             // memory (nothing to wait for); meanwhile a DMA copies all inputs into device memory on a second stream
@@ -661,18 +661,9 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
             CUDA_TRY(cudaMemcpyAsync(s.dl.params, src_p, sizeof(double) * (shared ? (size_t)P : (size_t)P * s.n),
                                      cudaMemcpyHostToDevice, st));
         {
-            // launch_on_device takes g_ctx_mu for the counter ring; we already hold it -> inline the ring step
-            bacon_launch_args a{};
-            a.cfg = *cfg;
-            a.n = s.n;
-            a.y0 = s.dl.y0;
-            a.params = s.dl.params;
-            a.out = s.dl.out;
-            a.stream = st;
-            a.sm_count = s.ctx->sm_count;
-            a.work_counter = s.ctx->counters + s.ctx->next_counter;
-            s.ctx->next_counter = (s.ctx->next_counter + 1) % kCounterSlots;
-            CUDA_TRY(cudaMemsetAsync(a.work_counter, 0, sizeof(unsigned long long), st));
+            bacon_launch_args a;  // (g_ctx_mu is held: lk_all)
+            rc = fill_args_locked(a, cfg, s.n, s.dl.y0, s.dl.params, s.dl.out, st, *s.ctx);
+            if (rc != 0) return rc;
             if (cap)  // slots beyond hist_len read as zero on the host (the staging buffer is reused between calls)
                 CUDA_TRY(cudaMemsetAsync(s.dl.out.hist, 0, sizeof(double) * s.n * cap * (D + 1), st));
             CUDA_TRY(cudaEventRecord(s.ctx->ev[1], st));

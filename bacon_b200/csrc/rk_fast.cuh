@@ -147,6 +147,7 @@ template <class Rhs, class Tab> struct RkFastStepper {
     // tick > next_check, enforces max_attempts.  Accepted = attempts - n_rej (- 1 when the trajectory failed in an
     // attempt that counts neither way: see attempt()).
     static constexpr uint32_t CHECK_EVERY = 64;
+    static constexpr bool UNROLL_DRIVER = true;  // drive.cuh: two attempts per loop iteration
     uint32_t tick, tick0, next_check, n_rej;
     static constexpr int VOID_ATTEMPT = 0x100;  // ORed into the status attempt() returns: the last attempt counts neither way
 
