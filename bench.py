@@ -141,7 +141,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.02)
 
     def summary(self):
         med = float(np.median(self.samples)) if self.samples else None
