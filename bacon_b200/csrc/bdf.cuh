@@ -112,9 +112,24 @@ template <int D, bool STRICT> __device__ __forceinline__ bool inverse_lu_partial
     return ok;
 }
 
+// 1/x for the Newton path's pivots: SFU seed (2^-23) + two Newton steps, 5 instructions against the ~20 of an IEEE
+// division; relative error ~1e-14 on normal x (a Newton iteration's linear solve needs far less), 0 or inf for
+// zero / overflow like the division.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e0 = fma(-x, r, 1.0);
+    r = fma(r, e0, r);
+    const double e1 = fma(-x, r, 1.0);
+    return fma(r, e1, r);
+}
+
 // In-register partial-pivot LU solve of M x = b (Newton path); M is destroyed.  false = singular.
+// One reciprocal per pivot, reused by the back substitution (an FP64 division is a ~15-instruction dependent chain,
+// and this kernel is latency-bound: profiles/r01k notes in launch.cuh).
 template <int D> __device__ __forceinline__ bool lu_solve(double (&M)[D][D], double (&b)[D]) {
     bool ok = true;
+    double inv_diag[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) {
         int piv = i;
@@ -133,10 +148,10 @@ template <int D> __device__ __forceinline__ bool lu_solve(double (&M)[D][D], dou
                 const double tb = b[i]; b[i] = b[r]; b[r] = tb;
             }
         }
-        const double inv_diag = 1.0 / M[i][i];
+        inv_diag[i] = fast_rcp(M[i][i]);
 #pragma unroll
         for (int r = i + 1; r < D; ++r) {
-            const double l = M[r][i] * inv_diag;
+            const double l = M[r][i] * inv_diag[i];
 #pragma unroll
             for (int c = i + 1; c < D; ++c) M[r][c] = fma(-l, M[i][c], M[r][c]);
             b[r] = fma(-l, b[i], b[r]);
@@ -147,7 +162,7 @@ template <int D> __device__ __forceinline__ bool lu_solve(double (&M)[D][D], dou
         double s = b[i];
 #pragma unroll
         for (int c = i + 1; c < D; ++c) s = fma(-M[i][c], b[c], s);
-        b[i] = s / M[i][i];
+        b[i] = s * inv_diag[i];
     }
     return ok;
 }
@@ -342,17 +357,34 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
         }
     }
 
-    // Newton on g with an in-register LU of g'(x) = I - dt*beta*J_f(tg, x)
+    // Newton on g with an in-register LU of g'(x) = I - dt*beta*J_f(tg, x).  The history part of g (bdf.rs:553-559),
+    // sum_ind coef[ind] * prev[O - ind], does not depend on x: it is summed once per solve, so an evaluation of g is
+    // the right-hand side plus two FMAs per component and the 7-deep history is dead while Newton iterates.
     template <bool HIGHER> __device__ __forceinline__ int newton(double (&res)[D]) {
         const double tg = t + dt;
         const double beta = HIGHER ? Coef::higher(0) : Coef::lower(0);
         const double hb = dt * beta;
-        double x[D];
+        double x[D], hsum[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) x[d] = y[d];
+        for (int d = 0; d < D; ++d) {
+            x[d] = y[d];
+            double sp = 0.0;
+            static_for<1, O>([&](auto I) {
+                constexpr int ind = decltype(I)::value;
+                constexpr double c = HIGHER ? Coef::higher(ind) : Coef::lower(ind);
+                if constexpr (c != 0.0) sp = fma(hy[O - ind][d], c, sp);
+            });
+            hsum[d] = sp;
+        }
+        auto g_of = [&](const double (&at)[D], double (&out)[D]) {
+            double dy[D];
+            f(tg, at, dy);
+#pragma unroll
+            for (int d = 0; d < D; ++d) out[d] = fma(-hb, dy[d], at[d] + hsum[d]);
+        };
         for (int n = 2; n < 1000; ++n) {
             double g[D], M[D][D];
-            g_eval<HIGHER>(tg, x, g);
+            g_of(x, g);
             if constexpr (has_jac<Rhs>::value) {
                 Rhs{}.jac(tg, x, p, M);
 #pragma unroll
@@ -367,9 +399,9 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
 #pragma unroll
                     for (int d = 0; d < D; ++d) xa[d] = x[d];
                     xa[c] = x[c] + dt;
-                    g_eval<HIGHER>(tg, xa, up);
+                    g_of(xa, up);
                     xa[c] = x[c] - dt;
-                    g_eval<HIGHER>(tg, xa, dn);
+                    g_of(xa, dn);
 #pragma unroll
                     for (int r = 0; r < D; ++r) M[r][c] = (up[r] - dn[r]) * inv2h;
                 }
