@@ -491,9 +491,12 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
             const double df = A::sub(hi[d], lo[d]);
             ss = A::madd(df, df, ss);
         }
-        const double error = sqrt(ss);
+        // error = ||hi - lo||_2 (:580-581).  The fast build compares squares (no square root on the path); the strict one
+        // takes the root like the oracle.
+        const double error = STRICT ? sqrt(ss) : ss;
+        const double tol_cmp = STRICT ? tol : tol * tol, tenth_cmp = STRICT ? A::mul(0.1, tol) : 0.01 * (tol * tol);
 
-        if (error <= tol) {  // :583-613
+        if (error <= tol_cmp) {  // :583-613
 #pragma unroll
             for (int d = 0; d < D; ++d) y[d] = hi[d];
             t = A::add(t, dt);
@@ -502,7 +505,7 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
                 return -1;  // Redo: the warm-up points are yielded first
             }
             push_pop(t, y);
-            if (error < A::mul(0.1, tol)) {  // :602-611
+            if (error < tenth_cmp) {  // :602-611
                 dt = A::mul(dt, 2.0);
                 if (dt > dt_max) dt = dt_max;
                 have = false;
