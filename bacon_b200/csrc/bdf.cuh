@@ -126,7 +126,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 
 // In-register partial-pivot LU solve of M x = b (Newton path); M is destroyed.  false = singular.
 // One reciprocal per pivot, reused by the back substitution (an FP64 division is a ~15-instruction dependent chain,
-// and this kernel is latency-bound: profiles/r01k notes in launch.cuh).
+// and this kernel is latency-bound: DESIGN.md §4, K3).
 template <int D> __device__ __forceinline__ bool lu_solve(double (&M)[D][D], double (&b)[D]) {
     bool ok = true;
     double inv_diag[D];

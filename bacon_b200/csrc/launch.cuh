@@ -135,9 +135,9 @@ template <class Rhs, class Tab, int MINB = 1> int launch_rk_strict(bacon_launch_
 }
 
 // ---- BDF (Broyden as in the reference, or Newton + in-register LU with BACON_FLAG_BDF_NEWTON)
-// Resident CTAs per SM the kernels are compiled for.  Newton + in-register LU: 4 (128 registers, ~140 bytes spilled on
+// Resident CTAs per SM the kernels are compiled for.  Newton + in-register LU: 4 (128 registers, ~170 bytes spilled on
 // cold paths) — the kernel is latency-bound (ncu: 3 warps per sub-partition at 168 registers, 45 % of stalls are
-// fixed-latency waits), measured 7.38e10 steps/s against 7.00e10 at 3 and 7.09e10 at 5.  The reference's Broyden
+// fixed-latency waits), measured 7.38e10 steps/s against 7.00e10 at 3 and 7.09e10 at 5 (DESIGN.md §4, K3).  The reference's Broyden
 // iteration keeps two D x D matrices alive and stays at 2.
 template <class Rhs, class Coef, bool STRICT, int MINB = 2, int MINB_NEWTON = 4> int launch_bdf(bacon_launch_args* a) {
     if (a->cfg.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;  // REF_LITERAL BDF: CPU oracle only
