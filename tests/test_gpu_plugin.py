@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture(scope="module")
 def user_lib(engine):
     so = os.path.join(ROOT, "examples", "libuser_rhs.so")
-    if not os.path.exists(so):
-        subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True)
+    # always through make: the plug-in is compiled against the library's headers and must follow them
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True)
     from bacon_b200._lib import lib
     lib()
     return C.CDLL(so, mode=C.RTLD_GLOBAL)
