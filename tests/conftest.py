@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+os.environ.setdefault("BACON_IVP_SENTINEL", "1")  # status arrays start at -1: a trajectory the kernels lost would show
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
