@@ -1,7 +1,7 @@
 """ctypes mirror of include/bacon_ivp.h (structs, enums).  No logic here."""
 import ctypes as C
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # bacon_method  (rk.rs:561, rk.rs:656, bdf.rs:706, bdf.rs:762)
 RK45, RK23, BDF6, BDF2, ADAMS5, ADAMS3, EULER = 0, 1, 2, 3, 4, 5, 6
@@ -80,4 +80,6 @@ EXPORTED_SYMBOLS = [
     "bacon_rhs_info", "bacon_ivp_solve_ensemble", "bacon_ivp_solve_ensemble_device",
     "bacon_ivp_solve_ensemble_multi", "bacon_ivp_last_launch", "bacon_last_error",
     "bacon_status_name", "bacon_fp64_peak_tflops", "bacon_device_sm_count", "bacon_host_alloc", "bacon_host_free",
+    "bacon_ivp_sample_paths", "bacon_ivp_sample_paths_device", "bacon_ivp_locate_events",
+    "bacon_ivp_locate_events_device",
 ]

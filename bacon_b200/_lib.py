@@ -59,6 +59,10 @@ def lib():
         "bacon_device_sm_count": (i32, []),
         "bacon_host_alloc": (vp, [sz]),
         "bacon_host_free": (None, [vp]),
+        "bacon_ivp_sample_paths": (i32, [cfgp, i32, sz, vp, vp, resp, sz, vp, vp]),
+        "bacon_ivp_sample_paths_device": (i32, [cfgp, i32, sz, vp, vp, resp, sz, vp, vp, vp]),
+        "bacon_ivp_locate_events": (i32, [cfgp, i32, sz, vp, vp, resp, vp, dbl, i32, i32, vp, vp]),
+        "bacon_ivp_locate_events_device": (i32, [cfgp, i32, sz, vp, vp, resp, vp, dbl, i32, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -22,6 +22,7 @@
 
 #include "../../include/bacon_ivp.h"
 #include "ivp_common.cuh"
+#include "path_query.cuh"
 
 namespace {
 
@@ -62,6 +63,7 @@ struct RhsEntry {
     std::string name;
     int dim, n_params;
     bacon_launch_fn launch[2][BACON_N_METHODS];
+    bacon_path_fn path_query[2];
 };
 struct Registry {
     std::mutex mu;
@@ -444,6 +446,8 @@ int bacon_rhs_register(const bacon_rhs_desc* d) {
             for (int s = 0; s < 2; ++s)
                 for (int m = 0; m < BACON_N_METHODS; ++m)
                     if (d->launch[s][m]) e.launch[s][m] = d->launch[s][m];
+            for (int s = 0; s < 2; ++s)
+                if (d->path_query[s]) e.path_query[s] = d->path_query[s];
             return (int)i;
         }
     }
@@ -452,6 +456,7 @@ int bacon_rhs_register(const bacon_rhs_desc* d) {
     e.dim = d->dim;
     e.n_params = d->n_params;
     std::memcpy(e.launch, d->launch, sizeof(e.launch));
+    std::memcpy(e.path_query, d->path_query, sizeof(e.path_query));
     r.entries.push_back(e);
     return (int)r.entries.size() - 1;
 }
@@ -737,6 +742,222 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
     g_last_launch.regs_per_thread = shards[0].filled.regs_per_thread;
     g_last_launch.n_kernels = G * shards[0].filled.n_kernels;
     return 0;
+}
+
+// ---------------------------------------------------------------- queries on stored paths
+}  // extern "C"
+namespace {
+
+struct PathQuery {
+    int op;
+    size_t n_times;
+    const double* times;
+    double* samples;
+    const double* w;  // host, [dim]
+    double c;
+    int direction, capacity;
+    double* events;
+    uint32_t* n_events;
+};
+
+int path_query_check(const bacon_ivp_config* cfg, int rhs_id, const double* y0, const double* params,
+                     const bacon_ivp_result* solved, const PathQuery& q, RhsEntry* entry, bacon_path_fn* fn) {
+    if (!cfg || !solved) return fail(BACON_E_BAD_ARGUMENT, "cfg and the solved result must not be NULL");
+    const int v = bacon_ivp_validate(cfg);
+    if (v != 0) return v;
+    {
+        Registry& r = registry();
+        std::lock_guard<std::mutex> lk(r.mu);
+        if (rhs_id < 0 || rhs_id >= (int)r.entries.size()) return fail(BACON_E_BAD_ARGUMENT, "unknown rhs id %d", rhs_id);
+        *entry = r.entries[rhs_id];
+    }
+    if (cfg->dim != entry->dim || cfg->n_params != entry->n_params)
+        return fail(BACON_E_BAD_ARGUMENT, "cfg (dim %d, n_params %d) does not match rhs '%s' (%d, %d)", cfg->dim,
+                    cfg->n_params, entry->name.c_str(), entry->dim, entry->n_params);
+    if (cfg->history_capacity <= 0 || !solved->hist || !solved->hist_len)
+        return fail(BACON_E_BAD_ARGUMENT, "a path query needs the history of a dense-output solve (history_capacity > 0, hist, hist_len)");
+    if (!y0) return fail(BACON_E_BAD_ARGUMENT, "y0 is required (knot 0 of every path)");
+    if (entry->n_params > 0 && !params) return fail(BACON_E_BAD_ARGUMENT, "rhs '%s' needs params", entry->name.c_str());
+    if (q.op == BACON_PATH_SAMPLE) {
+        if (q.n_times > 0 && (!q.times || !q.samples)) return fail(BACON_E_BAD_ARGUMENT, "times and samples are required");
+    } else {
+        if (!q.w || !q.n_events) return fail(BACON_E_BAD_ARGUMENT, "w and n_events are required");
+        if (q.capacity < 0 || (q.capacity > 0 && !q.events)) return fail(BACON_E_BAD_ARGUMENT, "capacity > 0 needs events");
+        if (q.direction < -1 || q.direction > 1) return fail(BACON_E_BAD_ARGUMENT, "direction must be -1, 0 or +1");
+        if (cfg->dim > BACON_PATH_MAX_DIM) return fail(BACON_E_UNSUPPORTED, "events: dim <= %d", BACON_PATH_MAX_DIM);
+    }
+    const int strict = ((cfg->flags & BACON_FLAG_STRICT_FP) || cfg->semantics == BACON_SEM_LITERAL) ? 1 : 0;
+    *fn = entry->path_query[strict] ? entry->path_query[strict] : entry->path_query[1 - strict];
+    if ((cfg->flags & BACON_FLAG_STRICT_FP) && !entry->path_query[1]) *fn = nullptr;  // strict was asked for by name
+    if (!*fn)
+        return fail(BACON_E_UNSUPPORTED, "rhs '%s' has no path-query kernels (%s build)", entry->name.c_str(),
+                    strict ? "strict" : "fast");
+    return 0;
+}
+
+int path_query_device(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* d_y0, const double* d_params,
+                      const bacon_ivp_result* d_solved, const PathQuery& q, void* stream) {
+    RhsEntry entry;
+    bacon_path_fn fn = nullptr;
+    int rc = path_query_check(cfg, rhs_id, d_y0, d_params, d_solved, q, &entry, &fn);
+    if (rc != 0) return rc;
+    g_last_launch = bacon_ivp_launch_info{};
+    if (n == 0 || (q.op == BACON_PATH_SAMPLE && q.n_times == 0)) return 0;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(BACON_E_UNSUPPORTED, "device ordinal %d", dev);
+    if (!g_tl.start[dev]) {
+        CUDA_TRY(cudaEventCreate(&g_tl.start[dev]));
+        CUDA_TRY(cudaEventCreate(&g_tl.stop[dev]));
+    }
+    bacon_path_args a{};
+    a.cfg = *cfg;
+    a.n = n;
+    a.y0 = d_y0;
+    a.params = d_params;
+    a.hist = d_solved->hist;
+    a.hist_len = d_solved->hist_len;
+    if (d_solved->t_end && d_solved->y_end) {
+        a.t_end = d_solved->t_end;
+        a.y_end = d_solved->y_end;
+    }
+    a.op = q.op;
+    a.n_times = q.n_times;
+    a.times = q.times;
+    a.samples = q.samples;
+    if (q.op == BACON_PATH_EVENTS) {
+        for (int d = 0; d < cfg->dim; ++d) a.ev_w[d] = q.w[d];
+        a.ev_c = q.c;
+        a.ev_direction = q.direction;
+        a.ev_capacity = q.capacity;
+        a.events = q.events;
+        a.n_events = q.n_events;
+    }
+    a.stream = stream;
+    CUDA_TRY(cudaEventRecord(g_tl.start[dev], (cudaStream_t)stream));
+    g_last_error.clear();
+    rc = fn(&a);
+    if (rc != 0) return launch_failed(rc, dev);
+    CUDA_TRY(cudaEventRecord(g_tl.stop[dev], (cudaStream_t)stream));
+    g_tl.last_dev = dev;
+    g_tl.pending = true;
+    g_last_launch.grid = a.grid;
+    g_last_launch.block = a.block;
+    g_last_launch.regs_per_thread = a.regs_per_thread;
+    g_last_launch.n_kernels = 1;
+    return 0;
+}
+
+// plain device allocation for the host variants (queries are not on the timed path of anything)
+struct DevBlock {
+    void* p = nullptr;
+    ~DevBlock() {
+        if (p) cudaFree(p);
+    }
+    int put(const void* host, size_t bytes) {
+        CUDA_TRY(cudaMalloc(&p, bytes ? bytes : 1));
+        if (host && bytes) CUDA_TRY(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    int get(void* host, size_t bytes) const {
+        if (host && bytes) CUDA_TRY(cudaMemcpy(host, p, bytes, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+};
+
+int path_query_host(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0, const double* params,
+                    const bacon_ivp_result* solved, const PathQuery& q) {
+    RhsEntry entry;
+    bacon_path_fn fn = nullptr;
+    int rc = path_query_check(cfg, rhs_id, y0, params, solved, q, &entry, &fn);
+    if (rc != 0) return rc;
+    if (n == 0 || (q.op == BACON_PATH_SAMPLE && q.n_times == 0)) return 0;
+    const size_t dim = (size_t)cfg->dim, cap = (size_t)cfg->history_capacity, np = (size_t)cfg->n_params;
+    DevBlock b_y0, b_par, b_hist, b_len, b_tend, b_yend, b_times, b_out, b_cnt;
+    if ((rc = b_y0.put(y0, 8 * dim * n))) return rc;
+    if (np > 0 && (rc = b_par.put(params, 8 * np * ((cfg->flags & BACON_FLAG_SHARED_PARAMS) ? 1 : n)))) return rc;
+    if ((rc = b_hist.put(solved->hist, 8 * n * cap * (1 + dim)))) return rc;
+    if ((rc = b_len.put(solved->hist_len, 4 * n))) return rc;
+    bacon_ivp_result d{};
+    d.hist = (double*)b_hist.p;
+    d.hist_len = (uint32_t*)b_len.p;
+    if (solved->t_end && solved->y_end) {
+        if ((rc = b_tend.put(solved->t_end, 8 * n))) return rc;
+        if ((rc = b_yend.put(solved->y_end, 8 * dim * n))) return rc;
+        d.t_end = (double*)b_tend.p;
+        d.y_end = (double*)b_yend.p;
+    }
+    PathQuery dq = q;
+    size_t out_bytes = 0;
+    if (q.op == BACON_PATH_SAMPLE) {
+        if ((rc = b_times.put(q.times, 8 * q.n_times))) return rc;
+        out_bytes = 8 * n * q.n_times * dim;
+        if ((rc = b_out.put(nullptr, out_bytes))) return rc;
+        dq.times = (const double*)b_times.p;
+        dq.samples = (double*)b_out.p;
+    } else {
+        out_bytes = 8 * n * (size_t)q.capacity * (1 + dim);
+        if ((rc = b_out.put(nullptr, out_bytes))) return rc;
+        if ((rc = b_cnt.put(nullptr, 4 * n))) return rc;
+        if (out_bytes) CUDA_TRY(cudaMemset(b_out.p, 0, out_bytes));
+        dq.events = (double*)b_out.p;
+        dq.n_events = (uint32_t*)b_cnt.p;
+    }
+    rc = path_query_device(cfg, rhs_id, n, (const double*)b_y0.p, (const double*)b_par.p, &d, dq, nullptr);
+    if (rc != 0) return rc;
+    CUDA_TRY(cudaStreamSynchronize(nullptr));
+    if (q.op == BACON_PATH_SAMPLE) return b_out.get(q.samples, out_bytes);
+    if ((rc = b_out.get(q.events, out_bytes))) return rc;
+    return b_cnt.get(q.n_events, 4 * n);
+}
+
+}  // namespace
+extern "C" {
+
+int bacon_ivp_sample_paths_device(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* d_y0,
+                                  const double* d_params, const bacon_ivp_result* d_solved, size_t n_times,
+                                  const double* d_times, double* d_samples, void* stream) {
+    PathQuery q{};
+    q.op = BACON_PATH_SAMPLE;
+    q.n_times = n_times;
+    q.times = d_times;
+    q.samples = d_samples;
+    return path_query_device(cfg, rhs_id, n, d_y0, d_params, d_solved, q, stream);
+}
+int bacon_ivp_sample_paths(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0, const double* params,
+                           const bacon_ivp_result* solved, size_t n_times, const double* times, double* samples) {
+    PathQuery q{};
+    q.op = BACON_PATH_SAMPLE;
+    q.n_times = n_times;
+    q.times = times;
+    q.samples = samples;
+    return path_query_host(cfg, rhs_id, n, y0, params, solved, q);
+}
+int bacon_ivp_locate_events_device(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* d_y0,
+                                   const double* d_params, const bacon_ivp_result* d_solved, const double* w, double c,
+                                   int direction, int capacity, double* d_events, uint32_t* d_n_events, void* stream) {
+    PathQuery q{};
+    q.op = BACON_PATH_EVENTS;
+    q.w = w;
+    q.c = c;
+    q.direction = direction;
+    q.capacity = capacity;
+    q.events = d_events;
+    q.n_events = d_n_events;
+    return path_query_device(cfg, rhs_id, n, d_y0, d_params, d_solved, q, stream);
+}
+int bacon_ivp_locate_events(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0, const double* params,
+                            const bacon_ivp_result* solved, const double* w, double c, int direction, int capacity,
+                            double* events, uint32_t* n_events) {
+    PathQuery q{};
+    q.op = BACON_PATH_EVENTS;
+    q.w = w;
+    q.c = c;
+    q.direction = direction;
+    q.capacity = capacity;
+    q.events = events;
+    q.n_events = n_events;
+    return path_query_host(cfg, rhs_id, n, y0, params, solved, q);
 }
 
 void* bacon_host_alloc(size_t bytes) {

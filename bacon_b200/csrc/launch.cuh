@@ -12,6 +12,7 @@
 #include "adams.cuh"
 #include "bdf.cuh"
 #include "drive.cuh"
+#include "path_query.cuh"
 #include "rk_fast.cuh"
 #include "rk_strict.cuh"
 
@@ -183,6 +184,8 @@ template <class Rhs> int register_rhs(const char* name) {
         d.launch[S][BACON_RK45] = &launch_rk_fast<Rhs, TabRKF45>;
         d.launch[S][BACON_RK23] = &launch_rk_fast<Rhs, TabBS23>;
     }
+    // queries on stored paths (path_query.cuh) serve every method; they live in the object that holds the RK kernels
+    d.path_query[S] = &launch_path_query<Rhs, S != 0>;
 #endif
 #ifndef BACON_SKIP_BDF
     d.launch[S][BACON_BDF6] = &launch_bdf<Rhs, CoefBDF6, S != 0>;

@@ -99,11 +99,48 @@ class EnsembleResult:
         self.hist_y = None if self.hist is None else self.hist[:, :, 1:]
         self.hist_len = arrays.get("hist_len")
         self.launch = launch                  # dict: kernel_ms, h2d_ms, d2h_ms, grid, block, regs_per_thread
+        self._query = None                    # (cfg, rhs id, y0, params) of the solve, for sample() / locate_events()
 
     def path(self, i):
         """The `Path` of trajectory i (src/ivp.rs:203): [(t, y)] of accepted points."""
         m = int(self.hist_len[i])
         return [(float(self.hist_t[i, k]), np.array(self.hist_y[i, k])) for k in range(m)]
+
+    # ---- queries on the stored paths (SURVEY.md §8f N4; not in the reference: include/bacon_ivp.h)
+    def _solved(self):
+        if self.hist is None or self._query is None:
+            raise IVPError(_abi.E_BAD_ARGUMENT, "path queries need a dense-output solve (with_history(capacity))")
+        cfg, rid, y0, params = self._query
+        res = _abi.Result(hist=self.hist.ctypes.data, hist_len=self.hist_len.ctypes.data,
+                          t_end=self.t_end.ctypes.data, y_end=self.y_end.ctypes.data)
+        return cfg, rid, y0, (None if params is None else params.ctypes.data), res
+
+    def sample(self, times):
+        """The state of every trajectory at `times`: (n, len(times), dim); NaN where a time lies outside a
+        trajectory's path.  Cubic Hermite between accepted points with the right-hand side's slopes."""
+        cfg, rid, y0, pptr, res = self._solved()
+        times = np.ascontiguousarray(times, dtype=np.float64).reshape(-1)
+        n = y0.shape[1]
+        out = np.empty((n, times.size, cfg.dim))
+        _check(lib().bacon_ivp_sample_paths(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res), times.size,
+                                            times.ctypes.data, out.ctypes.data))
+        return out
+
+    def locate_events(self, w, c=0.0, direction=0, capacity=8):
+        """Zeros of g(y) = w . y - c along every path, in order.  Returns (events, n_events): events is
+        (n, capacity, 1 + dim) records (t*, y(t*)), n_events the number found per trajectory (may exceed capacity).
+        direction +1: rising only, -1: falling only, 0: both."""
+        cfg, rid, y0, pptr, res = self._solved()
+        w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1)
+        if w.size != cfg.dim:
+            raise IVPError(_abi.E_BAD_ARGUMENT, f"w must have {cfg.dim} entries")
+        n = y0.shape[1]
+        events = np.zeros((n, int(capacity), 1 + cfg.dim))
+        counts = np.zeros(n, dtype=np.uint32)
+        _check(lib().bacon_ivp_locate_events(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res), w.ctypes.data,
+                                             float(c), int(direction), int(capacity), events.ctypes.data,
+                                             counts.ctypes.data))
+        return events, counts
 
 
 class _Solver:
@@ -310,7 +347,51 @@ class _Solver:
             _check(L.bacon_ivp_solve_ensemble(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res)))
         else:
             _check(L.bacon_ivp_solve_ensemble_multi(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res), int(n_gpus)))
-        return EnsembleResult(arrays, last_launch())
+        out = EnsembleResult(arrays, last_launch())
+        out._query = (cfg, rid, y0, params if npar > 0 else None)
+        return out
+
+    # ---- queries on paths resident in HBM (torch CUDA tensors; `out` = what solve_ivp_ensemble_device returned,
+    # the solver still configured as for that solve)
+    def _device_query(self, y0, params, out, shared_params, params_aos):
+        rid, dim, npar = self._rhs_info()
+        flags = (_abi.FLAG_SHARED_PARAMS if shared_params else 0) | (_abi.FLAG_PARAMS_AOS if params_aos else 0)
+        cfg = self._config(npar, flags)
+        if cfg.history_capacity <= 0 or "hist" not in out:
+            raise IVPError(_abi.E_BAD_ARGUMENT, "path queries need a dense-output solve (with_history(capacity))")
+        res = _abi.Result(hist=out["hist"].data_ptr(), hist_len=out["hist_len"].data_ptr(),
+                          t_end=out["t_end"].data_ptr(), y_end=out["y_end"].data_ptr())
+        return cfg, rid, dim, (params.data_ptr() if npar > 0 else None), res
+
+    def sample_paths_device(self, y0, params, out, times, *, shared_params=False, params_aos=False, samples=None,
+                            stream=None):
+        import torch
+        cfg, rid, dim, pptr, res = self._device_query(y0, params, out, shared_params, params_aos)
+        n, m = y0.shape[1], times.numel()
+        if samples is None:
+            samples = torch.empty((n, m, dim), dtype=torch.float64, device=y0.device)
+        with torch.cuda.device(y0.device):
+            s = torch.cuda.current_stream(y0.device) if stream is None else stream
+            _check(lib().bacon_ivp_sample_paths_device(C.byref(cfg), rid, n, y0.data_ptr(), pptr, C.byref(res), m,
+                                                       times.data_ptr(), samples.data_ptr(), C.c_void_p(s.cuda_stream)))
+        return samples
+
+    def locate_events_device(self, y0, params, out, w, c=0.0, direction=0, capacity=8, *, shared_params=False,
+                             params_aos=False, stream=None):
+        import torch
+        cfg, rid, dim, pptr, res = self._device_query(y0, params, out, shared_params, params_aos)
+        n = y0.shape[1]
+        w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1)
+        if w.size != dim:
+            raise IVPError(_abi.E_BAD_ARGUMENT, f"w must have {dim} entries")
+        events = torch.zeros((n, int(capacity), 1 + dim), dtype=torch.float64, device=y0.device)
+        counts = torch.zeros(n, dtype=torch.int32, device=y0.device)
+        with torch.cuda.device(y0.device):
+            s = torch.cuda.current_stream(y0.device) if stream is None else stream
+            _check(lib().bacon_ivp_locate_events_device(C.byref(cfg), rid, n, y0.data_ptr(), pptr, C.byref(res),
+                                                        w.ctypes.data, float(c), int(direction), int(capacity),
+                                                        events.data_ptr(), counts.data_ptr(), C.c_void_p(s.cuda_stream)))
+        return events, counts
 
     # ---- device-resident variant: torch CUDA tensors in, torch CUDA tensors out, no copies
     def solve_ivp_ensemble_device(self, y0, params=None, *, shared_params=False, params_aos=False, out=None,

@@ -31,7 +31,7 @@ typedef unsigned long size_t;
 extern "C" {
 #endif
 
-#define BACON_IVP_ABI_VERSION 4
+#define BACON_IVP_ABI_VERSION 5
 
 /* ---- solver families: src/ivp/rk.rs:561 (RungeKutta45), rk.rs:656
  * (RungeKutta23), src/ivp/bdf.rs:706 (BDF6), bdf.rs:762 (BDF2),
@@ -168,12 +168,17 @@ int bacon_ivp_validate(const bacon_ivp_config*);
 struct bacon_launch_args; /* defined in bacon_b200/csrc/ivp_common.cuh; opaque to C callers */
 typedef int (*bacon_launch_fn)(struct bacon_launch_args*); /* fills grid/block/regs on return */
 
+struct bacon_path_args;   /* defined in bacon_b200/csrc/path_query.cuh; opaque to C callers */
+typedef int (*bacon_path_fn)(struct bacon_path_args*);
+
 typedef struct bacon_rhs_desc {
     const char* name;
     int32_t dim;
     int32_t n_params;
     /* [strict_fp 0/1][method]; NULL = not built for that slot */
     bacon_launch_fn launch[2][BACON_N_METHODS];
+    /* [strict_fp 0/1]: the path queries below (sampling, events) for this RHS; NULL = not built */
+    bacon_path_fn path_query[2];
 } bacon_rhs_desc;
 
 int bacon_rhs_register(const bacon_rhs_desc*); /* returns rhs id >= 0, or -bacon_status */
@@ -209,6 +214,36 @@ int bacon_ivp_solve_ensemble_device(const bacon_ivp_config*, int rhs_id, size_t 
  * n_gpus visible devices of this process (one stream per device). */
 int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config*, int rhs_id, size_t n, const double* y0,
                                    const double* params, const bacon_ivp_result* out, int n_gpus);
+
+/* ---- queries on stored paths: the continuous extension.
+ * NOT in the reference — its `Path` is the accepted points and nothing between them (src/ivp.rs:203-211); this is the
+ * step after the path.  Both calls take what a dense-output solve left behind (the same cfg, y0, params, and its
+ * bacon_ivp_result with hist + hist_len; t_end + y_end, when given, close a path whose last points the stepper did not
+ * yield) and treat every trajectory's path as the knots (t_start, y0), (t_1, y_1) ... (t_m, y_m).
+ * Between two knots the state is the cubic Hermite interpolant through both points with the right-hand side's own
+ * slopes f(t_k, y_k), f(t_k+1, y_k+1) (local error O(h^4): the order of every adaptive stepper's propagated solution
+ * here or better), evaluated by a second, HBM-bound kernel family compiled per right-hand side (path_query.cuh).
+ * Works for every method; BACON_FLAG_STRICT_FP selects the uncontracted build (bit-comparable with the CPU oracle).
+ *
+ * bacon_ivp_sample_paths*: samples[n][n_times][dim] = the state of every trajectory at `times` (any order; a time
+ *   outside a trajectory's path — before t_start, after its last knot, e.g. a trajectory that failed early — gives NaN).
+ * bacon_ivp_locate_events*: the zeros of g(y) = w . y - c along every path, in order: where g changes sign between two
+ *   knots (direction +1: rising only, -1: falling only, 0: both; an interval whose right knot is exactly zero counts, one
+ *   whose left knot is does not), the root of the interpolant's g is located by bisection to the last bit of theta.
+ *   events[n][capacity][1 + dim] receives the first `capacity` (t*, y(t*)) records of a trajectory, n_events[n] the
+ *   number found (it may exceed capacity).  `w` is a HOST array of dim doubles in both variants.
+ * Host variants stage through the current device; *_device take device pointers and enqueue on `stream`. */
+int bacon_ivp_sample_paths(const bacon_ivp_config*, int rhs_id, size_t n, const double* y0, const double* params,
+                           const bacon_ivp_result* solved, size_t n_times, const double* times, double* samples);
+int bacon_ivp_sample_paths_device(const bacon_ivp_config*, int rhs_id, size_t n, const double* d_y0,
+                                  const double* d_params, const bacon_ivp_result* d_solved, size_t n_times,
+                                  const double* d_times, double* d_samples, void* stream);
+int bacon_ivp_locate_events(const bacon_ivp_config*, int rhs_id, size_t n, const double* y0, const double* params,
+                            const bacon_ivp_result* solved, const double* w, double c, int direction, int capacity,
+                            double* events, uint32_t* n_events);
+int bacon_ivp_locate_events_device(const bacon_ivp_config*, int rhs_id, size_t n, const double* d_y0,
+                                   const double* d_params, const bacon_ivp_result* d_solved, const double* w, double c,
+                                   int direction, int capacity, double* d_events, uint32_t* d_n_events, void* stream);
 
 /* Page-locked host memory for the host entry points (cached by size inside the
  * library; cudaHostAlloc is slow).  Buffers from here make the H2D/D2H legs of

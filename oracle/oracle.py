@@ -56,6 +56,13 @@ def lib():
         L.oracle_nth_root.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_nth_root.restype = None
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_sample_paths.argtypes = [C.POINTER(_abi.Config), C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
+                                          C.POINTER(_abi.Result), C.c_size_t, C.c_void_p, C.c_void_p]
+        L.oracle_sample_paths.restype = C.c_int
+        L.oracle_locate_events.argtypes = [C.POINTER(_abi.Config), C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
+                                           C.POINTER(_abi.Result), C.c_void_p, C.c_double, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p]
+        L.oracle_locate_events.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -119,6 +126,53 @@ def solve_ensemble(method, rhs, y0, params=None, *, dt_min, dt_max, tol, t_start
     if rc != 0:
         raise RuntimeError(f"oracle_ivp_solve_ensemble rc={rc}")
     return out
+
+
+def _path_query_args(rhs, y0, params, solved, t_start, shared_params, params_aos):
+    rid, dim, npar = rhs_info(rhs)
+    y0 = np.ascontiguousarray(y0, dtype=np.float64)
+    hist = np.ascontiguousarray(solved["hist"], dtype=np.float64)
+    n, cap = hist.shape[0], hist.shape[1]
+    assert y0.shape == (dim, n) and hist.shape[2] == 1 + dim
+    flags = (_abi.FLAG_SHARED_PARAMS if shared_params else 0) | (_abi.FLAG_PARAMS_AOS if params_aos else 0)
+    keep = [y0, hist, np.ascontiguousarray(solved["hist_len"], dtype=np.uint32)]
+    res = _abi.Result(hist=hist.ctypes.data, hist_len=keep[2].ctypes.data)
+    if solved.get("t_end") is not None and solved.get("y_end") is not None:
+        keep += [np.ascontiguousarray(solved["t_end"], dtype=np.float64), np.ascontiguousarray(solved["y_end"], dtype=np.float64)]
+        res.t_end, res.y_end = keep[3].ctypes.data, keep[4].ctypes.data
+    pptr = None
+    if npar > 0:
+        keep.append(np.ascontiguousarray(params, dtype=np.float64))
+        pptr = keep[-1].ctypes.data
+    cfg = _abi.Config(method=0, dim=dim, n_params=npar, flags=flags, history_capacity=cap, t_start=t_start)
+    return cfg, rid, n, dim, y0.ctypes.data, pptr, res, keep
+
+
+def sample_paths(rhs, y0, params, solved, times, *, t_start, shared_params=False, params_aos=False):
+    """CPU statement of bacon_ivp_sample_paths.  solved: dict with hist, hist_len (and t_end, y_end)."""
+    cfg, rid, n, dim, yptr, pptr, res, keep = _path_query_args(rhs, y0, params, solved, t_start, shared_params, params_aos)
+    times = np.ascontiguousarray(times, dtype=np.float64).reshape(-1)
+    out = np.empty((n, times.size, dim))
+    rc = lib().oracle_sample_paths(C.byref(cfg), rid, n, yptr, pptr, C.byref(res), times.size, times.ctypes.data,
+                                   out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"oracle_sample_paths rc={rc}")
+    return out
+
+
+def locate_events(rhs, y0, params, solved, w, c=0.0, direction=0, capacity=8, *, t_start, shared_params=False,
+                  params_aos=False):
+    """CPU statement of bacon_ivp_locate_events."""
+    cfg, rid, n, dim, yptr, pptr, res, keep = _path_query_args(rhs, y0, params, solved, t_start, shared_params, params_aos)
+    w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1)
+    assert w.size == dim
+    events = np.zeros((n, capacity, 1 + dim))
+    counts = np.zeros(n, dtype=np.uint32)
+    rc = lib().oracle_locate_events(C.byref(cfg), rid, n, yptr, pptr, C.byref(res), w.ctypes.data, float(c),
+                                    int(direction), int(capacity), events.ctypes.data, counts.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"oracle_locate_events rc={rc}")
+    return events, counts
 
 
 def roots_secant(which, start, h, tol, n_max=1000, central=False):

@@ -196,14 +196,181 @@ template <class Rhs> static void run_one(const RunArgs& a, size_t i) {
     store<D>(a, i, s);
 }
 
+
+// ---- queries on stored paths (not in the reference, whose Path is the accepted points only,
+// src/ivp.rs:203-211).  CPU statement of bacon_b200/csrc/path_query.cuh, same operation order (this file is built
+// -ffp-contract=off, the strict device build -fmad=false): cubic Hermite interpolant between neighbouring knots
+// with the right-hand side's slopes; knot 0 = the initial condition, knots 1..m = the records, the exit state
+// closes the path when it lies beyond the last record. ------------------------------------------------------
+struct PathArgs {
+    const bacon_ivp_config* cfg;
+    size_t n;
+    const double* y0;
+    const double* params;
+    const bacon_ivp_result* solved;
+    size_t n_times;
+    const double* times;
+    double* samples;
+    const double* w;
+    double c;
+    int direction, capacity;
+    double* events;
+    uint32_t* n_events;
+};
+
+template <int D> struct Knots {
+    const PathArgs& a;
+    size_t i;
+    const double* rec;
+    uint32_t m;
+    bool closing;
+    double t0, tc;
+    Knots(const PathArgs& a_, size_t i_) : a(a_), i(i_) {
+        const uint32_t cap = (uint32_t)a.cfg->history_capacity;
+        rec = a.solved->hist + i * (size_t)cap * (1 + D);
+        const uint32_t len = a.solved->hist_len[i];
+        m = len < cap ? len : cap;
+        t0 = a.cfg->t_start;
+        closing = false;
+        tc = 0.0;
+        if (a.solved->t_end && a.solved->y_end) {
+            tc = a.solved->t_end[i];
+            closing = tc > (m > 0 ? rec[(size_t)(m - 1) * (1 + D)] : t0);
+        }
+    }
+    uint32_t last() const { return m + (closing ? 1u : 0u); }
+    double time(uint32_t k) const { return k == 0 ? t0 : (k <= m ? rec[(size_t)(k - 1) * (1 + D)] : tc); }
+    void state(uint32_t k, double* y) const {
+        for (int d = 0; d < D; ++d)
+            y[d] = k == 0 ? a.y0[(size_t)d * a.n + i]
+                          : (k <= m ? rec[(size_t)(k - 1) * (1 + D) + 1 + d] : a.solved->y_end[(size_t)d * a.n + i]);
+    }
+};
+
+template <int D>
+static void hermite_eval(double th, double h, const double* ya, const double* yb, const double* fa, const double* fb,
+                         double* out) {
+    const double om = 1.0 - th, tt = th * (th - 1.0), c0 = 1.0 - 2.0 * th, c1 = th - 1.0;
+    for (int d = 0; d < D; ++d) {
+        const double dy = yb[d] - ya[d];
+        const double v = (c0 * dy + c1 * (h * fa[d])) + th * (h * fb[d]);
+        out[d] = (om * ya[d] + th * yb[d]) + tt * v;
+    }
+}
+
+template <class Rhs> static void load_params(const PathArgs& a, size_t i, std::vector<double>& p) {
+    constexpr int P = Rhs::NPARAM;
+    p.assign(P > 0 ? P : 1, 0.0);
+    const bool shared = (a.cfg->flags & BACON_FLAG_SHARED_PARAMS) != 0;
+    const bool aos = (a.cfg->flags & BACON_FLAG_PARAMS_AOS) != 0;
+    for (int k = 0; k < P; ++k)
+        p[k] = shared ? a.params[k] : (aos ? a.params[i * (size_t)P + k] : a.params[(size_t)k * a.n + i]);
+}
+
+template <class Rhs> static void sample_one(const PathArgs& a, size_t i) {
+    constexpr int D = Rhs::DIM;
+    const Knots<D> kn(a, i);
+    const uint32_t K = kn.last();
+    std::vector<double> p;
+    load_params<Rhs>(a, i, p);
+    for (size_t j = 0; j < a.n_times; ++j) {
+        const double tau = a.times[j];
+        double* out = a.samples + (i * a.n_times + j) * D;
+        if (K == 0 || !(tau >= kn.t0 && tau <= kn.time(K))) {
+            if (tau == kn.t0) kn.state(0, out);
+            else for (int d = 0; d < D; ++d) out[d] = std::nan("");
+            continue;
+        }
+        uint32_t lo = 1, hi = K;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (kn.time(mid) >= tau) hi = mid;
+            else lo = mid + 1;
+        }
+        const double ta = kn.time(lo - 1), tb = kn.time(lo);
+        double ya[D], yb[D], fa[D], fb[D];
+        kn.state(lo - 1, ya);
+        kn.state(lo, yb);
+        Rhs{}(ta, ya, p.data(), fa);
+        Rhs{}(tb, yb, p.data(), fb);
+        const double h = tb - ta;
+        const double th = h > 0.0 ? (tau - ta) / h : 0.0;
+        hermite_eval<D>(th, h, ya, yb, fa, fb, out);
+    }
+}
+
+template <int D> static double event_fn(const PathArgs& a, const double* y) {
+    double s = a.w[0] * y[0];
+    for (int d = 1; d < D; ++d) s += a.w[d] * y[d];
+    return s - a.c;
+}
+
+template <class Rhs> static void events_one(const PathArgs& a, size_t i) {
+    constexpr int D = Rhs::DIM;
+    const Knots<D> kn(a, i);
+    const uint32_t K = kn.last();
+    std::vector<double> p;
+    load_params<Rhs>(a, i, p);
+    double ya[D], yb[D];
+    kn.state(0, ya);
+    double ga = event_fn<D>(a, ya);
+    uint32_t count = 0;
+    for (uint32_t k = 1; k <= K; ++k) {
+        kn.state(k, yb);
+        const double gb = event_fn<D>(a, yb);
+        const bool rising = ga < 0.0 && gb >= 0.0, falling = ga > 0.0 && gb <= 0.0;
+        const bool hit = a.direction > 0 ? rising : (a.direction < 0 ? falling : (rising || falling));
+        if (hit) {
+            if (count < (uint32_t)a.capacity) {
+                const double ta = kn.time(k - 1), tb = kn.time(k);
+                double fa[D], fb[D];
+                Rhs{}(ta, ya, p.data(), fa);
+                Rhs{}(tb, yb, p.data(), fb);
+                const double h = tb - ta;
+                double da = a.w[0] * fa[0], db = a.w[0] * fb[0];
+                for (int d = 1; d < D; ++d) {
+                    da += a.w[d] * fa[d];
+                    db += a.w[d] * fb[d];
+                }
+                double th = 1.0;
+                if (gb != 0.0) {
+                    double lo = 0.0, hi = 1.0;
+                    for (int it = 0; it < 80; ++it) {
+                        const double mid = 0.5 * (lo + hi);
+                        if (!(mid > lo && mid < hi)) break;
+                        double v;
+                        hermite_eval<1>(mid, h, &ga, &gb, &da, &db, &v);
+                        if (v == 0.0) {
+                            hi = mid;
+                            break;
+                        }
+                        if ((v < 0.0) == (ga < 0.0)) lo = mid;
+                        else hi = mid;
+                    }
+                    th = hi;
+                }
+                double* dst = a.events + (i * (size_t)a.capacity + count) * (1 + D);
+                dst[0] = ta + th * h;
+                hermite_eval<D>(th, h, ya, yb, fa, fb, dst + 1);
+            }
+            ++count;
+        }
+        for (int d = 0; d < D; ++d) ya[d] = yb[d];
+        ga = gb;
+    }
+    a.n_events[i] = count;
+}
+
 typedef void (*run_fn)(const RunArgs&, size_t);
-struct Entry { const char* name; int dim; int n_params; run_fn run; };
+typedef void (*path_fn)(const PathArgs&, size_t);
+struct Entry { const char* name; int dim; int n_params; run_fn run; path_fn sample; path_fn events; };
+#define ORACLE_ENTRY(name, dim, np, R) {name, dim, np, run_one<R>, sample_one<R>, events_one<R>}
 static const Entry kTable[] = {
-    {"lorenz", 3, 3, run_one<RhsLorenz>},       {"vdp", 2, 1, run_one<RhsVdp>},
-    {"robertson", 3, 3, run_one<RhsRobertson>}, {"linear32", 32, 1024, run_one<RhsLinear<32>>},
-    {"exp", 1, 0, run_one<RhsExp>},             {"decay", 1, 0, run_one<RhsDecay>},
-    {"quadratic", 1, 0, run_one<RhsQuadratic>}, {"cos", 1, 0, run_one<RhsCos>},
-    {"harmonic", 2, 1, run_one<RhsHarmonic>},   {"linear4", 4, 16, run_one<RhsLinear<4>>},
+    ORACLE_ENTRY("lorenz", 3, 3, RhsLorenz),       ORACLE_ENTRY("vdp", 2, 1, RhsVdp),
+    ORACLE_ENTRY("robertson", 3, 3, RhsRobertson), ORACLE_ENTRY("linear32", 32, 1024, RhsLinear<32>),
+    ORACLE_ENTRY("exp", 1, 0, RhsExp),             ORACLE_ENTRY("decay", 1, 0, RhsDecay),
+    ORACLE_ENTRY("quadratic", 1, 0, RhsQuadratic), ORACLE_ENTRY("cos", 1, 0, RhsCos),
+    ORACLE_ENTRY("harmonic", 2, 1, RhsHarmonic),   ORACLE_ENTRY("linear4", 4, 16, RhsLinear<4>),
 };
 static const int kTableSize = sizeof(kTable) / sizeof(kTable[0]);
 
@@ -248,6 +415,39 @@ int oracle_ivp_solve_ensemble(const bacon_ivp_config* cfg, int rhs_id, size_t n,
 #endif
     for (long long i = 0; i < (long long)n; ++i) e.run(a, (size_t)i);
     (void)n_threads;
+    return 0;
+}
+
+// Same contracts as bacon_ivp_sample_paths / bacon_ivp_locate_events (host buffers).
+static int path_check(const bacon_ivp_config* cfg, int rhs_id, const double* y0, const double* params,
+                      const bacon_ivp_result* solved) {
+    if (!cfg || !solved || !y0 || !solved->hist || !solved->hist_len || cfg->history_capacity <= 0) return BACON_E_BAD_ARGUMENT;
+    if (rhs_id < 0 || rhs_id >= kTableSize) return BACON_E_BAD_ARGUMENT;
+    const Entry& e = kTable[rhs_id];
+    if (cfg->dim != e.dim || cfg->n_params != e.n_params) return BACON_E_BAD_ARGUMENT;
+    if (e.n_params > 0 && !params) return BACON_E_BAD_ARGUMENT;
+    return 0;
+}
+int oracle_sample_paths(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0, const double* params,
+                        const bacon_ivp_result* solved, size_t n_times, const double* times, double* samples) {
+    if (const int rc = path_check(cfg, rhs_id, y0, params, solved)) return rc;
+    PathArgs a{cfg, n, y0, params, solved, n_times, times, samples, nullptr, 0.0, 0, 0, nullptr, nullptr};
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+    for (long long i = 0; i < (long long)n; ++i) kTable[rhs_id].sample(a, (size_t)i);
+    return 0;
+}
+int oracle_locate_events(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0, const double* params,
+                         const bacon_ivp_result* solved, const double* w, double c, int direction, int capacity,
+                         double* events, uint32_t* n_events) {
+    if (const int rc = path_check(cfg, rhs_id, y0, params, solved)) return rc;
+    if (!w || !n_events || capacity < 0 || (capacity > 0 && !events)) return BACON_E_BAD_ARGUMENT;
+    PathArgs a{cfg, n, y0, params, solved, 0, nullptr, nullptr, w, c, direction, capacity, events, n_events};
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+    for (long long i = 0; i < (long long)n; ++i) kTable[rhs_id].events(a, (size_t)i);
     return 0;
 }
 

@@ -222,3 +222,47 @@ def test_runtime_compiled_rhs_is_checked_at_registration():
     assert bad.value.code == _abi.E_USER and "q" in str(bad.value) and "undefined" in str(bad.value)
     with pytest.raises(B.IVPError):  # DIM of the functor and of the registration must agree
         B.register_rhs_source("wrongdim_rtc_abi", "Brusselator", good, 3, 2)
+
+
+def test_path_query_argument_checks_need_no_gpu():
+    """bacon_ivp_sample_paths / bacon_ivp_locate_events reject a solve without history, a missing buffer and an unknown
+    direction before anything touches the device; linear32 (warp-per-trajectory kernels) has no query kernels yet."""
+    import ctypes as C
+
+    import numpy as np
+
+    from bacon_b200 import RungeKutta45
+    from bacon_b200._lib import lib
+    L = lib()
+    s = (RungeKutta45.new(3).with_minimum_dt(1e-9).with_maximum_dt(0.1).with_tolerance(1e-8).with_initial_time(0.0)
+         .with_ending_time(1.0).with_derivative("lorenz"))
+    rid = L.bacon_rhs_lookup(b"lorenz")
+    y0 = np.ones((3, 2))
+    p = np.ones((3, 2))
+    hist = np.zeros((2, 8, 4))
+    hl = np.zeros(2, dtype=np.uint32)
+    out = np.zeros((2, 1, 3))
+    t = np.zeros(1)
+    res = _abi.Result(hist=hist.ctypes.data, hist_len=hl.ctypes.data)
+    cfg = s._config(3)  # history_capacity == 0
+    assert L.bacon_ivp_sample_paths(C.byref(cfg), rid, 2, y0.ctypes.data, p.ctypes.data, C.byref(res), 1, t.ctypes.data,
+                                    out.ctypes.data) == _abi.E_BAD_ARGUMENT
+    cfg = s.with_history(8)._config(3)
+    assert L.bacon_ivp_sample_paths(C.byref(cfg), rid, 2, y0.ctypes.data, p.ctypes.data, C.byref(res), 1, None,
+                                    out.ctypes.data) == _abi.E_BAD_ARGUMENT
+    w = np.ones(3)
+    cnt = np.zeros(2, dtype=np.uint32)
+    ev = np.zeros((2, 2, 4))
+    assert L.bacon_ivp_locate_events(C.byref(cfg), rid, 2, y0.ctypes.data, p.ctypes.data, C.byref(res), w.ctypes.data, 0.0,
+                                     2, 2, ev.ctypes.data, cnt.ctypes.data) == _abi.E_BAD_ARGUMENT
+    assert L.bacon_ivp_locate_events(C.byref(cfg), rid, 2, y0.ctypes.data, p.ctypes.data, C.byref(res), None, 0.0,
+                                     0, 2, ev.ctypes.data, cnt.ctypes.data) == _abi.E_BAD_ARGUMENT
+    # n == 0 is a no-op success
+    assert L.bacon_ivp_sample_paths(C.byref(cfg), rid, 0, y0.ctypes.data, p.ctypes.data, C.byref(res), 1, t.ctypes.data,
+                                    out.ctypes.data) == 0
+    s32 = (RungeKutta45.new(32).with_minimum_dt(1e-9).with_maximum_dt(0.1).with_tolerance(1e-8).with_initial_time(0.0)
+           .with_ending_time(1.0).with_derivative("linear32").with_history(8))
+    cfg32 = s32._config(1024)
+    rid32 = L.bacon_rhs_lookup(b"linear32")
+    assert L.bacon_ivp_sample_paths(C.byref(cfg32), rid32, 2, y0.ctypes.data, p.ctypes.data, C.byref(res), 1, t.ctypes.data,
+                                    out.ctypes.data) == _abi.E_UNSUPPORTED

@@ -245,3 +245,57 @@ def test_reference_euler_tests(oracle, case):
     t, y = r["hist_t"][0, :m], r["hist_y"][0, :m, 0]
     assert np.abs(y - exact(t)).max() <= eps  # the reference's assertion
     assert t[0] == 0.0 and y[0] == y0[0, 0] and t[-1] < 1.0 and r["t_end"][0] >= 1.0
+
+
+# ---- path queries: the oracle's own statement against closed forms ------------------------------
+def test_path_sampling_against_closed_forms(oracle):
+    """Cubic Hermite between accepted points: the sampled harmonic oscillator stays within a small multiple of the
+    error at the knots themselves; exact at the knots; NaN outside the path."""
+    wv = np.array([1.0, 2.0, 3.5])
+    y0 = np.stack([np.ones(3), np.zeros(3)])
+    s = oracle.solve_ensemble(_abi.RK45, "harmonic", y0, wv.reshape(1, 3), dt_min=1e-9, dt_max=0.1, tol=1e-10,
+                              t_start=0.0, t_end=5.0, history_capacity=4096)
+    assert (s["status"] == _abi.OK).all()
+    times = np.linspace(0.0, 5.0, 1001)
+    got = oracle.sample_paths("harmonic", y0, wv.reshape(1, 3), s, times, t_start=0.0)
+    for i, w in enumerate(wv):
+        m = int(s["hist_len"][i])
+        tk = s["hist"][i, :m, 0]
+        knot_err = np.abs(s["hist"][i, :m, 1] - np.cos(w * tk)).max()
+        assert np.abs(got[i, :, 0] - np.cos(w * times)).max() < 3 * knot_err + 1e-12
+        at_knots = oracle.sample_paths("harmonic", y0, wv.reshape(1, 3), s, tk, t_start=0.0)[i]
+        assert np.array_equal(at_knots, s["hist"][i, :m, 1:])
+    edge = oracle.sample_paths("harmonic", y0, wv.reshape(1, 3), s, [-1e-9, 0.0, 5.0, 5.0 + 1e-9, np.nan], t_start=0.0)
+    assert np.isnan(edge[:, [0, 3, 4]]).all()
+    assert np.array_equal(edge[:, 1], y0.T) and np.array_equal(edge[:, 2], s["y_end"].T)
+
+
+def test_path_events_against_closed_forms(oracle):
+    """Zeros of cos(wt) and of its derivative, by direction; capacity overflow is counted, not stored."""
+    wv = np.array([1.0, 2.0, 3.5])
+    y0 = np.stack([np.ones(3), np.zeros(3)])
+    p = wv.reshape(1, 3)
+    s = oracle.solve_ensemble(_abi.RK45, "harmonic", y0, p, dt_min=1e-9, dt_max=0.1, tol=1e-10, t_start=0.0, t_end=5.0,
+                              history_capacity=4096)
+    ev, cnt = oracle.locate_events("harmonic", y0, p, s, [1.0, 0.0], 0.0, 0, 8, t_start=0.0)
+    ev_f, cnt_f = oracle.locate_events("harmonic", y0, p, s, [1.0, 0.0], 0.0, -1, 8, t_start=0.0)
+    ev_r, cnt_r = oracle.locate_events("harmonic", y0, p, s, [1.0, 0.0], 0.0, 1, 8, t_start=0.0)
+    for i, w in enumerate(wv):
+        exact = (2 * np.arange(64) + 1) * np.pi / (2 * w)
+        exact = exact[exact < 5.0]
+        assert cnt[i] == exact.size and cnt_f[i] + cnt_r[i] == cnt[i]
+        assert np.abs(ev[i, :exact.size, 0] - exact).max() < 1e-8
+        assert np.abs(ev[i, :exact.size, 1]).max() < 1e-12  # on the surface y = 0
+        assert np.abs(ev_f[i, :cnt_f[i], 0] - exact[0::2]).max() < 1e-8  # cos falls through zero first
+        assert np.abs(ev_r[i, :cnt_r[i], 0] - exact[1::2]).max(initial=0.0) < 1e-8
+    ev1, cnt1 = oracle.locate_events("harmonic", y0, p, s, [1.0, 0.0], 0.0, 0, 1, t_start=0.0)
+    np.testing.assert_array_equal(cnt1, cnt)
+    assert np.array_equal(ev1[:, 0], ev[:, 0])
+    # an exact zero at a knot belongs to the interval it closes, once: y' = -2t... use y = 1 - t^2 sampled through t = 1
+    q = oracle.solve_ensemble(_abi.EULER, "quadratic", np.array([[1.0]]), None, dt_min=0.25, dt_max=0.25, tol=1e-3,
+                              t_start=0.0, t_end=2.0, history_capacity=16)
+    tk = q["hist"][0, :q["hist_len"][0], 0]
+    yk = q["hist"][0, :q["hist_len"][0], 1]
+    assert (yk == 0.25).any()  # Euler on y' = -2t with dt = 1/4 is exact in binary: knots at y = 1 - t(t - 1/4)
+    ev, cnt = oracle.locate_events("quadratic", np.array([[1.0]]), None, q, [1.0], 0.25, 0, 4, t_start=0.0)
+    assert cnt[0] == 1 and ev[0, 0, 0] == tk[yk == 0.25][0] and ev[0, 0, 1] == 0.25
