@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hist", action="store_true", help="configs 2 and 4 without dense output (what the history costs)")
     ap.add_argument("--n", type=int, default=0, help="override the trajectory count")
+    ap.add_argument("--paths", action="store_true", help="config 2: also time the path queries (events, sampling) on the stored history")
     args = ap.parse_args()
 
     import torch
@@ -131,6 +132,45 @@ def main():
         hp, src = hbm_peak()
         line["dense_output"] = {"bytes_per_accepted_step": 8 * (1 + dim), "GB_written": gb, "achieved_GBs": gb / (ms * 1e-3),
                                 "peak_GBs": hp, "frac": gb / (ms * 1e-3) / hp, "peak_source": src}
+    if args.paths and hist and args.config == 2:
+        # Path queries on the history just written (path_query.cuh): both HBM-bound.  Algorithmic bytes:
+        # events = every record once, 8(1 + D) per accepted step; sampling = two records in + D doubles out per sample.
+        hp, src = hbm_peak()
+        pts = float(np.minimum(acc, hist).sum())
+        n_times = 64
+        d_times = torch.linspace(w["t_start"], w["t_end"], n_times, dtype=torch.float64, device=dev)
+        samples = torch.empty((n, n_times, dim), dtype=torch.float64, device=dev)
+
+        def timed(fn):
+            fn()
+            torch.cuda.synchronize()
+            tt = []
+            for k in range(max(args.steps, 3)):
+                flush.fill_(k)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                r = fn()
+                b.record()
+                torch.cuda.synchronize()
+                tt.append(a.elapsed_time(b))
+            return sum(tt) / len(tt), r
+
+        ms_ev, (d_ev, d_cnt) = timed(lambda: s.locate_events_device(d_y0, d_par, out, [0.0, 0.0, 1.0], 27.0, 0, 4))
+        ev_launch = B.last_launch()
+        ms_sm, _ = timed(lambda: s.sample_paths_device(d_y0, d_par, out, d_times, samples=samples))
+        sm_launch = B.last_launch()
+        ev_bytes = pts * 8 * (1 + dim)
+        sm_bytes = float(n) * n_times * (2 * 8 * (1 + dim) + 8 * dim)
+        line["path_queries"] = {
+            "events": {"surface": "z = 27 (Poincare section), both directions, capacity 4", "ms": ms_ev,
+                       "events_found": int(d_cnt.sum().item()), "algorithmic_GB": ev_bytes / 1e9,
+                       "achieved_GBs": ev_bytes / 1e9 / (ms_ev * 1e-3), "peak_GBs": hp,
+                       "frac": ev_bytes / 1e9 / (ms_ev * 1e-3) / hp, "regs_per_thread": ev_launch["regs_per_thread"],
+                       "note": "torch.zeros of the event buffers is inside the timed call"},
+            "sampling": {"n_times": n_times, "ms": ms_sm, "samples_per_s": float(n) * n_times / (ms_sm * 1e-3),
+                         "algorithmic_GB": sm_bytes / 1e9, "achieved_GBs": sm_bytes / 1e9 / (ms_sm * 1e-3), "peak_GBs": hp,
+                         "frac": sm_bytes / 1e9 / (ms_sm * 1e-3) / hp, "regs_per_thread": sm_launch["regs_per_thread"]},
+            "peak_source": src}
     if not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()

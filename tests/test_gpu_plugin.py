@@ -59,6 +59,30 @@ def test_user_rhs_against_scipy(cuda, engine, user_lib):
     assert e.value.variant == "Unsupported"
 
 
+def test_user_rhs_path_queries(cuda, engine, user_lib):
+    """A functor registered with BACON_REGISTER_RHS gets the path-query kernels like a built-in: the pendulum's
+    sampled energy stays constant to the solver's accuracy, and theta = 0 crossings alternate in direction."""
+    n = 32
+    rng = np.random.default_rng(9)
+    th = np.stack([rng.uniform(0.3, 1.0, n), np.zeros(n)])
+    gl = rng.uniform(5, 15, (1, n))
+    s = make_solver(engine, "RK45", 2, rhs="pendulum", dt_min=1e-10, dt_max=0.05, tol=1e-10, t_start=0.0, t_end=3.0,
+                    history=2048)
+    r = s.solve_ivp_ensemble(th, gl)
+    assert (r.status == _abi.OK).all()
+    times = np.linspace(0.0, 3.0, 301)
+    y = r.sample(times)
+    energy = 0.5 * y[:, :, 1] ** 2 - gl.T * np.cos(y[:, :, 0])
+    assert np.abs(energy - energy[:, :1]).max() < 1e-7
+    ev, cnt = r.locate_events([1.0, 0.0], 0.0, 0, 16)
+    up = r.locate_events([1.0, 0.0], 0.0, 1, 16)[1]
+    down = r.locate_events([1.0, 0.0], 0.0, -1, 16)[1]
+    assert (cnt >= 2).all() and (up + down == cnt).all() and (np.abs(down.astype(int) - up.astype(int)) <= 1).all()
+    for i in range(n):  # half-periods are equal
+        t = ev[i, :min(int(cnt[i]), 16), 0]
+        assert np.ptp(np.diff(t)) < 1e-6
+
+
 def test_cpp_facade_readme_example(cuda):
     exe = "/tmp/bacon_cpp_facade_test"
     subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp_facade_test.cpp"),
@@ -115,6 +139,12 @@ def test_runtime_compiled_rhs_equals_the_built_in(cuda, engine, oracle, monkeypa
     rid = engine.register_rhs_source("lorenz_rtc", "LorenzRtc", LORENZ_SRC, 3, 3)
     assert rid >= 0
     P = np.array(E.LORENZ["params"])
+    # (path queries are not part of the runtime-compiled programs yet: loud Unsupported, no fallback)
+    q = make_solver(engine, "RK45", 3, rhs="lorenz_rtc", history=64, t_end=0.05, dt_min=1e-9, dt_max=0.1, tol=1e-8,
+                    t_start=0.0).solve_ivp_ensemble(E.lorenz_y0(np.arange(8)), P, shared_params=True)
+    with pytest.raises(engine.IVPError) as e:
+        q.sample([0.01])
+    assert e.value.variant == "Unsupported"
     LOR = dict(dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0.0)
     n = 4000
     y0 = E.lorenz_y0(np.arange(n))
