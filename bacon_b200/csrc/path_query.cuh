@@ -17,7 +17,8 @@
 //   path_events_kernel   one warp per trajectory: the warp streams the path 32 records at a time (coalesced: a
 //                        record is 8(1 + D) bytes, a D = 3 chunk is 1 KB), each lane tests g(y) = w . y - c for a sign
 //                        change against its left neighbour, and the rare lane that finds one locates the root of the
-//                        interpolant by bisection.  Events come out in path order (ballot + prefix count).
+//                        interpolant (safeguarded Newton).  Events come out in path order (ballot + prefix count);
+//                        crossings wait in a per-warp queue and are located 32 at a time, one per lane.
 // Both are HBM-bound: the events kernel reads every record once (8(1 + D) bytes per accepted step), the sample kernel
 // touches 2 records + D outputs per sample.  Operation order matches oracle/oracle_capi.cpp (oracle_sample_paths,
 // oracle_locate_events): the strict build (-fmad=false) is bit-comparable with it.
@@ -62,6 +63,20 @@ struct bacon_path_args {
 namespace bacon {
 
 constexpr int PATH_BLOCK = 128;
+// Events kernel: chunks of 32 records in flight per lane, and resident CTAs per SM it is compiled for.  Measured on
+// config 2's history (profiles/r01o_path_queries.md): 4 chunks at 4 CTAs/SM (114 registers, nothing spilled) 4.67 TB/s;
+// 2 chunks at 8 CTAs (64 registers, spills on the cold path) 4.84; 4 chunks at 6 CTAs (80 registers) spills inside the
+// loop: 1.0 TB/s.  The default is the spill-free one; wider records take fewer chunks to stay inside 128 registers.
+#ifndef BACON_EV_MINB
+#define BACON_EV_MINB 4
+#endif
+template <int D> __host__ __device__ constexpr int ev_unroll() {
+#ifdef BACON_EV_UNROLL
+    return BACON_EV_UNROLL;
+#else
+    return 1 + D <= 4 ? 4 : (1 + D <= 8 ? 2 : 1);
+#endif
+}
 
 template <int D>
 __device__ __forceinline__ void hermite_eval(double th, double h, const double (&ya)[D], const double (&yb)[D],
@@ -72,6 +87,52 @@ __device__ __forceinline__ void hermite_eval(double th, double h, const double (
         const double dy = yb[d] - ya[d];
         const double v = (c0 * dy + c1 * (h * fa[d])) + th * (h * fb[d]);
         out[d] = (om * ya[d] + th * yb[d]) + tt * v;
+    }
+}
+
+// The zero in [0, 1] of the scalar Hermite cubic p through p(0) = ga, p(1) = gb (opposite signs, ga != 0) with end
+// slopes A = h p'(0), B = h p'(1): Newton from the secant point, kept inside the bracket the signs maintain (a step
+// that leaves it is replaced by the midpoint), until a step moves theta by no more than 1e-15.  A handful of iterations
+// where bisection to the last bit takes 52; oracle/oracle_capi.cpp (hermite_root) repeats it operation for operation.
+__device__ __forceinline__ double hermite_root(double ga, double gb, double A, double B) {
+    if (gb == 0.0) return 1.0;
+    const double dg = gb - ga, vs = (A + B) - 2.0 * dg;  // v'(theta) is constant
+    double lo = 0.0, hi = 1.0;
+    double th = ga / (ga - gb);
+    for (int it = 0; it < 60; ++it) {
+        const double tm1 = th - 1.0;
+        const double v = ((1.0 - 2.0 * th) * dg + tm1 * A) + th * B;
+        const double val = ((1.0 - th) * ga + th * gb) + (th * tm1) * v;
+        if (val == 0.0) break;
+        if ((val < 0.0) == (ga < 0.0)) lo = th;
+        else hi = th;
+        const double der = (dg + (2.0 * th - 1.0) * v) + (th * tm1) * vs;
+        double tn = th - val / der;
+        if (!(tn > lo && tn < hi)) tn = 0.5 * (lo + hi);
+        const double moved = fabs(tn - th);
+        th = tn;
+        if (moved <= 1e-15) break;
+    }
+    return th;
+}
+
+// One whole (t, y) record with the widest loads its alignment allows (history base and records of 1 + D = 4k doubles are
+// 32-byte aligned: one 256-bit load, the mirror of hist_stage.cuh's store; 128-bit when 1 + D is even).
+template <int R> __device__ __forceinline__ void load_record(const double* __restrict__ src, double (&r)[R]) {
+    if constexpr (R % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < R; j += 4)
+            asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r[j]), "=d"(r[j + 1]), "=d"(r[j + 2]), "=d"(r[j + 3]) : "l"(src + j));
+    } else if constexpr (R % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < R; j += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(src + j);
+            r[j] = v.x;
+            r[j + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) r[j] = src[j];
     }
 }
 
@@ -106,6 +167,18 @@ template <int D> struct PathView {
     __device__ __forceinline__ uint32_t last() const { return m + (closing ? 1u : 0u); }
     __device__ __forceinline__ double time(uint32_t k) const {
         return k == 0 ? t0 : (k <= m ? rec[(size_t)(k - 1) * R] : tc);
+    }
+    // time and state of knot k; a record comes in with one vector load
+    __device__ __forceinline__ double knot(uint32_t k, double (&y)[D]) const {
+        if (k >= 1 && k <= m) {
+            double r[R];
+            load_record<R>(rec + (size_t)(k - 1) * R, r);
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = r[1 + d];
+            return r[0];
+        }
+        state(k, y);
+        return k == 0 ? t0 : tc;
     }
     __device__ __forceinline__ void state(uint32_t k, double (&y)[D]) const {
         if (k == 0) {
@@ -156,16 +229,17 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_sample_kernel(const __grid_co
             for (int d = 0; d < D; ++d) res[d] = path_nan();
         }
     } else {
-        uint32_t lo = 1, hi = K;  // the first knot at or after tau
+        // The first knot at or after tau, by bisection: log2(K) dependent probes for every lane.  (An interpolated probe
+        // sequence needs 7 probes on average on Lorenz paths but up to 17 on the slowest lane of a warp, and the warp
+        // waits for that lane: measured 15 % slower.)
+        uint32_t lo = 1, hi = K;
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
             if (pv.time(mid) >= tau) hi = mid;
             else lo = mid + 1;
         }
-        const double ta = pv.time(lo - 1), tb = pv.time(lo);
         double ya[D], yb[D], fa[D], fb[D], p[P > 0 ? P : 1];
-        pv.state(lo - 1, ya);
-        pv.state(lo, yb);
+        const double ta = pv.knot(lo - 1, ya), tb = pv.knot(lo, yb);
         load_path_params<P>(a, i, p);
         const Rhs rhs{};
         rhs(ta, ya, p, fa);
@@ -196,10 +270,8 @@ __device__ __noinline__ void locate_event(const bacon_path_args& a, unsigned lon
     constexpr int D = Rhs::DIM;
     constexpr int P = Rhs::NPARAM;
     const PathView<D> pv(a, i);  // (rebuilt here: passing the caller's by reference would put it on the stack)
-    const double ta = pv.time(k - 1), tb = pv.time(k);
     double ya[D], yb[D], fa[D], fb[D], p[P > 0 ? P : 1];
-    pv.state(k - 1, ya);
-    pv.state(k, yb);
+    const double ta = pv.knot(k - 1, ya), tb = pv.knot(k, yb);
     load_path_params<P>(a, i, p);
     const Rhs rhs{};
     rhs(ta, ya, p, fa);
@@ -218,23 +290,7 @@ __device__ __noinline__ void locate_event(const bacon_path_args& a, unsigned lon
         da[0] = s;
         db[0] = r;
     }
-    double th = 1.0;
-    if (gb[0] != 0.0) {
-        double lo = 0.0, hi = 1.0;
-        for (int it = 0; it < 80; ++it) {
-            const double mid = 0.5 * (lo + hi);
-            if (!(mid > lo && mid < hi)) break;
-            double v[1];
-            hermite_eval<1>(mid, h, ga, gb, da, db, v);
-            if (v[0] == 0.0) {
-                hi = mid;
-                break;
-            }
-            if ((v[0] < 0.0) == (ga[0] < 0.0)) lo = mid;
-            else hi = mid;
-        }
-        th = hi;
-    }
+    const double th = hermite_root(ga[0], gb[0], h * da[0], h * db[0]);
     double ys[D];
     hermite_eval<D>(th, h, ya, yb, fa, fb, ys);
     dst[0] = ta + th * h;
@@ -243,7 +299,7 @@ __device__ __noinline__ void locate_event(const bacon_path_args& a, unsigned lon
 }
 
 template <class Rhs, bool STRICT>
-__global__ void __launch_bounds__(PATH_BLOCK, 6) path_events_kernel(const __grid_constant__ bacon_path_args a) {
+__global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(const __grid_constant__ bacon_path_args a) {
     constexpr int D = Rhs::DIM;
     const unsigned long long i = ((unsigned long long)blockIdx.x * PATH_BLOCK + threadIdx.x) >> 5;
     if (i >= a.n) return;  // (whole warps leave together)
@@ -252,33 +308,89 @@ __global__ void __launch_bounds__(PATH_BLOCK, 6) path_events_kernel(const __grid
     const uint32_t K = pv.last();
     double y[D];
     pv.state(0, y);
-    double g_carry = event_fn<D>(a, y);
+    const double g_carry = event_fn<D>(a, y);  // knot 0
     uint32_t count = 0;
     const uint32_t cap = (uint32_t)a.ev_capacity;
     double* ev = a.events + (size_t)i * cap * (1 + D);
 
-    // software pipeline: the next chunk's record is in flight while this one is tested
-    uint32_t k = 1 + lane;
-    bool have = k <= K;
-    if (have) pv.state(k, y);
-    for (uint32_t base = 1; base <= K; base += 32) {
-        const double gk = have ? event_fn<D>(a, y) : 0.0;
-        const uint32_t k_now = k;
-        const bool have_now = have;
-        k += 32;
-        have = k <= K;
-        if (have) pv.state(k, y);
-        double gprev = __shfl_up_sync(FULL_MASK, gk, 1);
-        if (lane == 0) gprev = g_carry;
-        g_carry = __shfl_sync(FULL_MASK, gk, 31);
-        const bool hit = have_now && event_crossing(gprev, gk, a.ev_direction);
-        const unsigned m = __ballot_sync(FULL_MASK, hit);
-        if (hit) {
-            const uint32_t slot = count + (uint32_t)__popc(m & lanemask_lt());
-            if (slot < cap) locate_event<Rhs>(a, i, k_now, ev + (size_t)slot * (1 + D));
+    // EV_UNROLL chunks of 32 records per iteration: every lane has EV_UNROLL whole-record loads in flight (4 KB per warp
+    // for D = 3) before the first is used.  Crossings are found on warp-wide sign masks (three votes per chunk; the left
+    // neighbour's sign is the mask shifted by one, the previous chunk's last lane carried in bit 0) — all of it in
+    // uniform registers, no shuffles.  Iterations that lie wholly inside the records run without bounds tests.
+    constexpr int R = 1 + D;
+    constexpr int EV_UNROLL = ev_unroll<D>();
+    __shared__ uint32_t pend_k[PATH_BLOCK / 32][32], pend_slot[PATH_BLOCK / 32][32];
+    const unsigned wid = threadIdx.x >> 5;
+    uint32_t n_pend = 0;  // warp-uniform
+    auto flush = [&]() {
+        __syncwarp();
+        if (lane < n_pend) locate_event<Rhs>(a, i, pend_k[wid][lane], ev + (size_t)pend_slot[wid][lane] * (1 + D));
+        __syncwarp();
+    };
+    unsigned carry_neg = g_carry < 0.0 ? 1u : 0u, carry_pos = g_carry > 0.0 ? 1u : 0u;
+    auto body = [&](auto full_tag, uint32_t base) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        double rec[EV_UNROLL][R];
+        unsigned hits[EV_UNROLL];
+#pragma unroll
+        for (int u = 0; u < EV_UNROLL; ++u) {
+            const uint32_t k = base + 32 * u + lane;
+            if (FULL || k <= pv.m) {
+                load_record<R>(pv.rec + (size_t)(k - 1) * R, rec[u]);
+            } else if (k <= K) {  // the closing knot
+#pragma unroll
+                for (int d = 0; d < D; ++d) rec[u][1 + d] = pv.y_end[(size_t)d * pv.n + i];
+            }
         }
-        count += (uint32_t)__popc(m);
-    }
+#pragma unroll
+        for (int u = 0; u < EV_UNROLL; ++u) {
+            const uint32_t k = base + 32 * u + lane;
+            const bool have = FULL || k <= K;
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = have ? rec[u][1 + d] : 0.0;
+            const double g = event_fn<D>(a, y);
+            const unsigned neg = __ballot_sync(FULL_MASK, have && g < 0.0), pos = __ballot_sync(FULL_MASK, have && g > 0.0);
+            const unsigned ord = __ballot_sync(FULL_MASK, have && g == g);  // (a NaN is neither side of the surface)
+            const unsigned rising = ((neg << 1) | carry_neg) & ~neg & ord, falling = ((pos << 1) | carry_pos) & ~pos & ord;
+            carry_neg = neg >> 31;
+            carry_pos = pos >> 31;
+            hits[u] = a.ev_direction > 0 ? rising : (a.ev_direction < 0 ? falling : (rising | falling));
+        }
+        // Crossings are queued (record index, output slot) and located a warp-load at a time, one per lane: locating
+        // one costs ~20 streaming iterations' worth of instructions, and done on the spot it ran with 1 lane of 32 —
+        // 3/4 of all instructions issued on config 2's history (profiles/r01o_path_queries.md).  Crossings past the
+        // capacity are only counted.
+        unsigned any = 0;
+#pragma unroll
+        for (int u = 0; u < EV_UNROLL; ++u) any |= hits[u];
+        if (any) {
+#pragma unroll 1
+            for (int u = 0; u < EV_UNROLL; ++u) {
+                unsigned h = 0;
+#pragma unroll
+                for (int v = 0; v < EV_UNROLL; ++v) h = u == v ? hits[v] : h;  // (no dynamic indexing: registers)
+                if (h == 0) continue;
+                const uint32_t nh = (uint32_t)__popc(h);
+                const uint32_t room = count < cap ? cap - count : 0u;
+                const uint32_t n_enq = nh < room ? nh : room;  // slots are handed out in order: the stored ones come first
+                if (n_pend + n_enq > 32u) {
+                    flush();
+                    n_pend = 0;
+                }
+                const uint32_t rank = (uint32_t)__popc(h & lanemask_lt());
+                if (((h >> lane) & 1u) && rank < n_enq) {
+                    pend_k[wid][n_pend + rank] = base + 32 * u + lane;
+                    pend_slot[wid][n_pend + rank] = count + rank;
+                }
+                n_pend += n_enq;
+                count += nh;
+            }
+        }
+    };
+    uint32_t base = 1;
+    for (; base + 32 * EV_UNROLL - 1 <= pv.m; base += 32 * EV_UNROLL) body(IC<1>{}, base);
+    for (; base <= K; base += 32 * EV_UNROLL) body(IC<0>{}, base);
+    if (n_pend) flush();
     if (lane == 0) a.n_events[i] = count;
 }
 

@@ -153,21 +153,24 @@ def main():
                 b.record()
                 torch.cuda.synchronize()
                 tt.append(a.elapsed_time(b))
-            return sum(tt) / len(tt), r
+            return sum(tt) / len(tt), r, B.last_launch()
 
-        ms_ev, (d_ev, d_cnt) = timed(lambda: s.locate_events_device(d_y0, d_par, out, [0.0, 0.0, 1.0], 27.0, 0, 4))
-        ev_launch = B.last_launch()
-        ms_sm, _ = timed(lambda: s.sample_paths_device(d_y0, d_par, out, d_times, samples=samples))
-        sm_launch = B.last_launch()
+        # "call_ms": CUDA events around the whole Python call (incl. zeroing the event buffers and the host-side call path,
+        # during which the GPU idles); "ms": the library's own event pair around the kernel (bacon_ivp_last_launch)
+        call_ev, (d_ev, d_cnt), ev_launch = timed(lambda: s.locate_events_device(d_y0, d_par, out, [0.0, 0.0, 1.0], 27.0, 0, 4))
+        call_sm, _, sm_launch = timed(lambda: s.sample_paths_device(d_y0, d_par, out, d_times, samples=samples))
+        ms_ev, ms_sm = ev_launch["kernel_ms"], sm_launch["kernel_ms"]
         ev_bytes = pts * 8 * (1 + dim)
         sm_bytes = float(n) * n_times * (2 * 8 * (1 + dim) + 8 * dim)
         line["path_queries"] = {
-            "events": {"surface": "z = 27 (Poincare section), both directions, capacity 4", "ms": ms_ev,
+            "events": {"surface": "z = 27 (Poincare section), both directions, capacity 4", "ms": ms_ev, "call_ms": call_ev,
                        "events_found": int(d_cnt.sum().item()), "algorithmic_GB": ev_bytes / 1e9,
                        "achieved_GBs": ev_bytes / 1e9 / (ms_ev * 1e-3), "peak_GBs": hp,
                        "frac": ev_bytes / 1e9 / (ms_ev * 1e-3) / hp, "regs_per_thread": ev_launch["regs_per_thread"],
-                       "note": "torch.zeros of the event buffers is inside the timed call"},
-            "sampling": {"n_times": n_times, "ms": ms_sm, "samples_per_s": float(n) * n_times / (ms_sm * 1e-3),
+                       "traffic_note": "ncu: dram bytes read = 30.08 GB = the algorithmic bytes (every record once)"},
+            "sampling": {"n_times": n_times, "ms": ms_sm, "call_ms": call_sm,
+                         "traffic_note": "ncu: 9.9 GB of DRAM reads at 5.9 TB/s: the bisection probes 8 of each 64-byte DRAM "
+                                         "burst; DRAM-bound on its actual traffic (profiles/r01o_path_queries.md)", "samples_per_s": float(n) * n_times / (ms_sm * 1e-3),
                          "algorithmic_GB": sm_bytes / 1e9, "achieved_GBs": sm_bytes / 1e9 / (ms_sm * 1e-3), "peak_GBs": hp,
                          "frac": sm_bytes / 1e9 / (ms_sm * 1e-3) / hp, "regs_per_thread": sm_launch["regs_per_thread"]},
             "peak_source": src}

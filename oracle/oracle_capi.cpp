@@ -258,6 +258,29 @@ static void hermite_eval(double th, double h, const double* ya, const double* yb
     }
 }
 
+// zero in [0, 1] of the scalar Hermite cubic: safeguarded Newton, as path_query.cuh (hermite_root)
+static double hermite_root(double ga, double gb, double A, double B) {
+    if (gb == 0.0) return 1.0;
+    const double dg = gb - ga, vs = (A + B) - 2.0 * dg;
+    double lo = 0.0, hi = 1.0;
+    double th = ga / (ga - gb);
+    for (int it = 0; it < 60; ++it) {
+        const double tm1 = th - 1.0;
+        const double v = ((1.0 - 2.0 * th) * dg + tm1 * A) + th * B;
+        const double val = ((1.0 - th) * ga + th * gb) + (th * tm1) * v;
+        if (val == 0.0) break;
+        if ((val < 0.0) == (ga < 0.0)) lo = th;
+        else hi = th;
+        const double der = (dg + (2.0 * th - 1.0) * v) + (th * tm1) * vs;
+        double tn = th - val / der;
+        if (!(tn > lo && tn < hi)) tn = 0.5 * (lo + hi);
+        const double moved = std::fabs(tn - th);
+        th = tn;
+        if (moved <= 1e-15) break;
+    }
+    return th;
+}
+
 template <class Rhs> static void load_params(const PathArgs& a, size_t i, std::vector<double>& p) {
     constexpr int P = Rhs::NPARAM;
     p.assign(P > 0 ? P : 1, 0.0);
@@ -332,23 +355,7 @@ template <class Rhs> static void events_one(const PathArgs& a, size_t i) {
                     da += a.w[d] * fa[d];
                     db += a.w[d] * fb[d];
                 }
-                double th = 1.0;
-                if (gb != 0.0) {
-                    double lo = 0.0, hi = 1.0;
-                    for (int it = 0; it < 80; ++it) {
-                        const double mid = 0.5 * (lo + hi);
-                        if (!(mid > lo && mid < hi)) break;
-                        double v;
-                        hermite_eval<1>(mid, h, &ga, &gb, &da, &db, &v);
-                        if (v == 0.0) {
-                            hi = mid;
-                            break;
-                        }
-                        if ((v < 0.0) == (ga < 0.0)) lo = mid;
-                        else hi = mid;
-                    }
-                    th = hi;
-                }
+                const double th = hermite_root(ga, gb, h * da, h * db);
                 double* dst = a.events + (i * (size_t)a.capacity + count) * (1 + D);
                 dst[0] = ta + th * h;
                 hermite_eval<D>(th, h, ya, yb, fa, fb, dst + 1);

@@ -116,6 +116,31 @@ def test_harmonic_closed_form(cuda, engine):
         assert np.abs(ev[i, :exact.size, 0] - exact).max(initial=0.0) < 1e-8
 
 
+def test_many_events_per_trajectory(cuda, engine, oracle):
+    """More crossings than the warp's queue holds (32) between two flushes, and capacity below / above the count."""
+    wv = np.array([40.0, 55.0, 3.0, 20.0, 0.5])
+    n = wv.size
+    y0 = np.stack([np.ones(n), np.zeros(n)])
+    p = wv.reshape(1, n)
+    s = make_solver(engine, "RK45", 2, rhs="harmonic", dt_min=1e-9, dt_max=0.1, tol=1e-5, t_start=0.0, t_end=5.0,
+                    history=8192)
+    res = s.solve_ivp_ensemble(y0, p)
+    assert (res.status == _abi.OK).all()
+    for cap in (256, 40):
+        ev, cnt = res.locate_events([1.0, 0.0], 0.0, 0, cap)
+        rev, rcnt = oracle.locate_events("harmonic", y0, p, _solved(res), [1.0, 0.0], 0.0, 0, cap, t_start=0.0)
+        np.testing.assert_array_equal(cnt, rcnt)
+        np.testing.assert_allclose(ev, rev, rtol=1e-12, atol=1e-13)
+        for i, w in enumerate(wv):
+            exact = (2 * np.arange(1024) + 1) * np.pi / (2 * w)
+            exact = exact[exact < 5.0]
+            assert cnt[i] == exact.size
+            k = min(exact.size, cap)
+            assert np.abs(ev[i, :k, 0] - exact[:k]).max() < 1e-4
+            assert (ev[i, k:] == 0).all()
+    assert cnt.max() > 80
+
+
 @pytest.mark.parametrize("method,rhs,cfg", [
     ("BDF6", "robertson", dict(dt_min=1e-10, dt_max=1e-4, tol=1e-6, t_end=0.02)),
     ("Adams5", "exp", dict(dt_min=1e-5, dt_max=0.1, tol=1e-5, t_end=2.0)),

@@ -13,5 +13,5 @@ $NV -DBACON_SKIP_BDF -fmad=false -DBACON_STRICT_FP -c $S/rhs_builtin.cu -o $B/st
 $NV -DBACON_SKIP_RK -c $S/rhs_builtin.cu -o $B/bdf_fast.o &
 $NV -DBACON_SKIP_RK -fmad=false -DBACON_STRICT_FP -c $S/rhs_builtin.cu -o $B/bdf_strict.o &
 wait
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/libbacon_ivp_$NAME.so $B/engine.o $B/fast.o $B/strict.o $B/bdf_fast.o $B/bdf_strict.o
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/libbacon_ivp_$NAME.so $B/engine.o $S/build/rtc.o $B/fast.o $B/strict.o $B/bdf_fast.o $B/bdf_strict.o -ldl
 grep -A2 "RkFastStepperINS_9RhsLorenzENS_8TabRKF45EEELb0" $B/ptxas_fast.log | grep -E "registers|spill"
