@@ -37,6 +37,10 @@ struct EnsembleResult {
     std::vector<int32_t> status;
     std::vector<uint32_t> n_accept, n_reject, n_rhs, hist_len;
     bacon_ivp_launch_info launch{};
+    // what the path queries below need of the solve (kept by solve_ivp_ensemble)
+    bacon_ivp_config cfg{};
+    int rhs = -1;
+    std::vector<double> y0, params;
     double y(size_t i, int d) const { return y_end[(size_t)d * n + i]; }
     Path path(size_t i) const {
         Path p;
@@ -45,6 +49,38 @@ struct EnsembleResult {
             p.emplace_back(rec[0], std::vector<double>(rec + 1, rec + 1 + dim));
         }
         return p;
+    }
+
+    // ---- queries on the stored paths (bacon_ivp_sample_paths / bacon_ivp_locate_events; not in the reference, whose
+    // Path is the accepted points only, src/ivp.rs:203-211).  Need a solve with_history(capacity).
+    bacon_ivp_result solved() const {
+        bacon_ivp_result o{};
+        o.hist = const_cast<double*>(hist.data());
+        o.hist_len = const_cast<uint32_t*>(hist_len.data());
+        o.t_end = const_cast<double*>(t_end.data());
+        o.y_end = const_cast<double*>(y_end.data());
+        return o;
+    }
+    // the state of every trajectory at `times`: [n][times.size()][dim], NaN outside a trajectory's path
+    std::vector<double> sample(const std::vector<double>& times) const {
+        std::vector<double> out(n * times.size() * (size_t)dim);
+        const bacon_ivp_result o = solved();
+        const int rc = bacon_ivp_sample_paths(&cfg, rhs, n, y0.data(), params.empty() ? nullptr : params.data(), &o,
+                                              times.size(), times.data(), out.data());
+        if (rc != 0) throw IVPError(rc, bacon_last_error());
+        return out;
+    }
+    // zeros of w . y - c along every path: events [n][capacity][1 + dim] = (t*, y(t*)), counts [n]
+    std::pair<std::vector<double>, std::vector<uint32_t>> locate_events(const std::vector<double>& w, double c,
+                                                                        int direction, int capacity) const {
+        if ((int)w.size() != dim) throw IVPError(BACON_E_BAD_ARGUMENT, "w must have dim entries");
+        std::vector<double> ev(n * (size_t)capacity * (size_t)(1 + dim));
+        std::vector<uint32_t> cnt(n);
+        const bacon_ivp_result o = solved();
+        const int rc = bacon_ivp_locate_events(&cfg, rhs, n, y0.data(), params.empty() ? nullptr : params.data(), &o,
+                                               w.data(), c, direction, capacity, ev.data(), cnt.data());
+        if (rc != 0) throw IVPError(rc, bacon_last_error());
+        return {std::move(ev), std::move(cnt)};
     }
 };
 
@@ -145,6 +181,12 @@ template <int METHOD> class Solver {
         }
         check(bacon_ivp_solve_ensemble_multi(&c, rhs_, n, y0, params, &o, n_gpus));
         check(bacon_ivp_last_launch(&r.launch));
+        if (c.history_capacity > 0) {  // for the path queries
+            r.cfg = c;
+            r.rhs = rhs_;
+            r.y0.assign(y0, y0 + (size_t)c.dim * n);
+            if (np > 0 && params) r.params.assign(params, params + (size_t)np * (shared_params ? 1 : n));
+        }
         return r;
     }
 

@@ -1,4 +1,4 @@
-//! Raw bindings to `include/bacon_ivp.h` (ABI version 4).  UNVERIFIED: no Rust toolchain in the build image.
+//! Raw bindings to `include/bacon_ivp.h` (ABI version 5).  UNVERIFIED: no Rust toolchain in the build image.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_double, c_int, c_void};
 
@@ -94,6 +94,21 @@ extern "C" {
                                            stream: *mut c_void) -> c_int;
     pub fn bacon_ivp_solve_ensemble_multi(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, y0: *const c_double,
                                           params: *const c_double, out: *const bacon_ivp_result, n_gpus: c_int) -> c_int;
+    /// Queries on stored paths (cubic Hermite continuous extension of a dense-output solve; not in bacon 0.16.2).
+    pub fn bacon_ivp_sample_paths(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, y0: *const c_double,
+                                  params: *const c_double, solved: *const bacon_ivp_result, n_times: usize,
+                                  times: *const c_double, samples: *mut c_double) -> c_int;
+    pub fn bacon_ivp_sample_paths_device(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, d_y0: *const c_double,
+                                         d_params: *const c_double, d_solved: *const bacon_ivp_result, n_times: usize,
+                                         d_times: *const c_double, d_samples: *mut c_double, stream: *mut c_void) -> c_int;
+    pub fn bacon_ivp_locate_events(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, y0: *const c_double,
+                                   params: *const c_double, solved: *const bacon_ivp_result, w: *const c_double,
+                                   c: c_double, direction: c_int, capacity: c_int, events: *mut c_double,
+                                   n_events: *mut u32) -> c_int;
+    pub fn bacon_ivp_locate_events_device(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, d_y0: *const c_double,
+                                          d_params: *const c_double, d_solved: *const bacon_ivp_result,
+                                          w: *const c_double, c: c_double, direction: c_int, capacity: c_int,
+                                          d_events: *mut c_double, d_n_events: *mut u32, stream: *mut c_void) -> c_int;
     pub fn bacon_ivp_last_launch(out: *mut bacon_ivp_launch_info) -> c_int;
     pub fn bacon_last_error() -> *const c_char;
     pub fn bacon_status_name(status: c_int) -> *const c_char;

@@ -37,6 +37,17 @@ int main(int argc, char** argv) {
             if (std::fabs(pt.second[0] - std::exp(pt.first)) > 2e-2 * std::exp(pt.first)) { std::printf("FAIL accuracy\n"); return 1; }
         if (path.back().first != 10.0) { std::printf("FAIL end time\n"); return 1; }
         std::printf("solve ok: %zu points, y(10) = %.10g\n", path.size(), path.back().second[0]);
+        // path queries: y = exp(t) sampled between the accepted points, and the crossing of y = 100 (t = ln 100)
+        s.with_history(256);
+        const double y0[1] = {1.0};
+        const EnsembleResult r = s.solve_ivp_ensemble(1, y0, nullptr);
+        const std::vector<double> ys = r.sample({0.0, 1.234, 5.0, 10.0, 11.0});
+        if (ys[0] != 1.0 || std::fabs(ys[1] / std::exp(1.234) - 1.0) > 1e-5 || std::fabs(ys[2] / std::exp(5.0) - 1.0) > 1e-5 ||
+            ys[3] != r.y(0, 0) || ys[4] == ys[4]) { std::printf("FAIL sample %g %g %g %g %g\n", ys[0], ys[1], ys[2], ys[3], ys[4]); return 1; }
+        const auto ev = r.locate_events({1.0}, 100.0, +1, 2);
+        if (ev.second[0] != 1 || std::fabs(ev.first[0] - std::log(100.0)) > 1e-5 || std::fabs(ev.first[1] - 100.0) > 1e-9) {
+            std::printf("FAIL event %u %g %g\n", ev.second[0], ev.first[0], ev.first[1]); return 1; }
+        std::printf("queries ok: y(1.234) = %.8g, y = 100 at t = %.8g\n", ys[1], ev.first[0]);
     }
     std::printf("ok\n");
     return 0;
