@@ -298,7 +298,15 @@ __device__ __noinline__ void locate_event(const bacon_path_args& a, unsigned lon
     for (int d = 0; d < D; ++d) dst[1 + d] = ys[d];
 }
 
-template <class Rhs, bool STRICT>
+// how a warp's queue of crossings is located: one crossing per lane (thread-sized states)
+template <class Rhs> struct LaneLocate {
+    static __device__ __forceinline__ void flush(const bacon_path_args& a, unsigned long long i, uint32_t n_pend, const uint32_t* pk,
+                                                 const uint32_t* ps, double* ev, unsigned lane) {
+        if (lane < n_pend) locate_event<Rhs>(a, i, pk[lane], ev + (size_t)ps[lane] * (1 + Rhs::DIM));
+    }
+};
+
+template <class Rhs, bool STRICT, class Locate = LaneLocate<Rhs>>
 __global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(const __grid_constant__ bacon_path_args a) {
     constexpr int D = Rhs::DIM;
     const unsigned long long i = ((unsigned long long)blockIdx.x * PATH_BLOCK + threadIdx.x) >> 5;
@@ -306,9 +314,16 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(
     const unsigned lane = lane_id();
     const PathView<D> pv(a, i);
     const uint32_t K = pv.last();
-    double y[D];
-    pv.state(0, y);
-    const double g_carry = event_fn<D>(a, y);  // knot 0
+    // g of a knot straight from memory (knot 0; and every record of a wide one, whose components are not worth holding)
+    auto knot_g = [&](uint32_t k) -> double {
+        const double* src = k == 0 ? pv.y0 + i : (k <= pv.m ? pv.rec + (size_t)(k - 1) * (1 + D) + 1 : pv.y_end + i);
+        const size_t stride = (k >= 1 && k <= pv.m) ? 1 : (size_t)pv.n;
+        double s = a.ev_w[0] * src[0];
+#pragma unroll
+        for (int d = 1; d < D; ++d) s += a.ev_w[d] * src[(size_t)d * stride];
+        return s - a.ev_c;
+    };
+    const double g_carry = knot_g(0);
     uint32_t count = 0;
     const uint32_t cap = (uint32_t)a.ev_capacity;
     double* ev = a.events + (size_t)i * cap * (1 + D);
@@ -324,31 +339,41 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(
     uint32_t n_pend = 0;  // warp-uniform
     auto flush = [&]() {
         __syncwarp();
-        if (lane < n_pend) locate_event<Rhs>(a, i, pend_k[wid][lane], ev + (size_t)pend_slot[wid][lane] * (1 + D));
+        Locate::flush(a, i, n_pend, pend_k[wid], pend_slot[wid], ev, lane);
         __syncwarp();
     };
     unsigned carry_neg = g_carry < 0.0 ? 1u : 0u, carry_pos = g_carry > 0.0 ? 1u : 0u;
     auto body = [&](auto full_tag, uint32_t base) {
         constexpr bool FULL = decltype(full_tag)::value;
-        double rec[EV_UNROLL][R];
+        constexpr bool WIDE = R > 8;
+        constexpr int RR = WIDE ? 1 : R;  // (wide records are not held: their g is summed straight from memory)
+        double rec[EV_UNROLL][RR];
         unsigned hits[EV_UNROLL];
+        if constexpr (!WIDE) {
 #pragma unroll
-        for (int u = 0; u < EV_UNROLL; ++u) {
-            const uint32_t k = base + 32 * u + lane;
-            if (FULL || k <= pv.m) {
-                load_record<R>(pv.rec + (size_t)(k - 1) * R, rec[u]);
-            } else if (k <= K) {  // the closing knot
+            for (int u = 0; u < EV_UNROLL; ++u) {
+                const uint32_t k = base + 32 * u + lane;
+                if (FULL || k <= pv.m) {
+                    load_record<RR>(pv.rec + (size_t)(k - 1) * R, rec[u]);
+                } else if (k <= K) {  // the closing knot
 #pragma unroll
-                for (int d = 0; d < D; ++d) rec[u][1 + d] = pv.y_end[(size_t)d * pv.n + i];
+                    for (int d = 0; d < D; ++d) rec[u][(1 + d) % RR] = pv.y_end[(size_t)d * pv.n + i];
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < EV_UNROLL; ++u) {
             const uint32_t k = base + 32 * u + lane;
             const bool have = FULL || k <= K;
+            double g = 0.0;
+            if constexpr (WIDE) {
+                if (have) g = knot_g(k);
+            } else {
+                double y[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) y[d] = have ? rec[u][1 + d] : 0.0;
-            const double g = event_fn<D>(a, y);
+                for (int d = 0; d < D; ++d) y[d] = have ? rec[u][(1 + d) % RR] : 0.0;
+                g = event_fn<D>(a, y);
+            }
             const unsigned neg = __ballot_sync(FULL_MASK, have && g < 0.0), pos = __ballot_sync(FULL_MASK, have && g > 0.0);
             const unsigned ord = __ballot_sync(FULL_MASK, have && g == g);  // (a NaN is neither side of the surface)
             const unsigned rising = ((neg << 1) | carry_neg) & ~neg & ord, falling = ((pos << 1) | carry_pos) & ~pos & ord;

@@ -1,0 +1,144 @@
+// path_query_warp.cuh — the path queries (path_query.cuh) for the wide-state right-hand side y' = A y, D = 32
+// (`linear32`, BASELINE config 4: the configuration whose dense output the queries read).  As in rk_warp_linear.cuh a
+// state does not fit one thread, so the interpolation is done by a WARP: lane d owns component d of both knots and of
+// both slopes, and row d of the trajectory's matrix; f = A y takes the other components by shuffle, in the oracle's
+// order (s = A[d][0] y[0]; s += A[d][k] y[k]), so the strict build stays bit-comparable with oracle/oracle_capi.cpp.
+//   path_sample_warp32_kernel   one warp per (trajectory, sample time); the bisection is warp-uniform (broadcast loads),
+//                               both knots come in as coalesced 256-byte rows, the sample leaves as one.
+//   events                      the streaming kernel is path_query.cuh's (one lane per record, g accumulated over the
+//                               record's 32 components); queued crossings are located by the whole warp, one at a time.
+#pragma once
+#include "path_query.cuh"
+#include "rhs_builtin.cuh"
+
+namespace bacon {
+
+// row `lane` of trajectory i's matrix, any parameter layout
+__device__ __forceinline__ void load_matrix_row32(const bacon_path_args& a, unsigned long long i, unsigned lane, double (&A)[32]) {
+    constexpr int N = 32;
+    const double* P = a.params;
+    if (a.cfg.flags & BACON_FLAG_SHARED_PARAMS) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) A[j] = P[lane * N + j];
+    } else if (a.cfg.flags & BACON_FLAG_PARAMS_AOS) {
+        const double2* row = reinterpret_cast<const double2*>(P + (size_t)i * (N * N) + (size_t)lane * N);
+#pragma unroll
+        for (int j2 = 0; j2 < N / 2; ++j2) {
+            const double2 v = row[j2];
+            A[2 * j2] = v.x;
+            A[2 * j2 + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) A[j] = P[(size_t)(lane * N + j) * a.n + i];
+    }
+}
+
+// (A y)[lane], y spread over the lanes; sequential in k like RhsLinear::operator()
+__device__ __forceinline__ double warp_matvec32(const double (&A)[32], double y_lane) {
+    double s = A[0] * __shfl_sync(FULL_MASK, y_lane, 0);
+#pragma unroll
+    for (int k = 1; k < 32; ++k) s += A[k] * __shfl_sync(FULL_MASK, y_lane, k);
+    return s;
+}
+
+// w . v over the lanes, sequential in d like event_fn; every lane gets the sum
+__device__ __forceinline__ double warp_seqdot32(const bacon_path_args& a, double v_lane) {
+    double s = a.ev_w[0] * __shfl_sync(FULL_MASK, v_lane, 0);
+#pragma unroll
+    for (int d = 1; d < 32; ++d) s += a.ev_w[d] * __shfl_sync(FULL_MASK, v_lane, d);
+    return s;
+}
+
+// component d of knot k
+__device__ __forceinline__ double knot_component32(const PathView<32>& pv, uint32_t k, unsigned d) {
+    if (k == 0) return pv.y0[(size_t)d * pv.n + pv.i];
+    if (k <= pv.m) return pv.rec[(size_t)(k - 1) * 33 + 1 + d];
+    return pv.y_end[(size_t)d * pv.n + pv.i];
+}
+
+template <bool STRICT>
+__global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __grid_constant__ bacon_path_args a) {
+    const unsigned long long g = ((unsigned long long)blockIdx.x * PATH_BLOCK + threadIdx.x) >> 5;
+    if (g >= a.n * a.n_times) return;  // (whole warps)
+    const unsigned lane = lane_id();
+    const unsigned long long i = g / a.n_times, j = g - i * a.n_times;
+    const PathView<32> pv(a, i);
+    const double tau = a.times[j];
+    double* out = a.samples + (size_t)g * 32;
+    const uint32_t K = pv.last();
+    if (K == 0 || !(tau >= pv.t0 && tau <= pv.time(K))) {
+        out[lane] = tau == pv.t0 ? knot_component32(pv, 0, lane) : path_nan();
+        return;
+    }
+    uint32_t lo = 1, hi = K;  // warp-uniform: every probe is one broadcast load
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pv.time(mid) >= tau) hi = mid;
+        else lo = mid + 1;
+    }
+    const double ta = pv.time(lo - 1), tb = pv.time(lo);
+    const double ya[1] = {knot_component32(pv, lo - 1, lane)}, yb[1] = {knot_component32(pv, lo, lane)};
+    double A[32];
+    load_matrix_row32(a, i, lane, A);
+    const double fa[1] = {warp_matvec32(A, ya[0])}, fb[1] = {warp_matvec32(A, yb[0])};
+    const double h = tb - ta;
+    const double th = h > 0.0 ? (tau - ta) / h : 0.0;
+    double res[1];
+    hermite_eval<1>(th, h, ya, yb, fa, fb, res);
+    out[lane] = res[0];
+}
+
+// the queue of crossings of one trajectory, located by the whole warp one after the other
+template <bool STRICT> struct WarpLocateLinear32 {
+    static __device__ __noinline__ void flush(const bacon_path_args& a, unsigned long long i, uint32_t n_pend, const uint32_t* pk,
+                                              const uint32_t* ps, double* ev, unsigned lane) {
+        const PathView<32> pv(a, i);
+        double A[32];
+        load_matrix_row32(a, i, lane, A);
+#pragma unroll 1
+        for (uint32_t e = 0; e < n_pend; ++e) {
+            const uint32_t k = pk[e];
+            double* dst = ev + (size_t)ps[e] * 33;
+            const double ta = pv.time(k - 1), tb = pv.time(k);
+            const double ya[1] = {knot_component32(pv, k - 1, lane)}, yb[1] = {knot_component32(pv, k, lane)};
+            const double fa[1] = {warp_matvec32(A, ya[0])}, fb[1] = {warp_matvec32(A, yb[0])};
+            const double h = tb - ta;
+            const double ga = warp_seqdot32(a, ya[0]) - a.ev_c, gb = warp_seqdot32(a, yb[0]) - a.ev_c;
+            const double da = warp_seqdot32(a, fa[0]), db = warp_seqdot32(a, fb[0]);
+            const double th = hermite_root(ga, gb, h * da, h * db);
+            double ys[1];
+            hermite_eval<1>(th, h, ya, yb, fa, fb, ys);
+            if (lane == 0) dst[0] = ta + th * h;
+            dst[1 + lane] = ys[0];
+        }
+    }
+};
+
+template <bool STRICT> int launch_path_query_linear32(bacon_path_args* a) {
+    cudaStream_t st = (cudaStream_t)a->stream;
+    cudaFuncAttributes fa;
+    unsigned long long blocks = 0;
+    if (a->op == BACON_PATH_SAMPLE) {
+        auto kernel = path_sample_warp32_kernel<STRICT>;
+        if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return BACON_E_CUDA;
+        blocks = (a->n * a->n_times * 32 + PATH_BLOCK - 1) / PATH_BLOCK;
+        if (blocks == 0 || blocks > 0x7fffffffull) return BACON_E_BAD_ARGUMENT;
+        kernel<<<(unsigned)blocks, PATH_BLOCK, 0, st>>>(*a);
+    } else if (a->op == BACON_PATH_EVENTS) {
+        auto kernel = path_events_kernel<RhsLinear<32>, STRICT, WarpLocateLinear32<STRICT>>;
+        if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return BACON_E_CUDA;
+        blocks = (a->n * 32 + PATH_BLOCK - 1) / PATH_BLOCK;
+        if (blocks == 0 || blocks > 0x7fffffffull) return BACON_E_BAD_ARGUMENT;
+        kernel<<<(unsigned)blocks, PATH_BLOCK, 0, st>>>(*a);
+    } else {
+        return BACON_E_BAD_ARGUMENT;
+    }
+    if (cudaGetLastError() != cudaSuccess) return BACON_E_CUDA;
+    a->grid = (int)blocks;
+    a->block = PATH_BLOCK;
+    a->regs_per_thread = fa.numRegs;
+    return 0;
+}
+
+}  // namespace bacon

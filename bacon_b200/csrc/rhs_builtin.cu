@@ -6,6 +6,7 @@
 // only to compile them in parallel; the registry merges launcher tables by RHS name.
 #include "launch.cuh"
 #include "rhs_builtin.cuh"
+#include "path_query_warp.cuh"
 #include "rk_warp_linear.cuh"
 
 using namespace bacon;
@@ -31,9 +32,11 @@ int register_linear32() {
 #ifdef BACON_STRICT_FP
     d.launch[1][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, true>;
     d.launch[1][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, true>;
+    d.path_query[1] = &launch_path_query_linear32<true>;
 #else
     d.launch[0][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, false>;
     d.launch[0][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, false>;
+    d.path_query[0] = &launch_path_query_linear32<false>;
 #endif
     return bacon_rhs_register(&d);
 }

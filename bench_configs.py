@@ -42,7 +42,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hist", action="store_true", help="configs 2 and 4 without dense output (what the history costs)")
     ap.add_argument("--n", type=int, default=0, help="override the trajectory count")
-    ap.add_argument("--paths", action="store_true", help="config 2: also time the path queries (events, sampling) on the stored history")
+    ap.add_argument("--paths", action="store_true", help="configs 2 and 4: also time the path queries (events, sampling) on the stored history")
     args = ap.parse_args()
 
     import torch
@@ -132,12 +132,13 @@ def main():
         hp, src = hbm_peak()
         line["dense_output"] = {"bytes_per_accepted_step": 8 * (1 + dim), "GB_written": gb, "achieved_GBs": gb / (ms * 1e-3),
                                 "peak_GBs": hp, "frac": gb / (ms * 1e-3) / hp, "peak_source": src}
-    if args.paths and hist and args.config == 2:
+    if args.paths and hist and args.config in (2, 4):
         # Path queries on the history just written (path_query.cuh): both HBM-bound.  Algorithmic bytes:
         # events = every record once, 8(1 + D) per accepted step; sampling = two records in + D doubles out per sample.
         hp, src = hbm_peak()
         pts = float(np.minimum(acc, hist).sum())
-        n_times = 64
+        n_times = 64 if args.config == 2 else 16
+        ev_w, ev_c = ([0.0, 0.0, 1.0], 27.0) if args.config == 2 else ([1.0] + [0.0] * (dim - 1), 0.0)
         d_times = torch.linspace(w["t_start"], w["t_end"], n_times, dtype=torch.float64, device=dev)
         samples = torch.empty((n, n_times, dim), dtype=torch.float64, device=dev)
 
@@ -157,19 +158,19 @@ def main():
 
         # "call_ms": CUDA events around the whole Python call (incl. zeroing the event buffers and the host-side call path,
         # during which the GPU idles); "ms": the library's own event pair around the kernel (bacon_ivp_last_launch)
-        call_ev, (d_ev, d_cnt), ev_launch = timed(lambda: s.locate_events_device(d_y0, d_par, out, [0.0, 0.0, 1.0], 27.0, 0, 4))
-        call_sm, _, sm_launch = timed(lambda: s.sample_paths_device(d_y0, d_par, out, d_times, samples=samples))
+        call_ev, (d_ev, d_cnt), ev_launch = timed(lambda: s.locate_events_device(d_y0, d_par, out, ev_w, ev_c, 0, 4, **kw_dev))
+        call_sm, _, sm_launch = timed(lambda: s.sample_paths_device(d_y0, d_par, out, d_times, samples=samples, **kw_dev))
         ms_ev, ms_sm = ev_launch["kernel_ms"], sm_launch["kernel_ms"]
         ev_bytes = pts * 8 * (1 + dim)
         sm_bytes = float(n) * n_times * (2 * 8 * (1 + dim) + 8 * dim)
         line["path_queries"] = {
-            "events": {"surface": "z = 27 (Poincare section), both directions, capacity 4", "ms": ms_ev, "call_ms": call_ev,
+            "events": {"surface": ("z = 27 (Poincare section)" if args.config == 2 else "y[0] = 0") + ", both directions, capacity 4", "ms": ms_ev, "call_ms": call_ev,
                        "events_found": int(d_cnt.sum().item()), "algorithmic_GB": ev_bytes / 1e9,
                        "achieved_GBs": ev_bytes / 1e9 / (ms_ev * 1e-3), "peak_GBs": hp,
                        "frac": ev_bytes / 1e9 / (ms_ev * 1e-3) / hp, "regs_per_thread": ev_launch["regs_per_thread"],
-                       "traffic_note": "ncu: dram bytes read = 30.08 GB = the algorithmic bytes (every record once)"},
+                       "traffic_note": "config 2, ncu: dram bytes read = 30.08 GB = the algorithmic bytes (every record once)"},
             "sampling": {"n_times": n_times, "ms": ms_sm, "call_ms": call_sm,
-                         "traffic_note": "ncu: 9.9 GB of DRAM reads at 5.9 TB/s: the bisection probes 8 of each 64-byte DRAM "
+                         "traffic_note": "config 2, ncu: 9.9 GB of DRAM reads at 5.9 TB/s: the bisection probes 8 of each 64-byte DRAM "
                                          "burst; DRAM-bound on its actual traffic (profiles/r01o_path_queries.md)", "samples_per_s": float(n) * n_times / (ms_sm * 1e-3),
                          "algorithmic_GB": sm_bytes / 1e9, "achieved_GBs": sm_bytes / 1e9 / (ms_sm * 1e-3), "peak_GBs": hp,
                          "frac": sm_bytes / 1e9 / (ms_sm * 1e-3) / hp, "regs_per_thread": sm_launch["regs_per_thread"]},

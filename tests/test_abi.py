@@ -226,7 +226,7 @@ def test_runtime_compiled_rhs_is_checked_at_registration():
 
 def test_path_query_argument_checks_need_no_gpu():
     """bacon_ivp_sample_paths / bacon_ivp_locate_events reject a solve without history, a missing buffer and an unknown
-    direction before anything touches the device; linear32 (warp-per-trajectory kernels) has no query kernels yet."""
+    direction before anything touches the device."""
     import ctypes as C
 
     import numpy as np
@@ -260,9 +260,3 @@ def test_path_query_argument_checks_need_no_gpu():
     # n == 0 is a no-op success
     assert L.bacon_ivp_sample_paths(C.byref(cfg), rid, 0, y0.ctypes.data, p.ctypes.data, C.byref(res), 1, t.ctypes.data,
                                     out.ctypes.data) == 0
-    s32 = (RungeKutta45.new(32).with_minimum_dt(1e-9).with_maximum_dt(0.1).with_tolerance(1e-8).with_initial_time(0.0)
-           .with_ending_time(1.0).with_derivative("linear32").with_history(8))
-    cfg32 = s32._config(1024)
-    rid32 = L.bacon_rhs_lookup(b"linear32")
-    assert L.bacon_ivp_sample_paths(C.byref(cfg32), rid32, 2, y0.ctypes.data, p.ctypes.data, C.byref(res), 1, t.ctypes.data,
-                                    out.ctypes.data) == _abi.E_UNSUPPORTED

@@ -186,6 +186,49 @@ def test_every_method_family(cuda, engine, oracle, method, rhs, cfg):
     assert cnt.sum() > 0
 
 
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("aos", [True, False])
+def test_linear32_warp_queries(cuda, engine, oracle, strict, aos):
+    """BASELINE config 4's right-hand side (D = 32, per-trajectory matrix): the warp-cooperative query kernels
+    (path_query_warp.cuh) against the oracle on the same paths — strict bit-exact, fast within 1e-12 — and against
+    the matrix exponential."""
+    from scipy.linalg import expm
+    n = 37
+    y0, A = E.linear32_problem(np.arange(n))          # (32, n), (n, 32, 32)
+    par = A.reshape(n, 1024) if aos else np.ascontiguousarray(A.reshape(n, 1024).T)
+    s = make_solver(engine, "RK45", 32, rhs="linear32", dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0.0, t_end=2.0,
+                    flags=_abi.FLAG_STRICT_FP if strict else 0, history=256)
+    res = s.solve_ivp_ensemble(y0, par, params_aos=aos)
+    assert (res.status == _abi.OK).all()
+    rng = np.random.default_rng(3)
+    times = np.concatenate([[0.0, 2.0, 2.5], rng.uniform(0.0, 2.0, 29)])
+    got = res.sample(times)
+    ref = oracle.sample_paths("linear32", y0, par, _solved(res), times, t_start=0.0, params_aos=aos)
+    assert np.isnan(got[:, 2]).all() and np.array_equal(got[:, 0], y0.T) and np.array_equal(got[:, 1], res.y_end.T)
+    if strict:
+        assert np.array_equal(_bits(got), _bits(ref))
+    else:
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-13, equal_nan=True)
+    for i in (0, n - 1):
+        for j in (3, 17):
+            exact = expm(A[i] * times[j]) @ y0[:, i]
+            assert np.abs(got[i, j] - exact).max() < 1e-6
+    w = rng.normal(size=32)
+    for direction, cap in ((0, 8), (1, 2)):
+        ev, cnt = res.locate_events(w, 0.05, direction, cap)
+        rev, rcnt = oracle.locate_events("linear32", y0, par, _solved(res), w, 0.05, direction, cap, t_start=0.0,
+                                         params_aos=aos)
+        np.testing.assert_array_equal(cnt, rcnt)
+        assert cnt.sum() > 0
+        if strict:
+            assert np.array_equal(_bits(ev), _bits(rev))
+        else:
+            np.testing.assert_allclose(ev, rev, rtol=1e-11, atol=1e-12)
+        for i in range(n):
+            k = min(int(cnt[i]), cap)
+            assert np.abs(ev[i, :k, 1:] @ w - 0.05).max(initial=0.0) < 1e-9
+
+
 def test_failed_trajectory_path_ends_early(cuda, engine, oracle):
     """A trajectory that fails (here: the attempt cap) has a path up to its failure time: NaN beyond."""
     y0 = np.array([[1.0, 1.0]])
