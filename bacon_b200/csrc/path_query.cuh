@@ -335,6 +335,8 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(
     constexpr int R = 1 + D;
     constexpr int EV_UNROLL = ev_unroll<D>();
     __shared__ uint32_t pend_k[PATH_BLOCK / 32][32], pend_slot[PATH_BLOCK / 32][32];
+    constexpr bool WIDE_REC = R > 8;
+    __shared__ double stage[WIDE_REC ? PATH_BLOCK / 32 : 1][WIDE_REC ? 32 * R : 1];
     const unsigned wid = threadIdx.x >> 5;
     uint32_t n_pend = 0;  // warp-uniform
     auto flush = [&]() {
@@ -349,7 +351,20 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(
         constexpr int RR = WIDE ? 1 : R;  // (wide records are not held: their g is summed straight from memory)
         double rec[EV_UNROLL][RR];
         unsigned hits[EV_UNROLL];
-        if constexpr (!WIDE) {
+        if constexpr (WIDE) {
+            // a chunk of 32 wide records is one contiguous block: the warp copies it into shared memory with coalesced
+            // loads (R per lane in flight), and each lane then sums its own record from there, in component order
+            const uint32_t nrec = FULL ? 32u : (base > pv.m ? 0u : (pv.m - base + 1 < 32u ? pv.m - base + 1 : 32u));
+            const double* src = pv.rec + (size_t)(base - 1) * R;
+            __syncwarp();
+            if (FULL) {
+#pragma unroll
+                for (int it = 0; it < R; ++it) stage[wid][it * 32 + lane] = src[it * 32 + lane];
+            } else {
+                for (uint32_t idx = lane; idx < nrec * R; idx += 32) stage[wid][idx] = src[idx];
+            }
+            __syncwarp();
+        } else {
 #pragma unroll
             for (int u = 0; u < EV_UNROLL; ++u) {
                 const uint32_t k = base + 32 * u + lane;
@@ -367,7 +382,15 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(
             const bool have = FULL || k <= K;
             double g = 0.0;
             if constexpr (WIDE) {
-                if (have) g = knot_g(k);
+                if (have && k <= pv.m) {
+                    const double* r = &stage[wid][(k - base) * R + 1];
+                    double sum = a.ev_w[0] * r[0];
+#pragma unroll
+                    for (int d = 1; d < D; ++d) sum += a.ev_w[d] * r[d];
+                    g = sum - a.ev_c;
+                } else if (have) {
+                    g = knot_g(k);  // the closing knot
+                }
             } else {
                 double y[D];
 #pragma unroll

@@ -3,7 +3,7 @@
 // state does not fit one thread, so the interpolation is done by a WARP: lane d owns component d of both knots and of
 // both slopes, and row d of the trajectory's matrix; f = A y takes the other components by shuffle, in the oracle's
 // order (s = A[d][0] y[0]; s += A[d][k] y[k]), so the strict build stays bit-comparable with oracle/oracle_capi.cpp.
-//   path_sample_warp32_kernel   one warp per (trajectory, sample time); the bisection is warp-uniform (broadcast loads),
+//   path_sample_warp32_kernel   one warp per (trajectory, 8 sample times); the bisection is warp-uniform (broadcast loads),
 //                               both knots come in as coalesced 256-byte rows, the sample leaves as one.
 //   events                      the streaming kernel is path_query.cuh's (one lane per record, g accumulated over the
 //                               record's 32 components); queued crossings are located by the whole warp, one at a time.
@@ -57,36 +57,46 @@ __device__ __forceinline__ double knot_component32(const PathView<32>& pv, uint3
     return pv.y_end[(size_t)d * pv.n + pv.i];
 }
 
+// sample times one warp takes of its trajectory: the 8 KB matrix (row d in lane d's registers) is loaded once per warp
+// and serves them all (one warp per sample re-read it per sample: 14.1 ms for 2^18 x 16 samples, profiles/r01o_path_queries.md)
+constexpr int WARP32_TIMES = 8;
+
 template <bool STRICT>
 __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __grid_constant__ bacon_path_args a) {
+    const unsigned long long chunks = (a.n_times + WARP32_TIMES - 1) / WARP32_TIMES;
     const unsigned long long g = ((unsigned long long)blockIdx.x * PATH_BLOCK + threadIdx.x) >> 5;
-    if (g >= a.n * a.n_times) return;  // (whole warps)
+    if (g >= a.n * chunks) return;  // (whole warps)
     const unsigned lane = lane_id();
-    const unsigned long long i = g / a.n_times, j = g - i * a.n_times;
+    const unsigned long long i = g / chunks, j0 = (g - i * chunks) * WARP32_TIMES;
+    const unsigned long long j1 = j0 + WARP32_TIMES < a.n_times ? j0 + WARP32_TIMES : a.n_times;
     const PathView<32> pv(a, i);
-    const double tau = a.times[j];
-    double* out = a.samples + (size_t)g * 32;
     const uint32_t K = pv.last();
-    if (K == 0 || !(tau >= pv.t0 && tau <= pv.time(K))) {
-        out[lane] = tau == pv.t0 ? knot_component32(pv, 0, lane) : path_nan();
-        return;
-    }
-    uint32_t lo = 1, hi = K;  // warp-uniform: every probe is one broadcast load
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (pv.time(mid) >= tau) hi = mid;
-        else lo = mid + 1;
-    }
-    const double ta = pv.time(lo - 1), tb = pv.time(lo);
-    const double ya[1] = {knot_component32(pv, lo - 1, lane)}, yb[1] = {knot_component32(pv, lo, lane)};
+    const double t_last = pv.time(K);
     double A[32];
     load_matrix_row32(a, i, lane, A);
-    const double fa[1] = {warp_matvec32(A, ya[0])}, fb[1] = {warp_matvec32(A, yb[0])};
-    const double h = tb - ta;
-    const double th = h > 0.0 ? (tau - ta) / h : 0.0;
-    double res[1];
-    hermite_eval<1>(th, h, ya, yb, fa, fb, res);
-    out[lane] = res[0];
+#pragma unroll 1
+    for (unsigned long long j = j0; j < j1; ++j) {
+        const double tau = a.times[j];
+        double* out = a.samples + ((size_t)i * a.n_times + j) * 32;
+        if (K == 0 || !(tau >= pv.t0 && tau <= t_last)) {
+            out[lane] = tau == pv.t0 ? knot_component32(pv, 0, lane) : path_nan();
+            continue;
+        }
+        uint32_t lo = 1, hi = K;  // warp-uniform: every probe is one broadcast load
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (pv.time(mid) >= tau) hi = mid;
+            else lo = mid + 1;
+        }
+        const double ta = pv.time(lo - 1), tb = pv.time(lo);
+        const double ya[1] = {knot_component32(pv, lo - 1, lane)}, yb[1] = {knot_component32(pv, lo, lane)};
+        const double fa[1] = {warp_matvec32(A, ya[0])}, fb[1] = {warp_matvec32(A, yb[0])};
+        const double h = tb - ta;
+        const double th = h > 0.0 ? (tau - ta) / h : 0.0;
+        double res[1];
+        hermite_eval<1>(th, h, ya, yb, fa, fb, res);
+        out[lane] = res[0];
+    }
 }
 
 // the queue of crossings of one trajectory, located by the whole warp one after the other
@@ -122,7 +132,7 @@ template <bool STRICT> int launch_path_query_linear32(bacon_path_args* a) {
     if (a->op == BACON_PATH_SAMPLE) {
         auto kernel = path_sample_warp32_kernel<STRICT>;
         if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return BACON_E_CUDA;
-        blocks = (a->n * a->n_times * 32 + PATH_BLOCK - 1) / PATH_BLOCK;
+        blocks = (a->n * ((a->n_times + WARP32_TIMES - 1) / WARP32_TIMES) * 32 + PATH_BLOCK - 1) / PATH_BLOCK;
         if (blocks == 0 || blocks > 0x7fffffffull) return BACON_E_BAD_ARGUMENT;
         kernel<<<(unsigned)blocks, PATH_BLOCK, 0, st>>>(*a);
     } else if (a->op == BACON_PATH_EVENTS) {
