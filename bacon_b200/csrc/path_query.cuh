@@ -70,6 +70,18 @@ constexpr int PATH_BLOCK = 128;
 #ifndef BACON_EV_MINB
 #define BACON_EV_MINB 4
 #endif
+#ifndef BACON_EV_WIDE_MINB
+#define BACON_EV_WIDE_MINB 4
+#endif
+// Wide records (1 + D > 8, linear32): each lane sums its record's g straight from memory (BACON_EV_WIDE_STAGE 0), or
+// the warp first copies the chunk into shared memory with coalesced loads (1).  Measured on config 4's history (2^18
+// paths of ~122 records of 264 B, 8.5 GB; profiles/r01o_path_queries.md): 3.66 ms direct against 3.87 staged, and
+// 4.06 at 6 or 8 resident CTAs either way — neither the access pattern nor the occupancy is the limit there; a warp
+// has only four chunks to stream per path, so its dependent prologue (length, last record, closing knot) dominates.
+#ifndef BACON_EV_WIDE_STAGE
+#define BACON_EV_WIDE_STAGE 0
+#endif
+template <int D> __host__ __device__ constexpr int ev_minb() { return 1 + D > 8 ? BACON_EV_WIDE_MINB : BACON_EV_MINB; }
 template <int D> __host__ __device__ constexpr int ev_unroll() {
 #ifdef BACON_EV_UNROLL
     return BACON_EV_UNROLL;
@@ -307,7 +319,7 @@ template <class Rhs> struct LaneLocate {
 };
 
 template <class Rhs, bool STRICT, class Locate = LaneLocate<Rhs>>
-__global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(const __grid_constant__ bacon_path_args a) {
+__global__ void __launch_bounds__(PATH_BLOCK, ev_minb<Rhs::DIM>()) path_events_kernel(const __grid_constant__ bacon_path_args a) {
     constexpr int D = Rhs::DIM;
     const unsigned long long i = ((unsigned long long)blockIdx.x * PATH_BLOCK + threadIdx.x) >> 5;
     if (i >= a.n) return;  // (whole warps leave together)
@@ -335,7 +347,7 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(
     constexpr int R = 1 + D;
     constexpr int EV_UNROLL = ev_unroll<D>();
     __shared__ uint32_t pend_k[PATH_BLOCK / 32][32], pend_slot[PATH_BLOCK / 32][32];
-    constexpr bool WIDE_REC = R > 8;
+    constexpr bool WIDE_REC = R > 8 && BACON_EV_WIDE_STAGE;
     __shared__ double stage[WIDE_REC ? PATH_BLOCK / 32 : 1][WIDE_REC ? 32 * R : 1];
     const unsigned wid = threadIdx.x >> 5;
     uint32_t n_pend = 0;  // warp-uniform
@@ -351,7 +363,7 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(
         constexpr int RR = WIDE ? 1 : R;  // (wide records are not held: their g is summed straight from memory)
         double rec[EV_UNROLL][RR];
         unsigned hits[EV_UNROLL];
-        if constexpr (WIDE) {
+        if constexpr (WIDE && WIDE_REC) {
             // a chunk of 32 wide records is one contiguous block: the warp copies it into shared memory with coalesced
             // loads (R per lane in flight), and each lane then sums its own record from there, in component order
             const uint32_t nrec = FULL ? 32u : (base > pv.m ? 0u : (pv.m - base + 1 < 32u ? pv.m - base + 1 : 32u));
@@ -364,7 +376,7 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(
                 for (uint32_t idx = lane; idx < nrec * R; idx += 32) stage[wid][idx] = src[idx];
             }
             __syncwarp();
-        } else {
+        } else if constexpr (!WIDE) {
 #pragma unroll
             for (int u = 0; u < EV_UNROLL; ++u) {
                 const uint32_t k = base + 32 * u + lane;
@@ -382,7 +394,7 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EV_MINB) path_events_kernel(
             const bool have = FULL || k <= K;
             double g = 0.0;
             if constexpr (WIDE) {
-                if (have && k <= pv.m) {
+                if (WIDE_REC && have && k <= pv.m) {
                     const double* r = &stage[wid][(k - base) * R + 1];
                     double sum = a.ev_w[0] * r[0];
 #pragma unroll

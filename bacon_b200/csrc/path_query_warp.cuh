@@ -3,7 +3,7 @@
 // state does not fit one thread, so the interpolation is done by a WARP: lane d owns component d of both knots and of
 // both slopes, and row d of the trajectory's matrix; f = A y takes the other components by shuffle, in the oracle's
 // order (s = A[d][0] y[0]; s += A[d][k] y[k]), so the strict build stays bit-comparable with oracle/oracle_capi.cpp.
-//   path_sample_warp32_kernel   one warp per (trajectory, 8 sample times); the bisection is warp-uniform (broadcast loads),
+//   path_sample_warp32_kernel   one warp per (trajectory, up to 32 sample times): one bisection per lane, then the warp interpolates;
 //                               both knots come in as coalesced 256-byte rows, the sample leaves as one.
 //   events                      the streaming kernel is path_query.cuh's (one lane per record, g accumulated over the
 //                               record's 32 components); queued crossings are located by the whole warp, one at a time.
@@ -57,9 +57,11 @@ __device__ __forceinline__ double knot_component32(const PathView<32>& pv, uint3
     return pv.y_end[(size_t)d * pv.n + pv.i];
 }
 
-// sample times one warp takes of its trajectory: the 8 KB matrix (row d in lane d's registers) is loaded once per warp
-// and serves them all (one warp per sample re-read it per sample: 14.1 ms for 2^18 x 16 samples, profiles/r01o_path_queries.md)
-constexpr int WARP32_TIMES = 8;
+// Sample times one warp takes of its trajectory.  The 8 KB matrix (row d in lane d's registers) is loaded once per warp
+// and serves them all, and the bisections of all its times run side by side, one per lane (one warp per sample re-read
+// the matrix per sample and searched with all 32 lanes in lockstep: 14.1 ms for 2^18 x 16 samples; 8 times per warp,
+// searched one after the other: 7.6 ms; profiles/r01o_path_queries.md).
+constexpr int WARP32_TIMES = 32;
 
 template <bool STRICT>
 __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __grid_constant__ bacon_path_args a) {
@@ -68,25 +70,38 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __
     if (g >= a.n * chunks) return;  // (whole warps)
     const unsigned lane = lane_id();
     const unsigned long long i = g / chunks, j0 = (g - i * chunks) * WARP32_TIMES;
-    const unsigned long long j1 = j0 + WARP32_TIMES < a.n_times ? j0 + WARP32_TIMES : a.n_times;
+    const unsigned n_here = (unsigned)(j0 + WARP32_TIMES < a.n_times ? WARP32_TIMES : a.n_times - j0);
     const PathView<32> pv(a, i);
     const uint32_t K = pv.last();
     const double t_last = pv.time(K);
+    // phase 1: lane l finds the interval of time j0 + l (0 = outside the path, ~0 = exactly t_start on an empty path)
+    double my_tau = 0.0;
+    uint32_t my_lo = 0;
+    if (lane < n_here) {
+        my_tau = a.times[j0 + lane];
+        if (K > 0 && my_tau >= pv.t0 && my_tau <= t_last) {
+            uint32_t lo = 1, hi = K;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (pv.time(mid) >= my_tau) hi = mid;
+                else lo = mid + 1;
+            }
+            my_lo = lo;
+        } else if (my_tau == pv.t0) {
+            my_lo = ~0u;
+        }
+    }
     double A[32];
     load_matrix_row32(a, i, lane, A);
-#pragma unroll 1
-    for (unsigned long long j = j0; j < j1; ++j) {
-        const double tau = a.times[j];
-        double* out = a.samples + ((size_t)i * a.n_times + j) * 32;
-        if (K == 0 || !(tau >= pv.t0 && tau <= t_last)) {
-            out[lane] = tau == pv.t0 ? knot_component32(pv, 0, lane) : path_nan();
+    // phase 2: the warp interpolates them one after the other
+#pragma unroll 2
+    for (unsigned l = 0; l < n_here; ++l) {
+        const double tau = __shfl_sync(FULL_MASK, my_tau, l);
+        const uint32_t lo = __shfl_sync(FULL_MASK, my_lo, l);
+        double* out = a.samples + ((size_t)i * a.n_times + j0 + l) * 32;
+        if (lo == 0 || lo == ~0u) {
+            out[lane] = lo ? knot_component32(pv, 0, lane) : path_nan();
             continue;
-        }
-        uint32_t lo = 1, hi = K;  // warp-uniform: every probe is one broadcast load
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (pv.time(mid) >= tau) hi = mid;
-            else lo = mid + 1;
         }
         const double ta = pv.time(lo - 1), tb = pv.time(lo);
         const double ya[1] = {knot_component32(pv, lo - 1, lane)}, yb[1] = {knot_component32(pv, lo, lane)};
