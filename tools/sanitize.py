@@ -48,4 +48,33 @@ s = (B.RungeKutta45.new(32).with_minimum_dt(1e-9).with_maximum_dt(0.1).with_tole
      .with_ending_time(0.5).with_derivative("linear32").with_history(64))
 res = s.solve_ivp_ensemble(y32, A32.reshape(64, 1024), params_aos=True)
 assert (res.status == _abi.OK).all()
+# path queries (path_query.cuh, path_query_warp.cuh): sampling + events incl. a queue that overflows (> 32 crossings
+# between flushes) and a capacity below the count, against the oracle on the same paths
+def _sv(r):
+    return dict(hist=r.hist, hist_len=r.hist_len, t_end=r.t_end, y_end=r.y_end)
+
+
+times = np.linspace(-0.1, 0.6, 23)
+got = res.sample(times)
+ref = O.sample_paths("linear32", y32, A32.reshape(64, 1024), _sv(res), times, t_start=0.0, params_aos=True)
+assert np.allclose(got, ref, rtol=1e-12, atol=1e-13, equal_nan=True)
+w32 = np.linspace(-1.0, 1.0, 32)
+ev, cnt = res.locate_events(w32, 0.02, 0, 2)
+rev, rcnt = O.locate_events("linear32", y32, A32.reshape(64, 1024), _sv(res), w32, 0.02, 0, 2, t_start=0.0, params_aos=True)
+assert (cnt == rcnt).all() and np.allclose(ev, rev, rtol=1e-11, atol=1e-12)
+g, r = run_both(B, O, "RK45", "lorenz", y0[:, :600], P, shared_params=True, t_end=1.5, history=2000, **LOR)
+sv = _sv(g)
+times = np.linspace(0.0, 1.5, 37)
+assert np.allclose(g.sample(times), O.sample_paths("lorenz", y0[:, :600], P, sv, times, t_start=0.0, shared_params=True),
+                   rtol=1e-12, atol=1e-12)
+for cap in (1, 16):
+    ev, cnt = g.locate_events([0.0, 0.0, 1.0], 27.0, 0, cap)
+    rev, rcnt = O.locate_events("lorenz", y0[:, :600], P, sv, [0.0, 0.0, 1.0], 27.0, 0, cap, t_start=0.0, shared_params=True)
+    assert (cnt == rcnt).all() and np.allclose(ev, rev, rtol=1e-12, atol=1e-12)
+wv = np.array([[45.0, 3.0, 60.0]])
+sh = (B.RungeKutta45.new(2).with_minimum_dt(1e-9).with_maximum_dt(0.1).with_tolerance(1e-5).with_initial_time(0.0)
+      .with_ending_time(5.0).with_derivative("harmonic").with_history(8192))
+h = sh.solve_ivp_ensemble(np.array([[1.0, 1.0, 1.0], [0.0, 0.0, 0.0]]), wv)
+ev, cnt = h.locate_events([1.0, 0.0], 0.0, 0, 200)
+assert cnt.max() > 64 and (np.diff(ev[2, :cnt[2], 0]) > 0).all()
 print("sanitize.py: all families ran")

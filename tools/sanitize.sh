@@ -1,8 +1,7 @@
 #!/bin/bash
-# tools/sanitize.sh — compute-sanitizer memcheck + racecheck over tools/sanitize.py (on the GPU box); logs in gpurun_out/
-export BACON_IVP_GRID=6
-python tools/sanitize.py 2>&1 | tail -2
+# tools/sanitize.sh TAG — on the GPU box: memcheck and racecheck over every kernel family (tools/sanitize.py)
+T=${1:-rXX}
 for tool in memcheck racecheck; do
-  timeout 1500 compute-sanitizer --tool $tool --log-file gpurun_out/sanitizer_$tool.log python tools/sanitize.py > gpurun_out/sanitizer_$tool.out 2>&1
-  echo "$tool: exit $? ; $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer_$tool.log | tail -1)"
+  BACON_IVP_GRID=6 timeout 400 compute-sanitizer --tool $tool python tools/sanitize.py > gpurun_out/${T}_sanitize_$tool.log 2>&1
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|all families ran|Error|AssertionError" gpurun_out/${T}_sanitize_$tool.log | head -5
 done
