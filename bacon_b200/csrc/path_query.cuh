@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(PATH_BLOCK, ev_minb<Rhs::DIM>()) path_events_k
     if (lane == 0) a.n_events[i] = count;
 }
 
+#ifndef __CUDACC_RTC__  // (runtime-compiled functors are launched through the driver API: rtc.cu)
 // host-side launcher of both queries for one right-hand side and one build flavour
 template <class Rhs, bool STRICT> int launch_path_query(bacon_path_args* a) {
     static_assert(Rhs::DIM <= BACON_PATH_MAX_DIM, "event weights are passed by value");
@@ -481,5 +482,6 @@ template <class Rhs, bool STRICT> int launch_path_query(bacon_path_args* a) {
     a->regs_per_thread = fa.numRegs;
     return 0;
 }
+#endif
 
 }  // namespace bacon

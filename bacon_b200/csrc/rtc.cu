@@ -23,6 +23,7 @@
 
 #include "../../include/bacon_ivp.h"
 #include "ivp_common.cuh"
+#include "path_query.cuh"
 #include "tableaux.cuh"
 
 namespace bacon_internal { void set_last_error(const char* msg); }  // engine.cu
@@ -317,6 +318,107 @@ int rtc_launch(int slot, bacon_launch_args* a) {
     return 0;
 }
 
+// ---------------------------------------------------------------- path queries (path_query.cuh) for a runtime-compiled functor
+// One more NVRTC program per (architecture, strict/fast): the sampling and the events kernel instantiated on the user's
+// functor.  Compiled keeps them as main (sampling) / tail (events).
+constexpr int kPathKey = 1000;  // in the method slot of the cache keys
+int compile_path_program(RtcRhs& r, bool strict, int cc_major, int cc_minor, Compiled* out) {
+    Api& A = api();
+    std::string src = "#include \"path_query.cuh\"\n";
+    src += "#line 1 \"" + r.name + ".cu\"\n" + r.source + "\n";
+    const std::string s = strict ? "true" : "false", T = r.type_name;
+    const std::string k_sample = "&bacon::path_sample_kernel<" + T + ", " + s + ">";
+    const std::string k_events = "&bacon::path_events_kernel<" + T + ", " + s + ", bacon::LaneLocate<" + T + " > >";
+    std::vector<const char*> hdr_text, hdr_name;
+    for (int i = 0; i < kNumHeaders; ++i) { hdr_text.push_back(kHeaders[i].text); hdr_name.push_back(kHeaders[i].name); }
+    nvrtcProgram prog = nullptr;
+    if (A.nvrtcCreateProgram(&prog, src.c_str(), (r.name + "_paths.cu").c_str(), kNumHeaders, hdr_text.data(), hdr_name.data()) != NVRTC_SUCCESS)
+        return rtc_fail(BACON_E_CUDA, "nvrtcCreateProgram failed");
+    A.nvrtcAddNameExpression(prog, k_sample.c_str());
+    A.nvrtcAddNameExpression(prog, k_events.c_str());
+    const std::string arch = "--gpu-architecture=sm_" + std::to_string(cc_major) + std::to_string(cc_minor) + (cc_major >= 9 ? "a" : "");
+    std::vector<const char*> opts = {arch.c_str(), "-std=c++17", "-default-device", "-lineinfo"};
+    if (strict) { opts.push_back("--fmad=false"); opts.push_back("-DBACON_STRICT_FP"); }
+    if (A.nvrtcCompileProgram(prog, (int)opts.size(), opts.data()) != NVRTC_SUCCESS) {
+        size_t n = 0;
+        A.nvrtcGetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) A.nvrtcGetProgramLog(prog, &log[0]);
+        A.nvrtcDestroyProgram(&prog);
+        return rtc_fail(BACON_E_USER, "rhs '%s': the path-query kernels do not compile:\n%.3500s", r.name.c_str(), log.c_str());
+    }
+    size_t nbin = 0;
+    A.nvrtcGetCUBINSize(prog, &nbin);
+    out->cubin.resize(nbin);
+    A.nvrtcGetCUBIN(prog, out->cubin.data());
+    const char* l = nullptr;
+    if (A.nvrtcGetLoweredName(prog, k_sample.c_str(), &l) == NVRTC_SUCCESS && l) out->main = l;
+    if (A.nvrtcGetLoweredName(prog, k_events.c_str(), &l) == NVRTC_SUCCESS && l) out->tail = l;
+    A.nvrtcDestroyProgram(&prog);
+    if (out->main.empty() || out->tail.empty()) return rtc_fail(BACON_E_CUDA, "rhs '%s': path-query kernel names not found", r.name.c_str());
+    return 0;
+}
+
+// mirrors launch_path_query (path_query.cuh)
+int rtc_path_query(int slot, bacon_path_args* a) {
+    Api& A = api();
+    RtcRhs* r = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (slot < 0 || slot >= (int)g_rtc.size()) return BACON_E_BAD_ARGUMENT;
+        r = g_rtc[slot].get();
+    }
+    const bool strict = (a->cfg.flags & BACON_FLAG_STRICT_FP) || a->cfg.semantics == BACON_SEM_LITERAL;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!A.drv_ok) return rtc_fail(BACON_E_UNSUPPORTED, "rhs '%s' cannot be launched: %s", r->name.c_str(), A.why.c_str());
+    Variant v;
+    {
+        std::lock_guard<std::mutex> lk(r->mu);
+        const std::vector<int> key = {dev, kPathKey, strict ? 1 : 0, 0, 0};
+        auto it = r->variants.find(key);
+        if (it == r->variants.end()) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return BACON_E_CUDA;
+            const std::vector<int> pkey = {prop.major * 10 + prop.minor, kPathKey, strict ? 1 : 0, 0, 0};
+            auto pit = r->programs.find(pkey);
+            if (pit == r->programs.end()) {
+                Compiled cp;
+                if (const int rc = compile_path_program(*r, strict, prop.major, prop.minor, &cp)) return rc;
+                pit = r->programs.emplace(pkey, std::move(cp)).first;
+            }
+            Variant nv;
+            if (const int rc = load_variant(*r, pit->second, &nv)) return rc;
+            it = r->variants.emplace(key, nv).first;
+        }
+        v = it->second;
+    }
+    CUfunction fn = nullptr;
+    unsigned long long blocks = 0;
+    if (a->op == BACON_PATH_SAMPLE) {
+        fn = v.main;
+        blocks = (a->n * a->n_times + bacon::PATH_BLOCK - 1) / bacon::PATH_BLOCK;
+    } else if (a->op == BACON_PATH_EVENTS) {
+        fn = v.tail;
+        blocks = (a->n * 32 + bacon::PATH_BLOCK - 1) / bacon::PATH_BLOCK;
+    }
+    if (!fn || blocks == 0 || blocks > 0x7fffffffull) return BACON_E_BAD_ARGUMENT;
+    int regs = 0;
+    A.cuFuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn);
+    bacon_path_args args = *a;
+    void* params[] = {&args};
+    if (A.cuLaunchKernel(fn, (unsigned)blocks, 1, 1, bacon::PATH_BLOCK, 1, 1, 0, (CUstream)a->stream, params, nullptr) != CUDA_SUCCESS)
+        return BACON_E_CUDA;
+    a->grid = (int)blocks;
+    a->block = bacon::PATH_BLOCK;
+    a->regs_per_thread = regs;
+    return 0;
+}
+template <int SLOT> int path_trampoline(bacon_path_args* a) { return rtc_path_query(SLOT, a); }
+template <int... I> void fill_path_trampolines(bacon_path_fn (&t)[kMaxRtc], std::integer_sequence<int, I...>) {
+    ((t[I] = &path_trampoline<I>), ...);
+}
+
 // bacon_launch_fn carries no context: a fixed pool of trampolines, one per runtime-compiled right-hand side
 template <int SLOT> int trampoline(bacon_launch_args* a) { return rtc_launch(SLOT, a); }
 template <int... I> void fill_trampolines(bacon_launch_fn (&t)[kMaxRtc], std::integer_sequence<int, I...>) {
@@ -331,8 +433,12 @@ extern "C" int bacon_rhs_register_source(const char* name, const char* type_name
     Api& A = api();
     if (!A.ok) return -rtc_fail(BACON_E_UNSUPPORTED, "runtime compilation is not available: %s", A.why.c_str());
     static bacon_launch_fn tramps[kMaxRtc];
+    static bacon_path_fn path_tramps[kMaxRtc];
     static std::once_flag once;
-    std::call_once(once, [] { fill_trampolines(tramps, std::make_integer_sequence<int, kMaxRtc>{}); });
+    std::call_once(once, [] {
+        fill_trampolines(tramps, std::make_integer_sequence<int, kMaxRtc>{});
+        fill_path_trampolines(path_tramps, std::make_integer_sequence<int, kMaxRtc>{});
+    });
     int slot;
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -366,6 +472,15 @@ extern "C" int bacon_rhs_register_source(const char* name, const char* type_name
             return -rc;
         }
         r.programs.emplace(std::vector<int>{major * 10 + minor, (int)BACON_RK45, 0, 0, 0}, std::move(cp));
+        // the path-query program is compiled at the first query; BACON_RTC_EAGER_PATHS=1 compiles it here as well (both
+        // flavours), which is how the CPU test suite checks that path_query.cuh goes through NVRTC
+        if (getenv("BACON_RTC_EAGER_PATHS")) {
+            for (int strict = 0; strict < 2; ++strict) {
+                Compiled pp;
+                if (const int rc = compile_path_program(r, strict != 0, major, minor, &pp)) return -rc;
+                r.programs.emplace(std::vector<int>{major * 10 + minor, kPathKey, strict, 0, 0}, std::move(pp));
+            }
+        }
     }
     bacon_rhs_desc d{};
     d.name = name;
@@ -373,5 +488,6 @@ extern "C" int bacon_rhs_register_source(const char* name, const char* type_name
     d.n_params = n_params;
     for (int s = 0; s < 2; ++s)
         for (int m = 0; m < BACON_N_METHODS; ++m) d.launch[s][m] = tramps[slot];
+    d.path_query[0] = d.path_query[1] = path_tramps[slot];
     return bacon_rhs_register(&d);
 }

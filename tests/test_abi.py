@@ -222,6 +222,12 @@ def test_runtime_compiled_rhs_is_checked_at_registration():
     assert bad.value.code == _abi.E_USER and "q" in str(bad.value) and "undefined" in str(bad.value)
     with pytest.raises(B.IVPError):  # DIM of the functor and of the registration must agree
         B.register_rhs_source("wrongdim_rtc_abi", "Brusselator", good, 3, 2)
+    # the path-query kernels (path_query.cuh) go through NVRTC too, fast and strict (compiled lazily otherwise)
+    os.environ["BACON_RTC_EAGER_PATHS"] = "1"
+    try:
+        assert B.register_rhs_source("brusselator_rtc_paths", "Brusselator", good, 2, 2) >= 0
+    finally:
+        del os.environ["BACON_RTC_EAGER_PATHS"]
 
 
 def test_path_query_argument_checks_need_no_gpu():

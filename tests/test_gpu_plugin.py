@@ -139,12 +139,26 @@ def test_runtime_compiled_rhs_equals_the_built_in(cuda, engine, oracle, monkeypa
     rid = engine.register_rhs_source("lorenz_rtc", "LorenzRtc", LORENZ_SRC, 3, 3)
     assert rid >= 0
     P = np.array(E.LORENZ["params"])
-    # (path queries are not part of the runtime-compiled programs yet: loud Unsupported, no fallback)
-    q = make_solver(engine, "RK45", 3, rhs="lorenz_rtc", history=64, t_end=0.05, dt_min=1e-9, dt_max=0.1, tol=1e-8,
-                    t_start=0.0).solve_ivp_ensemble(E.lorenz_y0(np.arange(8)), P, shared_params=True)
-    with pytest.raises(engine.IVPError) as e:
-        q.sample([0.01])
-    assert e.value.variant == "Unsupported"
+    # path queries: the runtime-compiled program (path_query.cuh through NVRTC) against the oracle on the same paths —
+    # strict bit for bit, fast within 1e-12
+    for strict in (True, False):
+        q = make_solver(engine, "RK45", 3, rhs="lorenz_rtc", history=700, t_end=0.5, dt_min=1e-9, dt_max=0.1, tol=1e-8,
+                        t_start=0.0, flags=_abi.FLAG_STRICT_FP if strict else 0)
+        yq = E.lorenz_y0(np.arange(300))
+        r = q.solve_ivp_ensemble(yq, P, shared_params=True)
+        assert (r.status == _abi.OK).all()
+        sv = dict(hist=r.hist, hist_len=r.hist_len, t_end=r.t_end, y_end=r.y_end)
+        times = np.linspace(-0.05, 0.55, 41)
+        got = r.sample(times)
+        ref = oracle.sample_paths("lorenz", yq, P, sv, times, t_start=0.0, shared_params=True)
+        ev, cnt = r.locate_events([0.0, 0.0, 1.0], 27.0, 0, 3)
+        rev, rcnt = oracle.locate_events("lorenz", yq, P, sv, [0.0, 0.0, 1.0], 27.0, 0, 3, t_start=0.0, shared_params=True)
+        assert (cnt == rcnt).all() and cnt.sum() > 0
+        if strict:
+            assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)) and np.array_equal(ev.view(np.uint64), rev.view(np.uint64))
+        else:
+            np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12, equal_nan=True)
+            np.testing.assert_allclose(ev, rev, rtol=1e-12, atol=1e-12)
     LOR = dict(dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0.0)
     n = 4000
     y0 = E.lorenz_y0(np.arange(n))
