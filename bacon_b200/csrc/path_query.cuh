@@ -133,8 +133,16 @@ __device__ __forceinline__ double hermite_root(double ga, double gb, double A, d
 template <int R> __device__ __forceinline__ void load_record(const double* __restrict__ src, double (&r)[R]) {
     if constexpr (R % 4 == 0) {
 #pragma unroll
-        for (int j = 0; j < R; j += 4)
+        for (int j = 0; j < R; j += 4) {
+#if defined(__CUDACC_VER_MAJOR__) && (__CUDACC_VER_MAJOR__ * 100 + __CUDACC_VER_MINOR__ < 1209)
+            // 256-bit vector loads need PTX ISA 8.8 (CUDA 12.9): an older NVRTC (bacon_rhs_register_source picks up whatever
+            // libnvrtc.so.12 the process has) reads the same sector as two 128-bit halves (as hist_stage.cuh's store)
+            asm volatile("ld.global.v2.f64 {%0, %1}, [%4];\n\tld.global.v2.f64 {%2, %3}, [%4+16];"
+                         : "=d"(r[j]), "=d"(r[j + 1]), "=d"(r[j + 2]), "=d"(r[j + 3]) : "l"(src + j));
+#else
             asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r[j]), "=d"(r[j + 1]), "=d"(r[j + 2]), "=d"(r[j + 3]) : "l"(src + j));
+#endif
+        }
     } else if constexpr (R % 2 == 0) {
 #pragma unroll
         for (int j = 0; j < R; j += 2) {

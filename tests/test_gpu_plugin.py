@@ -142,7 +142,7 @@ def test_runtime_compiled_rhs_equals_the_built_in(cuda, engine, oracle, monkeypa
     # path queries: the runtime-compiled program (path_query.cuh through NVRTC) against the oracle on the same paths —
     # strict bit for bit, fast within 1e-12
     for strict in (True, False):
-        q = make_solver(engine, "RK45", 3, rhs="lorenz_rtc", history=700, t_end=0.5, dt_min=1e-9, dt_max=0.1, tol=1e-8,
+        q = make_solver(engine, "RK45", 3, rhs="lorenz_rtc", history=1400, t_end=0.5, dt_min=1e-9, dt_max=0.1, tol=1e-8,
                         t_start=0.0, flags=_abi.FLAG_STRICT_FP if strict else 0)
         yq = E.lorenz_y0(np.arange(300))
         r = q.solve_ivp_ensemble(yq, P, shared_params=True)
