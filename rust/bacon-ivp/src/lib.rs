@@ -62,6 +62,11 @@ pub struct EnsembleResult {
     pub hist: Vec<f64>,    // [n][cap][1 + dim]: (t, y) records, the image of Vec<(f64, SVector<f64, D>)>
     pub hist_len: Vec<u32>,
     pub capacity: usize,
+    // what the path queries need of the solve (kept when capacity > 0)
+    cfg: sys::bacon_ivp_config,
+    rhs: i32,
+    y0: Vec<f64>,
+    params: Vec<f64>,
 }
 
 impl EnsembleResult {
@@ -72,6 +77,39 @@ impl EnsembleResult {
                 (self.hist[rec], self.hist[rec + 1..rec + 1 + self.dim].to_vec())
             })
             .collect()
+    }
+
+    fn solved(&self) -> sys::bacon_ivp_result {
+        sys::bacon_ivp_result {
+            y_end: self.y_end.as_ptr() as *mut f64, t_end: self.t_end.as_ptr() as *mut f64, dt_end: std::ptr::null_mut(),
+            status: std::ptr::null_mut(), n_accept: std::ptr::null_mut(), n_reject: std::ptr::null_mut(),
+            n_rhs: std::ptr::null_mut(), hist: self.hist.as_ptr() as *mut f64, hist_len: self.hist_len.as_ptr() as *mut u32,
+        }
+    }
+
+    /// The state of every trajectory at `times` ([n][times.len()][dim], NaN outside a trajectory's path): the cubic
+    /// Hermite interpolant between accepted points (`bacon_ivp_sample_paths`; not in bacon 0.16.2, whose `Path` is the
+    /// accepted points only, src/ivp.rs:203-211).  Needs a solve `with_history(capacity)`.
+    pub fn sample(&self, times: &[f64]) -> Result<Vec<f64>, IVPError> {
+        let mut out = vec![0.0; self.n * times.len() * self.dim];
+        let o = self.solved();
+        let pptr = if self.params.is_empty() { std::ptr::null() } else { self.params.as_ptr() };
+        check(unsafe { sys::bacon_ivp_sample_paths(&self.cfg, self.rhs, self.n, self.y0.as_ptr(), pptr, &o, times.len(),
+                                                   times.as_ptr(), out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+
+    /// Zeros of `w . y - c` along every path, in order (`bacon_ivp_locate_events`): ([n][capacity][1 + dim] records
+    /// (t*, y(t*)), [n] counts).  direction +1: rising only, -1: falling only, 0: both.
+    pub fn locate_events(&self, w: &[f64], c: f64, direction: i32, capacity: usize) -> Result<(Vec<f64>, Vec<u32>), IVPError> {
+        if w.len() != self.dim { return Err(IVPError::BadArgument); }
+        let mut ev = vec![0.0; self.n * capacity * (1 + self.dim)];
+        let mut cnt = vec![0u32; self.n];
+        let o = self.solved();
+        let pptr = if self.params.is_empty() { std::ptr::null() } else { self.params.as_ptr() };
+        check(unsafe { sys::bacon_ivp_locate_events(&self.cfg, self.rhs, self.n, self.y0.as_ptr(), pptr, &o, w.as_ptr(), c,
+                                                    direction, capacity as i32, ev.as_mut_ptr(), cnt.as_mut_ptr()) })?;
+        Ok((ev, cnt))
     }
 }
 
@@ -149,6 +187,7 @@ impl<const METHOD: i32> Solver<METHOD> {
             y_end: vec![0.0; self.dim * n], t_end: vec![0.0; n], dt_end: vec![0.0; n], status: vec![-1; n],
             n_accept: vec![0; n], n_reject: vec![0; n], n_rhs: vec![0; n],
             hist: vec![0.0; n * cap * (1 + self.dim)], hist_len: vec![0; n],
+            cfg, rhs, y0: if cap > 0 { y0.to_vec() } else { Vec::new() }, params: if cap > 0 { params.to_vec() } else { Vec::new() },
         };
         let out = sys::bacon_ivp_result {
             y_end: r.y_end.as_mut_ptr(), t_end: r.t_end.as_mut_ptr(), dt_end: r.dt_end.as_mut_ptr(),
