@@ -82,18 +82,28 @@ def cpu_run(w, n_sample, threads=0):
     return int(r["n_accept"].sum()), dt, cores
 
 
+def host_cores():
+    """Cores this process may run on (affinity / cgroup aware), not OMP_NUM_THREADS: torchrun sets that to 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     w = workload(args)
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     n_sample = args.cpu_sample or max(1024, min(w["n"], 4096 * cores))
+    # (threads named explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, and this arm is meant to use every
+    # host core, like the reference's rayon pool)
     for _ in range(min(args.warmup, 1)):
-        cpu_run(w, max(256, n_sample // 16))
+        cpu_run(w, max(256, n_sample // 16), threads=cores)
     steps_total, secs = 0, 0.0
     for _ in range(args.steps):
-        s, dt, cores = cpu_run(w, n_sample)
+        s, dt, cores = cpu_run(w, n_sample, threads=cores)
         steps_total += s
         secs += dt
     v = steps_total / secs
@@ -286,9 +296,9 @@ def ours(args):
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         n_sample = args.cpu_sample or max(1024, min(n, 8192 * cores))
-        s, dt, cores = cpu_run(w, n_sample)
+        s, dt, cores = cpu_run(w, n_sample, threads=cores)
         cpu_baseline = {"value": s / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"first {n_sample} trajectories of the same seeded ensemble, one pass ({dt:.1f} s)"}
 
