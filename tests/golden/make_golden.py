@@ -57,6 +57,24 @@ from scipy.linalg import expm  # noqa: E402
 y0, A = E.linear32_problem(np.arange(4))
 out["linear32_seeded4_T4"] = [(expm(A[i] * 4.0) @ y0[:, i]).tolist() for i in range(4)]
 
+# path queries: an independent continuous solution and independent event times — SciPy's DOP853 dense
+# output and its own event root-finder on the first 4 seeded Lorenz trajectories, T = 2
+times = np.linspace(0.0, 2.0, 21)
+
+
+def z27(t, y, s, r, b):
+    return y[2] - 27.0
+
+
+y0 = E.lorenz_y0(np.arange(4))
+pq = {"times": times.tolist(), "states": [], "z27_events": []}
+for i in range(4):
+    s = solve_ivp(lorenz, (0, 2), y0[:, i], method="DOP853", rtol=1e-13, atol=1e-13, args=(10.0, 28.0, 8.0 / 3.0),
+                  dense_output=True, events=z27)
+    pq["states"].append(s.sol(times).T.tolist())
+    pq["z27_events"].append(s.t_events[0].tolist())
+out["lorenz_seeded4_T2_paths"] = pq
+
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "anchors.json"), "w") as f:
     json.dump(out, f, indent=1)
 print("wrote anchors.json:", {k: (len(v) if hasattr(v, "__len__") else v) for k, v in out.items()})

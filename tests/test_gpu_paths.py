@@ -116,6 +116,31 @@ def test_harmonic_closed_form(cuda, engine):
         assert np.abs(ev[i, :exact.size, 0] - exact).max(initial=0.0) < 1e-8
 
 
+def test_against_scipy_dense_output_and_events(cuda, engine):
+    """Independent of the oracle: SciPy DOP853's own dense output and event root-finder on seeded Lorenz trajectories
+    (tests/golden/anchors.json, generated by tests/golden/make_golden.py).  The CPU oracle meets these anchors to 3e-12 /
+    9e-12 at this tolerance (tests/test_oracle.py); the fast kernels' solve differs from it inside the parity band."""
+    import json
+    import os
+    anchors = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "anchors.json")))["lorenz_seeded4_T2_paths"]
+    times = np.array(anchors["times"])
+    y0 = E.lorenz_y0(np.arange(4))
+    for strict in (False, True):
+        s = make_solver(engine, "RK45", 3, rhs="lorenz", dt_min=1e-9, dt_max=0.1, tol=1e-10, t_start=0.0, t_end=2.0,
+                        flags=_abi.FLAG_STRICT_FP if strict else 0, history=8192)
+        res = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+        assert (res.status == _abi.OK).all()
+        got = res.sample(times)
+        ref = np.array(anchors["states"])
+        assert np.abs(got - ref).max() < 1e-8 * np.abs(ref).max()
+        ev, cnt = res.locate_events([0.0, 0.0, 1.0], 27.0, 0, 16)
+        for i in range(4):
+            want = np.array(anchors["z27_events"][i])
+            assert cnt[i] == want.size
+            assert np.abs(ev[i, :want.size, 0] - want).max() < 1e-8
+            assert np.abs(ev[i, :want.size, 3] - 27.0).max() < 1e-9
+
+
 def test_many_events_per_trajectory(cuda, engine, oracle):
     """More crossings than the warp's queue holds (32) between two flushes, and capacity below / above the count."""
     wv = np.array([40.0, 55.0, 3.0, 20.0, 0.5])

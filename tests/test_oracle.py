@@ -299,3 +299,25 @@ def test_path_events_against_closed_forms(oracle):
     assert (yk == 0.25).any()  # Euler on y' = -2t with dt = 1/4 is exact in binary: knots at y = 1 - t(t - 1/4)
     ev, cnt = oracle.locate_events("quadratic", np.array([[1.0]]), None, q, [1.0], 0.25, 0, 4, t_start=0.0)
     assert cnt[0] == 1 and ev[0, 0, 0] == tk[yk == 0.25][0] and ev[0, 0, 1] == 0.25
+
+
+def test_path_queries_against_scipy_dense_output_and_events(oracle):
+    """Independent anchors (tests/golden/anchors.json, made by make_golden.py): SciPy DOP853's own dense output and its own
+    event root-finder on seeded Lorenz trajectories.  The oracle's sampled states and located z = 27 crossings agree to
+    the accuracy of the underlying RK45 solve (tol 1e-10; Lorenz amplifies errors by ~e^{0.9 t})."""
+    anchors = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "anchors.json")))["lorenz_seeded4_T2_paths"]
+    times = np.array(anchors["times"])
+    y0 = E.lorenz_y0(np.arange(4))
+    P = np.array(E.LORENZ["params"])
+    s = oracle.solve_ensemble(_abi.RK45, "lorenz", y0, P, shared_params=True, dt_min=1e-9, dt_max=0.1, tol=1e-10,
+                              t_start=0.0, t_end=2.0, history_capacity=8192)
+    assert (s["status"] == _abi.OK).all()
+    got = oracle.sample_paths("lorenz", y0, P, s, times, t_start=0.0, shared_params=True)
+    ref = np.array(anchors["states"])
+    assert np.abs(got - ref).max() < 1e-9 * np.abs(ref).max()  # (measured 3e-12)
+    ev, cnt = oracle.locate_events("lorenz", y0, P, s, [0.0, 0.0, 1.0], 27.0, 0, 16, t_start=0.0, shared_params=True)
+    for i in range(4):
+        want = np.array(anchors["z27_events"][i])
+        assert cnt[i] == want.size
+        assert np.abs(ev[i, :want.size, 0] - want).max() < 1e-9  # (measured 9e-12)
+        assert np.abs(ev[i, :want.size, 3] - 27.0).max() < 1e-10
