@@ -229,7 +229,7 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config*, int rhs_id, size_t n
  *   outside a trajectory's path — before t_start, after its last knot, e.g. a trajectory that failed early — gives NaN).
  * bacon_ivp_locate_events*: the zeros of g(y) = w . y - c along every path, in order: where g changes sign between two
  *   knots (direction +1: rising only, -1: falling only, 0: both; an interval whose right knot is exactly zero counts, one
- *   whose left knot is does not), the root of the interpolant's g is located by bisection to the last bit of theta.
+ *   whose left knot is does not), the root of the interpolant's g is located by a bracketed Newton iteration (theta to 1e-15).
  *   events[n][capacity][1 + dim] receives the first `capacity` (t*, y(t*)) records of a trajectory, n_events[n] the
  *   number found (it may exceed capacity).  `w` is a HOST array of dim doubles in both variants.
  * Host variants stage through the current device; *_device take device pointers and enqueue on `stream`. */
