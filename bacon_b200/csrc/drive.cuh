@@ -38,13 +38,18 @@ template <class S> struct StepperUnrolls<S, decltype(void(S::UNROLL_DRIVER))> { 
 constexpr int RAW_RUNNING = -1;     // attempt(): the trajectory goes on
 constexpr int RAW_CHECKPOINT = -2;  // attempt(): nothing was computed, the whole warp reports in (RkFastStepper::tick)
 
-// does the stepper support suspending a trajectory and resuming it on another lane (tail compaction)?
-template <class S, class = void> struct StepperMigrates { static constexpr bool value = false; };
+// does the stepper support suspending a trajectory and resuming it on another lane (regrouping, below)?  The CTA's
+// exchange buffer holds STATE_DOUBLES + 1 words per lane in shared memory.
+template <class S, int BLOCK, class = void> struct StepperMigrates { static constexpr bool value = false; };
 #ifndef BACON_NO_MIGRATE  // (A/B switch for measurements)
-template <class S> struct StepperMigrates<S, decltype(void(S::STATE_DOUBLES))> {
-    static constexpr bool value = (S::STATE_DOUBLES + 1) * 8 * (2 * ENSEMBLE_BLOCK) <= 40 * 1024;  // the tail CTA's exchange buffer
+template <class S, int BLOCK> struct StepperMigrates<S, BLOCK, decltype(void(S::STATE_DOUBLES))> {
+    static constexpr bool value = BLOCK >= 256 && (S::STATE_DOUBLES + 1) * 8 * BLOCK <= 160 * 1024;
 };
 #endif
+template <class S, int BLOCK> constexpr size_t ensemble_smem_bytes() {
+    if constexpr (StepperMigrates<S, BLOCK>::value) return (size_t)(S::STATE_DOUBLES + 1) * 8 * BLOCK;
+    else return 0;
+}
 
 // Work hand-out: per-warp blocks of consecutive trajectories.  Why blocks: with dense output every lane stores into its
 // own trajectory's history, and ONE store instruction whose 32 lanes touch 32 different 2 MB pages is 4 times slower
@@ -56,23 +61,25 @@ template <class S> struct StepperMigrates<S, decltype(void(S::STATE_DOUBLES))> {
 // One 64-bit word per warp in shared memory: base << 16 | size << 8 | used.  Loop-free and safe under divergence: the
 // lane whose atomicAdd finds the block exactly exhausted refills it from the global counter; a lane that arrives while
 // that refill is in flight takes a single index from the global counter instead.
+// The launch's work counter counts the trajectories handed out AFTER the static first deal: index = first + counter.
 struct WarpQueue {
     unsigned long long* word;       // shared memory
     unsigned long long* global;     // the launch's work counter
     unsigned long long n;
+    unsigned long long first;       // lanes of the grid: the indices below were dealt statically
     unsigned long long per_block;   // BACON_WQ_DIV x warps of the grid: remaining / per_block = next block size
 
     __device__ __noinline__ unsigned long long fetch() {
         const unsigned long long s = atomicAdd(word, 1ull);
         const unsigned used = (unsigned)(s & 0xff), size = (unsigned)((s >> 8) & 0xff);
         if (used < size) return (s >> 16) + used;
-        if (used > size) return atomicAdd(global, 1ull);  // a refill is in flight (rare): take a single index instead
+        if (used > size) return first + atomicAdd(global, 1ull);  // a refill is in flight (rare): take a single index instead
         // used == size: this lane refills
-        const unsigned long long seen = *(volatile unsigned long long*)global;
+        const unsigned long long seen = first + *(volatile unsigned long long*)global;
         const unsigned long long rem = seen < n ? n - seen : 0;
         unsigned long long b = rem / per_block;
         b = b < 1 ? 1 : (b > 32 ? 32 : b);
-        const unsigned long long nb = atomicAdd(global, b);
+        const unsigned long long nb = first + atomicAdd(global, b);
         // (a block may reach past n, or start there when the counter is dry: callers test idx < n, and every later
         // fetch from such a block returns an index >= n as well)
         atomicExch(word, (nb << 16) | (b << 8) | 1ull);
@@ -81,77 +88,171 @@ struct WarpQueue {
     // nothing left to start in this warp's block and nothing left in the global counter
     __device__ __forceinline__ bool dry() const {
         const unsigned long long v = *(volatile unsigned long long*)word;
-        return (unsigned)(v & 0xff) >= (unsigned)((v >> 8) & 0xff) && *(volatile unsigned long long*)global >= n;
+        const unsigned used = (unsigned)(v & 0xff), size = (unsigned)((v >> 8) & 0xff);
+        return (used >= size || (v >> 16) + used >= n) && first + *(volatile unsigned long long*)global >= n;
     }
 };
 
-// Main kernel.  No vote and no liveness test in the loop: a lane whose trajectory ends leaves the common path on its own
-// (the branch is inside attempt()), stores its record, takes the next trajectory index from its warp's block (WarpQueue)
-// and rejoins its warp at the next attempt.  A lane that finds the queue dry is done.
+__device__ __forceinline__ void named_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Regrouping, control side (see ensemble_kernel).  Everything warp- or CTA-collective lives in three functions that
+// are NOT inlined, for two reasons.  (1) The lanes of one warp come here along different paths — live lanes from the
+// persistent loop, lanes that hold nothing from idle_until_regrouped — and must meet at the SAME vote / shuffle /
+// barrier instructions.  (2) ptxas keeps the tableau in uniform registers across the persistent loop only while the
+// loop's function holds no other loop: with the waiting loop inlined it re-loads all coefficients from the constant
+// bank on every attempt (28 LDCU per pair of attempts, tools/sass_count.py).
+struct RegroupPlan {
+    int action;    // RG_CARRY_ON, RG_EXIT, RG_EXCHANGE or RG_NOTHING_TO_FREE
+    int slot;      // RG_EXCHANGE, live lanes: where this lane's state goes in the compacted order
+    int total;     // live trajectories of the CTA
+    int w_active;  // in: warps of the CTA that are running; out (regroup_meet): the same after this regrouping
+};
+constexpr int RG_CARRY_ON = 0, RG_EXIT = 1, RG_EXCHANGE = 2, RG_NOTHING_TO_FREE = 3;
+
+// Called by all 32 lanes of a running warp when its live lanes are at a checkpoint and the counter is dry (the vote is
+// the warp's meeting point).  Posts the warp's live count; if the CTA's live trajectories (as posted: other warps'
+// numbers may be stale — too high, never too low) fit in fewer warps than are running, asks for a regrouping; if one
+// is asked for, meets the CTA's running warps at the named barrier (every one of them arrives within CHECK_EVERY
+// attempts) and plans the exchange on exact counts.
+static __device__ __noinline__ void regroup_plan(RegroupPlan* p, int* live_cnt, int* req_word, bool live) {
+    const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+    const int w_active = p->w_active;
+    volatile int* cnt = live_cnt;
+    const unsigned live_mask = __ballot_sync(FULL_MASK, live);
+    const int mine = __popc(live_mask);
+    if (lane == 0) cnt[warp] = mine;
+    int c = lane < w_active ? (lane == warp ? mine : cnt[lane]) : 0;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(FULL_MASK, c, m);
+    if (((c + 31) >> 5) < w_active && lane == 0) *(volatile int*)req_word = 1;
+    __syncwarp();
+    int req = 0;  // (read by one lane: the whole warp must take the same side)
+    if (lane == 0) req = *(volatile int*)req_word;
+    p->action = RG_CARRY_ON;
+    if (__shfl_sync(FULL_MASK, req, 0) == 0) return;
+
+    named_barrier(1, w_active * 32);
+    c = lane < w_active ? cnt[lane] : 0;  // exact now
+    int incl = c;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        const int up = __shfl_up_sync(FULL_MASK, incl, m);
+        if (lane >= m) incl += up;
+    }
+    const int total = __shfl_sync(FULL_MASK, incl, 31);
+    const int my_off = __shfl_sync(FULL_MASK, incl - c, warp);
+    p->total = total;
+    p->slot = my_off + __popc(live_mask & lanemask_lt());
+    p->action = total == 0 ? RG_EXIT : (((total + 31) >> 5) < w_active ? RG_EXCHANGE : RG_NOTHING_TO_FREE);
+}
+// Second meeting of a regrouping: the live lanes' states are in shared memory (or there was nothing to exchange).
+// Afterwards the lowest ceil(total / 32) warps go on: lane l of warp w owns slot 32 w + l.
+static __device__ __noinline__ void regroup_meet(RegroupPlan* p, int* live_cnt, int* req_word) {
+    if (threadIdx.x == 0) *(volatile int*)req_word = 0;
+    __syncwarp();
+    named_barrier(1, p->w_active * 32);
+    if (p->action == RG_EXCHANGE) {
+        const int warp = (int)(threadIdx.x >> 5);
+        p->w_active = (p->total + 31) >> 5;
+        const int left = p->total - warp * 32;
+        if ((threadIdx.x & 31) == 0 && warp < p->w_active) *(volatile int*)&live_cnt[warp] = left < 32 ? left : 32;
+    }
+}
+// A lane that holds nothing waits for the regrouping that gives it a trajectory: returns its slot in the exchange
+// buffer, or -1 when its warp is freed (or the CTA is finished).
+static __device__ __noinline__ int idle_until_regrouped(RegroupPlan* p, int* live_cnt, int* req_word) {
+    for (;;) {
+        regroup_plan(p, live_cnt, req_word, false);
+        if (p->action == RG_CARRY_ON) continue;  // the others ran another CHECK_EVERY attempts
+        if (p->action == RG_EXIT) return -1;
+        regroup_meet(p, live_cnt, req_word);
+        if (p->action != RG_EXCHANGE) continue;
+        const int warp = (int)(threadIdx.x >> 5), slot = (int)threadIdx.x;  // = 32 warp + lane
+        if (warp >= p->w_active) return -1;
+        if (slot < p->total) return slot;
+    }
+}
+
+// The kernel.  One CTA of BLOCK lanes; a lane integrates one trajectory at a time.
 //
-// Tail (steppers that migrate, `tail` != nullptr).  The lanes decohere over the run, so when the counter runs dry the
-// remaining work per lane is spread evenly between nothing and a whole trajectory; left alone, each warp would run
-// until its LONGEST lane ends with ever fewer lanes active — and a warp instruction occupies the FP64 pipe for the same
-// time with 1 active lane as with 32: the tail costs half a trajectory time whatever the ensemble size (measured:
-// 1.75 ms of a 31.6 ms launch, profiles/r01g_tail.md).  So at its next checkpoint after the counter ran dry (every
-// CHECK_EVERY attempts the whole warp reports in: nothing is polled per attempt) a warp SUSPENDS: every lane writes
-// its trajectory's state to its slot of `tail` and the kernel ends; ensemble_tail_kernel re-deals and finishes them.
-// Slot layout: tail[w][grid*128] doubles, w < STATE_DOUBLES + 1 (the last word is the trajectory index, -1 = none).
-template <class Stepper, bool HIST, int MINB>
-__global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB)
-    ensemble_kernel(const __grid_constant__ bacon_launch_args a, double* __restrict__ tail) {
+// First deal (static): bundle j = 32 consecutive trajectories; warp w of CTA b starts on bundle w * gridDim.x + b, so a
+// small ensemble spreads over all CTAs (and, inside a CTA, over its lowest warps = evenly over the SM's four
+// sub-partitions) and a large one starts without a single atomic.  After that a lane whose trajectory retires
+// (Done / Failure) takes the next index from the launch's work counter.  No vote and no liveness test in the loop: the
+// lane leaves the common path on its own (the branch is inside attempt()), stores its record, re-arms and rejoins its
+// warp at the next attempt.
+//
+// End of the ensemble (steppers that migrate).  Once the counter is dry, lanes that retire have nothing to take, and a
+// warp instruction occupies the FP64 pipe for the same time with 1 active lane as with 32: left alone, every warp
+// would run until its LONGEST lane ends with ever fewer lanes active (measured in round 1: a fixed 1.75 ms per launch,
+// half a trajectory time, whatever the ensemble size; and for an ensemble that fits the grid once, every warp pays
+// max-of-32 instead of the mean step count: +12 % on Lorenz).  So the CTA REGROUPS: every CHECK_EVERY attempts the lanes
+// of a warp report in together (the tick axis of the stepper: nothing is polled per attempt); once the counter is dry
+// the warp posts how many of its lanes still hold a trajectory, and as soon as the CTA's live trajectories fit in fewer
+// warps than are running, all warps meet at a named barrier, the live lanes write their stepper state
+// (Stepper::save, STATE_DOUBLES + 1 words) to shared memory in compacted order, the lowest ceil(live / 32) warps read
+// them back (Stepper::load) and the freed warps exit.  Between two regroupings the warps run freely (no barrier), so a
+// sub-partition that holds one warp fewer simply runs its warps faster.  With one CTA per SM (BLOCK = all resident
+// lanes of the SM) this is an SM-wide re-deal; per-SM work is even by the law of large numbers (886 trajectories per SM
+// at 131072 per GPU: 0.3 % spread).  A trajectory's numbers do not depend on where it ran
+// (tests/test_gpu_rk.py::test_tail_kernel_and_dense_output_do_not_change_a_trajectory: bitwise).
+template <class Stepper, bool HIST, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_constant__ bacon_launch_args a) {
     constexpr int D = Stepper::D;
-    constexpr bool MIGRATE = StepperMigrates<Stepper>::value;
+    constexpr bool MIGRATE = StepperMigrates<Stepper, BLOCK>::value;
+    constexpr int NW = BLOCK / 32;
+    static_assert(BLOCK % 32 == 0 && NW <= 32, "a CTA is at most 32 warps");
     using Codec = StepperCodec<Stepper>;
+
+    extern __shared__ double xch[];  // MIGRATE: [STATE_DOUBLES + 1][BLOCK] exchange buffer of a regrouping
+    __shared__ unsigned long long wq_words[NW];
+    __shared__ int live_cnt[32];     // MIGRATE: live lanes per warp, as last posted
+    __shared__ int regroup_req;
 
     Stepper s(a);
     HistStage<D, HIST> hist(a);
     const unsigned long long n = a.n;
-    const size_t lanes = (size_t)gridDim.x * ENSEMBLE_BLOCK, me = (size_t)blockIdx.x * ENSEMBLE_BLOCK + threadIdx.x;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned long long lanes = (unsigned long long)gridDim.x * BLOCK;
+    const unsigned long long n_rest = n > lanes ? n - lanes : 0;  // what the work counter hands out
 
-    // a lane leaves the kernel: its slot of `tail` says what it leaves behind (nothing, or a suspended trajectory)
-    auto leave = [&](bool suspended, unsigned long long idx) {
-        if constexpr (MIGRATE) {
-            if (tail) {
-                constexpr int W = Stepper::STATE_DOUBLES + 1;
-                if (suspended) {
-                    double st[W];
-                    s.save(st);
-#pragma unroll
-                    for (int w = 0; w < W - 1; ++w) tail[(size_t)w * lanes + me] = st[w];
-                }
-                tail[(size_t)(W - 1) * lanes + me] = __longlong_as_double(suspended ? (long long)idx : -1ll);
-            }
-        }
-    };
+    // ---- static first deal
+    const unsigned long long bundles = ((n < lanes ? n : lanes) + 31) >> 5;
+    int w_active = 0;  // warps of this CTA that hold a bundle
+    if (bundles > blockIdx.x) {
+        const unsigned long long mine = (bundles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        w_active = mine < (unsigned long long)NW ? (int)mine : NW;
+    }
+    if constexpr (MIGRATE) {
+        if (threadIdx.x < 32) live_cnt[threadIdx.x] = 32;
+        if (threadIdx.x == 0) regroup_req = 0;
+        __syncthreads();
+    }
+    if ((int)warp >= w_active) return;
+    unsigned long long idx = ((unsigned long long)warp * gridDim.x + blockIdx.x) * 32 + lane;
+    bool live = idx < n;
 
-    __shared__ unsigned long long wq_words[ENSEMBLE_BLOCK / 32];
 #ifndef BACON_WQ_DIV
 #define BACON_WQ_DIV 1  // block size = remaining / (BACON_WQ_DIV x warps of the grid), clamped to [1, 32]
 #endif
-    WarpQueue wq{&wq_words[threadIdx.x >> 5], a.work_counter, n, (unsigned long long)BACON_WQ_DIV * (ENSEMBLE_BLOCK / 32) * gridDim.x};
-    // the first 32 trajectories of the warp: one aggregated fetch; the queue starts as an exhausted block
-    unsigned long long idx = warp_fetch(a.work_counter, true);
-    if ((threadIdx.x & 31) == 0) *wq.word = (1ull << 8) | 1ull;
+    WarpQueue wq{&wq_words[warp], a.work_counter, n, lanes, (unsigned long long)BACON_WQ_DIV * NW * gridDim.x};
+    if (HIST && lane == 0) *wq.word = (1ull << 8) | 1ull;  // the queue starts as an exhausted block
     __syncwarp();
 
-    if (idx >= n) {
-        leave(false, 0);
-        return;
+    if (live) {
+        s.reset(a, idx, true);
+        hist.begin(idx);
     }
-    s.reset(a, idx, true);
-    hist.begin(idx);
-    auto step = [&]() -> bool {  // one IVPIterator::next; true = this lane leaves the kernel
+    auto step = [&]() -> bool {  // one IVPIterator::next; true = this lane leaves the loop (nothing to run, or its warp reports in)
         bool yielded = false;
         const uint32_t n_acc_before = HIST ? Codec::acc_running(s) : 0u;
         const int raw = s.attempt(yielded);
         hist.push(yielded, n_acc_before, s.out_t(), s.out_y());
         if (raw != RAW_RUNNING) {  // rare
             if (raw == RAW_CHECKPOINT) {
-                if (MIGRATE && tail && (HIST ? wq.dry() : *(volatile unsigned long long*)a.work_counter >= n)) {
-                    leave(true, idx);  // suspend
-                    return true;
-                }
+                if (MIGRATE && (HIST ? wq.dry() : *(volatile unsigned long long*)a.work_counter >= n_rest)) return true;
             } else {
                 const uint32_t n_acc = Codec::acc(s, raw);
                 hist.retire(idx, n_acc);
@@ -159,9 +260,9 @@ __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB)
                 if (HIST && st == BACON_OK && n_acc > (uint32_t)a.cfg.history_capacity) st = BACON_E_HISTORY_OVERFLOW;
                 store_result<D>(a.out, n, idx, s.end_y(), s.t, s.dt, st, n_acc, s.n_rej, s.n_rhs());
                 // (final state only: which trajectory a lane runs next does not matter — one global atomicAdd)
-                idx = HIST ? wq.fetch() : atomicAdd(a.work_counter, 1ull);
+                idx = HIST ? wq.fetch() : lanes + atomicAdd(a.work_counter, 1ull);
                 if (idx >= n) {
-                    leave(false, 0);
+                    live = false;
                     return true;
                 }
                 s.reset(a, idx, true);
@@ -170,92 +271,57 @@ __global__ void __launch_bounds__(ENSEMBLE_BLOCK, MINB)
         }
         return false;
     };
+    // the warp reports in (its live lanes are at a checkpoint and the counter is dry, the others hold nothing); true =
+    // this lane leaves the kernel.  (No loop in here: see RegroupPlan.)
+    auto report = [&]() -> bool {
+        if constexpr (!MIGRATE) {
+            return true;  // (the lane has nothing left to run)
+        } else {
+            constexpr int W = Stepper::STATE_DOUBLES + 1;
+            RegroupPlan plan;
+            plan.w_active = w_active;
+            int slot = -1;
+            if (live) {
+                regroup_plan(&plan, live_cnt, &regroup_req, true);
+                if (plan.action == RG_CARRY_ON) return false;
+                if (plan.action == RG_EXIT) return true;
+                if (plan.action == RG_EXCHANGE) {
+                    double st[W];
+                    s.save(st);
+                    st[W - 1] = __longlong_as_double((long long)idx);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) xch[w * BLOCK + plan.slot] = st[w];
+                }
+                regroup_meet(&plan, live_cnt, &regroup_req);
+                if (plan.action != RG_EXCHANGE) return false;
+                w_active = plan.w_active;
+                if ((int)warp >= w_active) return true;  // freed
+                live = (int)threadIdx.x < plan.total;
+                if (live) slot = (int)threadIdx.x;
+            }
+            if (!live) {
+                slot = idle_until_regrouped(&plan, live_cnt, &regroup_req);
+                if (slot < 0) return true;
+                w_active = plan.w_active;
+                live = true;
+            }
+            double st[W];
+#pragma unroll
+            for (int w = 0; w < W; ++w) st[w] = xch[w * BLOCK + slot];
+            idx = (unsigned long long)__double_as_longlong(st[W - 1]);
+            s.load(st);
+            hist.begin(idx);
+            return false;
+        }
+    };
+    if (!live && report()) return;  // (the ragged end of the last bundle)
     for (;;) {
-        if (step()) return;
+        if (step() && report()) return;
         // steppers with a short body (RkFastStepper) take two per iteration: the copies that carry dt and the call
         // counter round the loop, and the loop's own branch, are then paid once per pair (31 -> 28.5 non-FP64
         // instructions per attempt)
         if constexpr (StepperUnrolls<Stepper>::value) {
-            if (step()) return;
-        }
-    }
-}
-
-// Which eighth of the CTA's sorted trajectories a warp takes in the tail.  Measured with tools/smsp_probe.cu on B200:
-// a warp runs on sub-partition %warpid % 4 (two warps with the same value share one FP64 pipe), a 256-thread CTA holds
-// hardware warp slots 8k..8k+7 (k = %warpid / 8 = the CTA's slot on its SM; its warps w and w+4 share a
-// sub-partition), and the hardware already rotates which warp of the CTA starts on sub-partition 0.  The two warps of
-// a CTA on sub-partition j take the octiles o and 7 - o, o = (j + k) mod 4: every sub-partition holds the same amount
-// of work whatever the number of resident CTAs, and its warps retire at evenly spread times.
-constexpr int TAIL_BLOCK = 2 * ENSEMBLE_BLOCK;
-__device__ __forceinline__ int tail_octile() {
-    unsigned hw;
-    asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw));
-    const int j = hw & 3, second = (hw >> 2) & 1, k = hw >> 3;
-    const int o = (j + k) & 3;
-    return second ? 7 - o : o;
-}
-
-// Tail kernel (one CTA of 256 lanes per two CTAs of the main kernel): the CTA sorts the 256 suspended trajectories of its
-// slots by remaining time and deals them so that each warp holds one octile — warps retire one after the other and
-// the sub-partitions thin out — then runs them to their end, no refills.
-template <class Stepper, bool HIST, int MINB>
-__global__ void __launch_bounds__(TAIL_BLOCK, (MINB + 1) / 2)
-    ensemble_tail_kernel(const __grid_constant__ bacon_launch_args a, const double* __restrict__ tail, unsigned long long lanes) {
-    constexpr int D = Stepper::D;
-    using Codec = StepperCodec<Stepper>;
-    constexpr int W = Stepper::STATE_DOUBLES + 1;
-    __shared__ double slots[W][TAIL_BLOCK];
-    __shared__ int keys[TAIL_BLOCK];
-
-    Stepper s(a);
-    HistStage<D, HIST> hist(a);
-    const size_t g = (size_t)blockIdx.x * TAIL_BLOCK + threadIdx.x;  // slot written by lane g of the main kernel
-    const int me = threadIdx.x;
-
-    double st[W];
-    st[W - 1] = g < lanes ? tail[(size_t)(W - 1) * lanes + g] : __longlong_as_double(-1ll);
-    const bool had = __double_as_longlong(st[W - 1]) >= 0;
-#pragma unroll
-    for (int w = 0; w < W - 1; ++w) st[w] = had ? tail[(size_t)w * lanes + g] : 0.0;
-    // sort key: the float's bit pattern as an integer — monotone for the non-negative values that matter, and a total
-    // order (with the index as tie-break) whatever the value, so `rank` is always a permutation; empty slots sort low
-    int key = -1;
-    if (had) {
-        s.load(st);
-        key = __float_as_int((float)s.remaining());
-    }
-    keys[me] = key;
-    __syncthreads();
-    int rank = 0;
-    for (int j = 0; j < TAIL_BLOCK; ++j) {
-        const int kj = keys[j];
-        rank += (kj < key || (kj == key && j < me)) ? 1 : 0;
-    }
-#pragma unroll
-    for (int w = 0; w < W; ++w) slots[w][rank] = st[w];
-    __syncthreads();
-    const int src = tail_octile() * 32 + (me & 31);
-#pragma unroll
-    for (int w = 0; w < W; ++w) st[w] = slots[w][src];
-    const long long moved = __double_as_longlong(st[W - 1]);
-    if (moved < 0) return;
-    const unsigned long long idx = (unsigned long long)moved;
-    s.load(st);
-    hist.begin(idx);
-
-    for (;;) {
-        bool yielded = false;
-        const uint32_t n_acc_before = HIST ? Codec::acc_running(s) : 0u;
-        const int raw = s.attempt(yielded);
-        hist.push(yielded, n_acc_before, s.out_t(), s.out_y());
-        if (raw >= 0) {
-            const uint32_t n_acc = Codec::acc(s, raw);
-            hist.retire(idx, n_acc);
-            int stt = Codec::status(s, raw);
-            if (HIST && stt == BACON_OK && n_acc > (uint32_t)a.cfg.history_capacity) stt = BACON_E_HISTORY_OVERFLOW;
-            store_result<D>(a.out, a.n, idx, s.end_y(), s.t, s.dt, stt, n_acc, s.n_rej, s.n_rhs());
-            return;
+            if (step() && report()) return;
         }
     }
 }

@@ -18,15 +18,16 @@
 
 namespace bacon {
 
-// grid of a persistent launch: resident CTAs per SM (occupancy of `kernel`) x SM count, capped by the work
-template <class K> inline int persistent_grid(K kernel, bacon_launch_args* a, size_t smem) {
+// grid of a persistent launch: resident CTAs per SM (occupancy of `kernel`) x SM count, capped by the work (one
+// bundle of 32 trajectories per warp: a small ensemble spreads over as many CTAs as it has bundles)
+template <int BLOCK, class K> inline int persistent_grid(K kernel, bacon_launch_args* a, size_t smem) {
     cudaError_t e;
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {  // (static + dynamic above 48 KB needs the opt-in: the kernel holds a few hundred static bytes)
         e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return BACON_E_CUDA;
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ENSEMBLE_BLOCK, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, smem);
     if (e != cudaSuccess || per_sm < 1) return BACON_E_CUDA;
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, kernel);
@@ -36,67 +37,36 @@ template <class K> inline int persistent_grid(K kernel, bacon_launch_args* a, si
         if (want >= 1 && want < per_sm) per_sm = want;
     }
     long long grid = (long long)per_sm * a->sm_count;
-    const long long need = (long long)((a->n + ENSEMBLE_BLOCK - 1) / ENSEMBLE_BLOCK);
+    const long long need = (long long)((a->n + 31) / 32);
     if (grid > need) grid = need;
     if (a->grid_override > 0) grid = a->grid_override;
-    if (const char* env = getenv("BACON_IVP_GRID")) {  // a small grid makes small ensembles refill, run dry and suspend
+    if (const char* env = getenv("BACON_IVP_GRID")) {  // a small grid makes small ensembles refill, run dry and regroup
         const int want = atoi(env);                     // (tests, compute-sanitizer runs)
         if (want >= 1 && want < grid) grid = want;
     }
     if (grid < 1) grid = 1;
     a->grid = (int)grid;
-    a->block = ENSEMBLE_BLOCK;
+    a->block = BLOCK;
     a->regs_per_thread = fa.numRegs;
-    a->late_from = (unsigned long long)grid * ENSEMBLE_BLOCK;  // the first trajectory of every lane comes before this
+    a->late_from = (unsigned long long)grid * BLOCK;  // the first trajectory of every lane comes before this
     return 0;
 }
 
-// stream-ordered scratch for the suspended trajectories of the tail (drive.cuh): the pool keeps its memory between
-// launches (release threshold raised once per device), so this is a free-list lookup, not a cudaMalloc
-inline cudaError_t tail_scratch_alloc(double** p, size_t bytes, cudaStream_t st) {
-    static bool pool_ready[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        pool_ready[dev] = true;
-    }
-    return cudaMallocAsync((void**)p, bytes, st);
-}
+// Steppers that can suspend and resume a trajectory (Stepper::save / load) run as ONE CTA per SM holding all the
+// lanes the register budget allows (128 x MINB), so that the end-of-ensemble regrouping (drive.cuh) is SM-wide;
+// the others keep 128-lane CTAs, MINB of them per SM.
+template <class Stepper, class = void> struct StepperSuspends { static constexpr bool value = false; };
+template <class Stepper> struct StepperSuspends<Stepper, decltype(void(Stepper::STATE_DOUBLES))> { static constexpr bool value = true; };
 
 template <class Stepper, bool HIST, int MINB> inline int launch_stepper_hist(bacon_launch_args* a) {
-    auto kernel = ensemble_kernel<Stepper, HIST, MINB>;
-    if (const int rc = persistent_grid(kernel, a, 0)) return rc;
-    cudaStream_t st = (cudaStream_t)a->stream;
-    double* tail = nullptr;
-    if constexpr (StepperMigrates<Stepper>::value) {
-        // a tail only exists when lanes take more than one trajectory; BACON_IVP_NO_TAIL=1 switches it off (A/B)
-        static const bool no_tail = getenv("BACON_IVP_NO_TAIL") != nullptr;
-        if (!no_tail && a->n > (unsigned long long)a->grid * ENSEMBLE_BLOCK) {
-            const size_t bytes = sizeof(double) * (Stepper::STATE_DOUBLES + 1) * (size_t)a->grid * ENSEMBLE_BLOCK;
-            if (tail_scratch_alloc(&tail, bytes, st) != cudaSuccess) {
-                (void)cudaGetLastError();
-                tail = nullptr;  // no scratch: the main kernel runs every trajectory to its end itself
-            }
-        }
-    }
+    constexpr bool WIDE = StepperSuspends<Stepper>::value && StepperMigrates<Stepper, ENSEMBLE_BLOCK * MINB>::value;
+    constexpr int BLOCK = WIDE ? ENSEMBLE_BLOCK * MINB : ENSEMBLE_BLOCK;
+    auto kernel = ensemble_kernel<Stepper, HIST, BLOCK, (WIDE ? 1 : MINB)>;
+    constexpr size_t smem = ensemble_smem_bytes<Stepper, BLOCK>();
+    if (const int rc = persistent_grid<BLOCK>(kernel, a, smem)) return rc;
     a->n_kernels = 1;
-    kernel<<<(unsigned)a->grid, ENSEMBLE_BLOCK, 0, st>>>(*a, tail);
+    kernel<<<(unsigned)a->grid, BLOCK, smem, (cudaStream_t)a->stream>>>(*a);
     if (cudaGetLastError() != cudaSuccess) return BACON_E_CUDA;
-    if constexpr (StepperMigrates<Stepper>::value) {
-        if (tail) {
-            const unsigned long long lanes = (unsigned long long)a->grid * ENSEMBLE_BLOCK;
-            const unsigned tail_grid = (unsigned)((lanes + TAIL_BLOCK - 1) / TAIL_BLOCK);
-            ensemble_tail_kernel<Stepper, HIST, MINB><<<tail_grid, TAIL_BLOCK, 0, st>>>(*a, tail, lanes);
-            if (cudaGetLastError() != cudaSuccess) return BACON_E_CUDA;
-            a->n_kernels = 2;
-            if (cudaFreeAsync(tail, st) != cudaSuccess) return BACON_E_CUDA;
-        }
-    }
     return 0;
 }
 

@@ -3,7 +3,7 @@
 // The registration-macro path (include/bacon_ivp_rhs.cuh) needs nvcc when the user's crate is built.  This path needs
 // nothing but the library: the functor arrives as CUDA C++ source text, NVRTC compiles it TOGETHER with the kernel
 // headers (embedded in the library at build time, build/embedded_headers.inc), so the right-hand side is inlined into
-// the stage loops exactly as for a built-in — the same ensemble_kernel / ensemble_tail_kernel templates, instantiated
+// the stage loops exactly as for a built-in — the same ensemble_kernel template, instantiated
 // on demand: one NVRTC program per (method, strict/fast, dense output or not) the caller actually uses, cached per
 // device.  libnvrtc and libcuda are loaded lazily (dlopen), so the library still loads where they are absent
 // (BACON_E_UNSUPPORTED from this entry point only).  Launching mirrors launch.cuh through the driver API.
@@ -50,7 +50,7 @@ int rtc_fail(int code, const char* fmt, ...) {
 #define RTC_SYMS(X) X(nvrtcCreateProgram) X(nvrtcCompileProgram) X(nvrtcGetProgramLogSize) X(nvrtcGetProgramLog) \
     X(nvrtcGetCUBINSize) X(nvrtcGetCUBIN) X(nvrtcAddNameExpression) X(nvrtcGetLoweredName) X(nvrtcDestroyProgram)
 #define DRV_SYMS(X) X(cuModuleLoadData) X(cuModuleGetFunction) X(cuModuleGetGlobal_v2) X(cuLaunchKernel)         \
-    X(cuFuncGetAttribute) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemcpyHtoDAsync_v2) X(cuGetErrorString)
+    X(cuFuncGetAttribute) X(cuFuncSetAttribute) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemcpyHtoDAsync_v2) X(cuGetErrorString)
 struct Api {
     bool ok = false, drv_ok = false;  // NVRTC alone is enough to compile (and to reject) a source; launching needs the driver
     std::string why;
@@ -90,10 +90,14 @@ Api& api() {
 // ---------------------------------------------------------------- one registered source
 struct Compiled {  // one NVRTC program: the kernels of one (method, strict, newton, hist) for one architecture
     std::vector<char> cubin;
-    std::string main, tail, tableau;  // lowered names ("" = not in this program)
+    std::string main, tail, tableau;  // lowered names ("" = not in this program; tail: the events kernel of a path program)
+    int block = 128;                  // CTA size the ensemble kernel was instantiated for
+    size_t smem = 0;                  // its dynamic shared memory (exchange buffer of the regrouping)
 };
 struct Variant {  // ... loaded on one device
     CUfunction main = nullptr, tail = nullptr;
+    int block = 128;
+    size_t smem = 0;
     CUdeviceptr tableau = 0;  // strict RK: address of bacon::c_rk_tab in this module
 };
 struct RtcRhs {
@@ -109,12 +113,13 @@ std::vector<std::unique_ptr<RtcRhs>> g_rtc;
 
 const char* tab_name(int method) { return (method == BACON_RK45) ? "bacon::TabRKF45" : "bacon::TabBS23"; }
 
-// what launch.cuh would instantiate for this call: stepper type, register budget, and whether a tail kernel exists
-struct Plan { std::string stepper; int minb; bool tail; };
+// what launch.cuh would instantiate for this call: stepper type, CTA size, resident CTAs per SM the kernel is compiled
+// for, and the exchange buffer of the end-of-ensemble regrouping (drive.cuh)
+struct Plan { std::string stepper; int minb; int block; size_t smem; int state_doubles; };
 int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist, Plan* p) {
     const std::string T = r.type_name;
     const bool newton = (c.flags & BACON_FLAG_BDF_NEWTON) != 0;
-    p->tail = false;
+    p->state_doubles = 0;
     switch (c.method) {
         case BACON_RK45:
         case BACON_RK23: {
@@ -126,7 +131,7 @@ int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
                 if (c.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;
                 p->stepper = "bacon::RkFastStepper<" + T + ", " + tab_name(c.method) + ">";
                 p->minb = r.dim * (O + 1) + r.n_params <= 28 ? 6 : 4;                 // rk_fast_minb (launch.cuh)
-                p->tail = (r.dim + r.n_params + 3 + 1) * 8 * 256 <= 40 * 1024;         // StepperMigrates (drive.cuh)
+                p->state_doubles = r.dim + r.n_params + 3;                             // RkFastStepper::STATE_DOUBLES
             }
             break;
         }
@@ -154,6 +159,17 @@ int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
             return BACON_E_BAD_ARGUMENT;
     }
     if (hist && p->minb >= 6) p->minb -= 1;  // MINB_HIST (launch.cuh)
+    // launch_stepper_hist (launch.cuh): steppers that suspend run as one wide CTA per SM when its exchange buffer fits
+    p->block = 128;
+    p->smem = 0;
+    if (p->state_doubles > 0) {
+        const int wide = 128 * p->minb;
+        if (wide >= 256 && (size_t)(p->state_doubles + 1) * 8 * wide <= 160 * 1024) {  // StepperMigrates (drive.cuh)
+            p->block = wide;
+            p->minb = 1;
+            p->smem = (size_t)(p->state_doubles + 1) * 8 * wide;
+        }
+    }
     return 0;
 }
 
@@ -168,8 +184,7 @@ int compile_program(RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
     src += "static_assert(" + r.type_name + "::DIM == " + std::to_string(r.dim) + " && " + r.type_name +
            "::NPARAM == " + std::to_string(r.n_params) + ", \"DIM / NPARAM of the functor differ from the registration\");\n";
     const std::string h = hist ? "true" : "false", m = std::to_string(plan.minb);
-    const std::string k_main = "&bacon::ensemble_kernel<" + plan.stepper + ", " + h + ", " + m + ">";
-    const std::string k_tail = "&bacon::ensemble_tail_kernel<" + plan.stepper + ", " + h + ", " + m + ">";
+    const std::string k_main = "&bacon::ensemble_kernel<" + plan.stepper + ", " + h + ", " + std::to_string(plan.block) + ", " + m + ">";
     const std::string k_tab = "&bacon::c_rk_tab";
     const bool want_tab = strict && (c.method == BACON_RK45 || c.method == BACON_RK23);
 
@@ -179,7 +194,6 @@ int compile_program(RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
     if (A.nvrtcCreateProgram(&prog, src.c_str(), (r.name + ".cu").c_str(), kNumHeaders, hdr_text.data(), hdr_name.data()) != NVRTC_SUCCESS)
         return rtc_fail(BACON_E_CUDA, "nvrtcCreateProgram failed");
     A.nvrtcAddNameExpression(prog, k_main.c_str());
-    if (plan.tail) A.nvrtcAddNameExpression(prog, k_tail.c_str());
     if (want_tab) A.nvrtcAddNameExpression(prog, k_tab.c_str());
     const std::string arch = "--gpu-architecture=sm_" + std::to_string(cc_major) + std::to_string(cc_minor) + (cc_major >= 9 ? "a" : "");
     std::vector<const char*> opts = {arch.c_str(), "-std=c++17", "-default-device", "-lineinfo"};
@@ -200,7 +214,8 @@ int compile_program(RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
     const char* l = nullptr;
     A.nvrtcGetLoweredName(prog, k_main.c_str(), &l);
     out->main = l ? l : "";
-    if (plan.tail && A.nvrtcGetLoweredName(prog, k_tail.c_str(), &l) == NVRTC_SUCCESS) out->tail = l;
+    out->block = plan.block;
+    out->smem = plan.smem;
     if (want_tab && A.nvrtcGetLoweredName(prog, k_tab.c_str(), &l) == NVRTC_SUCCESS) out->tableau = l;
     A.nvrtcDestroyProgram(&prog);
     return 0;
@@ -220,6 +235,11 @@ int load_variant(const RtcRhs& r, const Compiled& p, Variant* out) {
     if ((e = A.cuModuleGetFunction(&out->main, mod, p.main.c_str())) != CUDA_SUCCESS) return drv_fail("cuModuleGetFunction");
     if (!p.tail.empty() && (e = A.cuModuleGetFunction(&out->tail, mod, p.tail.c_str())) != CUDA_SUCCESS)
         return drv_fail("cuModuleGetFunction(tail)");
+    out->block = p.block;
+    out->smem = p.smem;
+    if (p.smem > 32 * 1024 &&
+        (e = A.cuFuncSetAttribute(out->main, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)p.smem)) != CUDA_SUCCESS)
+        return drv_fail("cuFuncSetAttribute(max dynamic shared memory)");
     if (!p.tableau.empty()) {
         size_t bytes = 0;
         if ((e = A.cuModuleGetGlobal_v2(&out->tableau, &bytes, mod, p.tableau.c_str())) != CUDA_SUCCESS) return drv_fail("cuModuleGetGlobal");
@@ -264,16 +284,16 @@ int rtc_launch(int slot, bacon_launch_args* a) {
         }
         v = it->second;
     }
-    constexpr int BLOCK = 128;
+    const int BLOCK = v.block;
     int per_sm = 0, regs = 0;
-    if (A.cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.main, BLOCK, 0) != CUDA_SUCCESS || per_sm < 1) return BACON_E_CUDA;
+    if (A.cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.main, BLOCK, v.smem) != CUDA_SUCCESS || per_sm < 1) return BACON_E_CUDA;
     A.cuFuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, v.main);
     if (const char* env = getenv("BACON_IVP_BLOCKS_PER_SM")) {
         const int want = atoi(env);
         if (want >= 1 && want < per_sm) per_sm = want;
     }
     long long grid = (long long)per_sm * a->sm_count;
-    const long long need = (long long)((a->n + BLOCK - 1) / BLOCK);
+    const long long need = (long long)((a->n + 31) / 32);  // one bundle of 32 trajectories per warp (persistent_grid)
     if (grid > need) grid = need;
     if (a->grid_override > 0) grid = a->grid_override;
     if (const char* env = getenv("BACON_IVP_GRID")) {
@@ -294,27 +314,9 @@ int rtc_launch(int slot, bacon_launch_args* a) {
         // (pageable source: the driver stages the bytes before it returns)
         if (A.cuMemcpyHtoDAsync_v2(v.tableau, &T, sizeof(T), st) != CUDA_SUCCESS) return BACON_E_CUDA;
     }
-    double* tail = nullptr;
-    const unsigned long long lanes = (unsigned long long)grid * BLOCK;
-    if (v.tail && !getenv("BACON_IVP_NO_TAIL") && a->n > lanes) {
-        const size_t bytes = sizeof(double) * (size_t)(r->dim + r->n_params + 3 + 1) * lanes;
-        if (cudaMallocAsync((void**)&tail, bytes, (cudaStream_t)st) != cudaSuccess) {
-            (void)cudaGetLastError();
-            tail = nullptr;
-        }
-    }
     bacon_launch_args args = *a;
-    void* p_main[] = {&args, &tail};
-    if (A.cuLaunchKernel(v.main, (unsigned)grid, 1, 1, BLOCK, 1, 1, 0, st, p_main, nullptr) != CUDA_SUCCESS) return BACON_E_CUDA;
-    if (tail) {
-        unsigned long long lanes_arg = lanes;
-        const double* tail_c = tail;
-        void* p_tail[] = {&args, &tail_c, &lanes_arg};
-        const unsigned tail_grid = (unsigned)((lanes + 255) / 256);
-        if (A.cuLaunchKernel(v.tail, tail_grid, 1, 1, 256, 1, 1, 0, st, p_tail, nullptr) != CUDA_SUCCESS) return BACON_E_CUDA;
-        a->n_kernels = 2;
-        if (cudaFreeAsync(tail, (cudaStream_t)st) != cudaSuccess) return BACON_E_CUDA;
-    }
+    void* p_main[] = {&args};
+    if (A.cuLaunchKernel(v.main, (unsigned)grid, 1, 1, BLOCK, 1, 1, (unsigned)v.smem, st, p_main, nullptr) != CUDA_SUCCESS) return BACON_E_CUDA;
     return 0;
 }
 

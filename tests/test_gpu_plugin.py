@@ -133,7 +133,7 @@ struct LorenzRtc {  // p = (sigma, rho, beta): the same expression trees as the 
 def test_runtime_compiled_rhs_equals_the_built_in(cuda, engine, oracle, monkeypatch):
     """bacon_rhs_register_source: the Lorenz functor handed over as source text and compiled by NVRTC with the library's
     own kernel headers must behave like the built-in compiled by nvcc — bit for bit with the oracle in the strict
-    kernels (history included), inside the parity band of the built-in in the fast ones, through every stepper family, with the tail kernel, and a source error must surface as UserError."""
+    kernels (history included), inside the parity band of the built-in in the fast ones, through every stepper family, with regrouping, and a source error must surface as UserError."""
     from bacon_b200 import ensembles as E
     from parity import run_both
     rid = engine.register_rhs_source("lorenz_rtc", "LorenzRtc", LORENZ_SRC, 3, 3)
@@ -172,8 +172,8 @@ def test_runtime_compiled_rhs_equals_the_built_in(cuda, engine, oracle, monkeypa
         np.testing.assert_array_equal(g.n_accept, r["n_accept"])
         mask = np.arange(96)[None, :] < g.hist_len[:, None]
         assert np.array_equal(g.hist_y[mask], r["hist_y"][mask])
-    # fast, on a tiny grid so that lanes refill and the tail kernel runs: the same bits as the built-in
-    monkeypatch.setenv("BACON_IVP_GRID", "6")
+    # fast, on a tiny grid so that lanes refill and the CTAs regroup: the same bits as the built-in
+    monkeypatch.setenv("BACON_IVP_GRID", "2")
     for method, extra in (("RK45", {}), ("RK23", {}), ("BDF6", dict(flags=_abi.FLAG_BDF_NEWTON)), ("BDF2", {}), ("Adams5", {}),
                           ("Euler", {})):
         cfg = dict(LOR, t_end=0.05)
@@ -182,7 +182,8 @@ def test_runtime_compiled_rhs_equals_the_built_in(cuda, engine, oracle, monkeypa
         a = make_solver(engine, method, 3, rhs="lorenz_rtc", **extra, **cfg).solve_ivp_ensemble(y0, P, shared_params=True)
         launch = engine.last_launch()
         b = make_solver(engine, method, 3, rhs="lorenz", **extra, **cfg).solve_ivp_ensemble(y0, P, shared_params=True)
-        assert launch["n_kernels"] == engine.last_launch()["n_kernels"] == (2 if method.startswith("RK") else 1), method
+        assert launch["n_kernels"] == engine.last_launch()["n_kernels"] == 1, method
+        assert launch["block"] == engine.last_launch()["block"] == (768 if method.startswith("RK") else 128), method
         np.testing.assert_array_equal(a.status, b.status, err_msg=method)
         # (the process may hold an NVRTC of another minor version than the nvcc that built the library: FMA contraction
         # can then differ in the last bit, so the fast kernels are compared inside the parity band, counts side by side)

@@ -174,18 +174,19 @@ def test_dense_output_matches_oracle_path(cuda, engine, oracle):
             np.testing.assert_array_equal(gpu.hist_y[np.arange(n)[ok], last[ok]], gpu.y_end[:, ok].T)
 
 
-def test_tail_kernel_and_dense_output_do_not_change_a_trajectory(cuda, engine):
+def test_regrouping_and_dense_output_do_not_change_a_trajectory(cuda, engine):
     """Scheduling must be invisible: a trajectory's numbers depend on its inputs only.  150 000 trajectories take more
-    than one per lane, so the work counter runs dry, warps suspend at a checkpoint and ensemble_tail_kernel finishes
-    them on other lanes (drive.cuh), each trajectory's history written partly by one kernel and partly by the other
-    (hist_stage.cuh); lanes take their trajectories from per-warp blocks (WarpQueue).  The same trajectories solved in
-    three smaller launches (at most one per lane: no tail) must give the same bits: final states, counters and every
-    history record."""
+    than one per lane, so the work counter runs dry and the CTAs regroup: warps report in at their checkpoints, live
+    trajectories are suspended, compacted through shared memory and resumed on other lanes, freed warps exit
+    (drive.cuh) — each such trajectory's history is written partly by one lane and partly by another (hist_stage.cuh);
+    lanes take their trajectories from per-warp blocks (WarpQueue).  The same trajectories solved in three smaller
+    launches (one trajectory per lane from the static first deal, regrouped at other moments) must give the same bits:
+    final states, counters and every history record."""
     n, cap = 150_000, 512
     y0 = E.lorenz_y0(np.arange(n))
     s = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.15, history=cap, **LOR)
     a = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
-    assert engine.last_launch()["n_kernels"] == 2
+    assert engine.last_launch()["n_kernels"] == 1 and engine.last_launch()["block"] == 640  # one wide CTA per SM
     assert (a.status == _abi.OK).all() and len(set(a.hist_len % 4)) == 4
     for lo in range(0, n, 50_000):
         b = s.solve_ivp_ensemble(np.ascontiguousarray(y0[:, lo:lo + 50_000]), LOR_P, shared_params=True)
@@ -201,7 +202,7 @@ def test_tail_kernel_and_dense_output_do_not_change_a_trajectory(cuda, engine):
     assert (a.hist_t[~mask] == 0).all() and (np.diff(a.hist_t, axis=1)[mask[:, 1:]] > 0).all()
     last = a.hist_len.astype(np.int64) - 1
     np.testing.assert_array_equal(a.hist_y[np.arange(n), last], a.y_end.T)
-    # final state only, and a history overflow that ends inside the tail kernel
+    # final state only, and a history overflow that ends after a regrouping
     s0 = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.15, **LOR)
     c = s0.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
     assert np.array_equal(c.y_end.view(np.uint64), a.y_end.view(np.uint64))
@@ -216,8 +217,8 @@ def test_tail_kernel_and_dense_output_do_not_change_a_trajectory(cuda, engine):
 def test_work_queue_blocks_strict_history_bit_exact(cuda, engine, oracle):
     """More trajectories than lanes with dense output: lanes refill from their warp's block of consecutive indices
     (WarpQueue, drive.cuh), blocks shrink towards the end of the ensemble, and a ragged n leaves partial blocks.  The
-    strict kernels (no tail kernel: they do not migrate) must still match the oracle bit for bit, every record."""
-    for n in (130_001, 114_000):  # just above the 113 664 resident lanes: most lanes refill once, from small blocks
+    strict kernels (they do not migrate: no regrouping) must still match the oracle bit for bit, every record."""
+    for n in (130_001, 114_000):  # just above the 113 664 resident lanes (6 CTAs of 128 per SM): most lanes refill once, from small blocks
         y0 = E.lorenz_y0(np.arange(n))
         gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, strict=True, history=48,
                             t_end=0.03, **LOR)
@@ -228,21 +229,21 @@ def test_work_queue_blocks_strict_history_bit_exact(cuda, engine, oracle):
         assert (gpu.hist_t[~mask] == 0).all()
 
 
-def test_tiny_grid_refill_dry_suspend_tail(cuda, engine, oracle, monkeypatch):
-    """BACON_IVP_GRID caps the grid: 5 CTAs for 3000 trajectories make every lane refill several times, the counter run
-    dry, warps suspend and the tail kernel finish them — on sizes where the oracle checks every record."""
+def test_tiny_grid_refill_dry_regroup(cuda, engine, oracle, monkeypatch):
+    """BACON_IVP_GRID caps the grid: 2 CTAs for 3000 trajectories make every lane refill several times, the counter run
+    dry and the CTAs regroup until their last warp — on sizes where the oracle checks every record."""
     n = 3000
     y0 = E.lorenz_y0(np.arange(n))
     ref_fast = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, history=160, t_end=0.15, **LOR)[0]
-    monkeypatch.setenv("BACON_IVP_GRID", "5")
+    monkeypatch.setenv("BACON_IVP_GRID", "2")
     gpu, ref = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, strict=True, history=160,
                         t_end=0.15, **LOR)
-    assert engine.last_launch()["grid"] == 5
+    assert engine.last_launch()["grid"] == 2 and engine.last_launch()["block"] == 128
     _assert_bit_exact(gpu, ref)
     mask = np.arange(160)[None, :] < gpu.hist_len[:, None]
     assert np.array_equal(gpu.hist_t[mask], ref["hist_t"][mask]) and np.array_equal(gpu.hist_y[mask], ref["hist_y"][mask])
     fast = run_both(engine, oracle, "RK45", "lorenz", y0, LOR_P, shared_params=True, history=160, t_end=0.15, **LOR)[0]
-    assert engine.last_launch()["n_kernels"] == 2 and engine.last_launch()["grid"] == 5
+    assert engine.last_launch()["grid"] == 2 and engine.last_launch()["block"] == 640
     for k in ("y_end", "t_end", "dt_end"):  # the same bits as on the full grid, where no lane ever refilled
         assert np.array_equal(getattr(fast, k).view(np.uint64), getattr(ref_fast, k).view(np.uint64)), k
     np.testing.assert_array_equal(fast.n_accept, ref_fast.n_accept)
@@ -451,3 +452,27 @@ def test_multi_gpu_host_entry_matches_single_gpu(cuda, engine):
     b = sv.solve_ivp_ensemble(y0v, mu, n_gpus=g)
     for k in ("y_end", "status", "n_accept", "hist_len", "hist_t", "hist_y"):
         np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)
+
+
+def test_concurrent_solves_on_two_streams_lose_nothing(cuda, engine):
+    """Two solves in flight on different streams share the SMs (each launch has its own work counter and its own
+    CTAs: nothing in the regrouping depends on where a CTA or a warp landed).  Status arrays start at -1: every
+    trajectory of both ensembles must have been finished, with the bits of the same solve run alone."""
+    import torch
+    n = 200_000  # more than one trajectory per lane: refills, dry counter, regrouping — in both launches at once
+    s = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.1, **LOR)
+    p = torch.from_numpy(LOR_P).cuda()
+    ya = torch.from_numpy(E.lorenz_y0(np.arange(n))).cuda()
+    yb = torch.from_numpy(E.lorenz_y0(np.arange(n, 2 * n))).cuda()
+    alone_a = {k: v.clone() for k, v in s.solve_ivp_ensemble_device(ya, p, shared_params=True).items()}
+    alone_b = {k: v.clone() for k, v in s.solve_ivp_ensemble_device(yb, p, shared_params=True).items()}
+    torch.cuda.synchronize()
+    st_a, st_b = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        oa = s.solve_ivp_ensemble_device(ya, p, shared_params=True, stream=st_a)
+        ob = s.solve_ivp_ensemble_device(yb, p, shared_params=True, stream=st_b)
+        torch.cuda.synchronize()
+        for got, ref in ((oa, alone_a), (ob, alone_b)):
+            assert (got["status"] == _abi.OK).all()
+            for k in ("y_end", "t_end", "dt_end", "n_accept", "n_reject"):
+                assert torch.equal(got[k], ref[k]), k

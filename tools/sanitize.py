@@ -1,7 +1,7 @@
 """tools/sanitize.py — small ensembles through every kernel family on a tiny grid (BACON_IVP_GRID), so that lanes refill,
-the work counter runs dry, warps suspend and the tail kernel runs; meant to be run under compute-sanitizer:
-    BACON_IVP_GRID=6 compute-sanitizer --tool memcheck  python tools/sanitize.py
-    BACON_IVP_GRID=6 compute-sanitizer --tool racecheck python tools/sanitize.py
+the work counter runs dry and the CTAs regroup (drive.cuh); meant to be run under compute-sanitizer:
+    BACON_IVP_GRID=2 compute-sanitizer --tool memcheck  python tools/sanitize.py
+    BACON_IVP_GRID=2 compute-sanitizer --tool racecheck python tools/sanitize.py
 Checks results against the oracle as it goes (the sanitizer only sees what actually ran)."""
 import os
 import sys
@@ -20,11 +20,11 @@ P = np.array(E.LORENZ["params"])
 LOR = dict(dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0.0)
 n = 3000
 y0 = E.lorenz_y0(np.arange(n))
-# fast RK45: final state only (tail kernel), with history (work-queue blocks + tail), strict with history
+# fast RK45: final state only (regrouping), with history (work-queue blocks + regrouping), strict with history
 g, r = run_both(B, O, "RK45", "lorenz", y0, P, shared_params=True, t_end=0.2, **LOR)
-assert B.last_launch()["n_kernels"] == 2 and rel_err(g.y_end, r["y_end"]).max() <= band(1e-8)
+assert B.last_launch()["block"] == 768 and rel_err(g.y_end, r["y_end"]).max() <= band(1e-8)
 g, r = run_both(B, O, "RK45", "lorenz", y0, P, shared_params=True, t_end=0.2, history=256, **LOR)
-assert B.last_launch()["n_kernels"] == 2 and (g.hist_len == r["hist_len"]).all()
+assert B.last_launch()["block"] == 640 and (g.hist_len == r["hist_len"]).all()
 g, r = run_both(B, O, "RK45", "lorenz", y0, P, shared_params=True, strict=True, t_end=0.1, history=100, **LOR)
 assert np.array_equal(g.y_end.view(np.uint64), r["y_end"].view(np.uint64))
 # RK23 with per-trajectory parameters
