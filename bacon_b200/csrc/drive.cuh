@@ -165,7 +165,10 @@ static __device__ __noinline__ void regroup_meet(RegroupPlan* p, int* live_cnt, 
 static __device__ __noinline__ int idle_until_regrouped(RegroupPlan* p, int* live_cnt, int* req_word) {
     for (;;) {
         regroup_plan(p, live_cnt, req_word, false);
-        if (p->action == RG_CARRY_ON) continue;  // the others ran another CHECK_EVERY attempts
+        if (p->action == RG_CARRY_ON) {  // the others ran another CHECK_EVERY attempts (a warp that holds nothing at all
+            __nanosleep(256);            // comes straight back: it must not eat the issue slots of the running warps)
+            continue;
+        }
         if (p->action == RG_EXIT) return -1;
         regroup_meet(p, live_cnt, req_word);
         if (p->action != RG_EXCHANGE) continue;
@@ -197,7 +200,7 @@ static __device__ __noinline__ int idle_until_regrouped(RegroupPlan* p, int* liv
 // sub-partition that holds one warp fewer simply runs its warps faster.  With one CTA per SM (BLOCK = all resident
 // lanes of the SM) this is an SM-wide re-deal; per-SM work is even by the law of large numbers (886 trajectories per SM
 // at 131072 per GPU: 0.3 % spread).  A trajectory's numbers do not depend on where it ran
-// (tests/test_gpu_rk.py::test_tail_kernel_and_dense_output_do_not_change_a_trajectory: bitwise).
+// (tests/test_gpu_rk.py::test_regrouping_and_dense_output_do_not_change_a_trajectory: bitwise).
 template <class Stepper, bool HIST, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_constant__ bacon_launch_args a) {
     constexpr int D = Stepper::D;

@@ -30,6 +30,7 @@ template <int D, bool ENABLED> struct HistStage;
 template <int D> struct HistStage<D, false> {
     __device__ __forceinline__ explicit HistStage(const bacon_launch_args&) {}
     __device__ __forceinline__ void begin(unsigned long long) {}
+    __device__ __forceinline__ void mute() {}
     __device__ __forceinline__ void push(bool, uint32_t, double, const double (&)[D]) {}
     __device__ __forceinline__ void retire(unsigned long long, uint32_t) {}
 };
@@ -39,17 +40,22 @@ template <int D> struct HistStage<D, true> {
 
     double* hist;
     uint32_t* hist_len;
-    uint32_t cap;
-    double* base;  // the current trajectory's first record
+    uint32_t cap, cap_all;  // records kept per trajectory: for the lane's current trajectory (0 = muted) / as configured
+    double* base;           // the current trajectory's first record
 
     __device__ __forceinline__ explicit HistStage(const bacon_launch_args& a) {
         hist = a.out.hist;
         hist_len = a.out.hist_len;
-        cap = (uint32_t)a.cfg.history_capacity;
+        cap = cap_all = (uint32_t)a.cfg.history_capacity;
         base = hist;
     }
     // this lane now runs trajectory idx
-    __device__ __forceinline__ void begin(unsigned long long idx) { base = hist + (size_t)idx * cap * R; }
+    __device__ __forceinline__ void begin(unsigned long long idx) {
+        cap = cap_all;
+        base = hist + (size_t)idx * cap * R;
+    }
+    // ... or a ghost (drive.cuh): nothing is written until the next begin()
+    __device__ __forceinline__ void mute() { cap = 0; }
 
     // called by every lane once per step() call; lanes that yielded a point write its record
     __device__ __forceinline__ void push(bool yielded, uint32_t n_acc_before, double t, const double (&y)[D]) {

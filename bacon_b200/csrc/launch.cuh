@@ -70,6 +70,26 @@ template <class Stepper, bool HIST, int MINB> inline int launch_stepper_hist(bac
     return 0;
 }
 
+// An ensemble that does not fit the machine's lanes ONCE but would with one more warp per sub-partition (final state
+// only; e.g. the 2^20-trajectory ensemble sharded over 8 GPUs: 131072 per GPU against 148 x 768 = 113664 lanes):
+// with 768 lanes per SM the 17408 trajectories left over start when the first lanes free up, i.e. when everything
+// else is nearly finished, and then run their ~3600 attempts almost alone (measured 4.9 ms against 3.7 ms of work).
+// The same kernel compiled for 128 x (MINB + 1) lanes per SM (Lorenz / RKF45: 69 registers instead of 78, no
+// spills) holds all of them from the start; a sub-partition saturates its FP64 pipe from ~4 resident warps
+// (tools/tau_probe.py), so the seventh costs nothing.  On larger ensembles the narrower kernel is 1.7 % faster
+// (profiles/r02_strong_scaling.md), so this one is used for that window of sizes only.
+template <class Stepper, int MINB> inline bool fits_one_more_warp(const bacon_launch_args* a) {
+    if constexpr (!(StepperSuspends<Stepper>::value && StepperMigrates<Stepper, ENSEMBLE_BLOCK * (MINB + 1)>::value &&
+                    ENSEMBLE_BLOCK * (MINB + 1) <= 1024 && MINB >= 6)) {
+        return false;
+    } else {
+        static const bool off = getenv("BACON_IVP_NO_FIT") != nullptr;  // (A/B switch for measurements)
+        const unsigned long long lanes = (unsigned long long)a->sm_count * ENSEMBLE_BLOCK * MINB;
+        const unsigned long long lanes_fit = (unsigned long long)a->sm_count * ENSEMBLE_BLOCK * (MINB + 1);
+        return !off && a->grid_override <= 0 && a->n > lanes && a->n <= lanes_fit;
+    }
+}
+
 template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* a) {
     // Dense output: one resident CTA fewer when the budget is tight (6 -> 5: 80 -> 96 registers, no re-loads of launch
     // constants inside the loop).  Measured 1-2 % faster than 6 (profiles/r01i_dense_output.md).
@@ -78,6 +98,9 @@ template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* 
 #endif
     constexpr int MINB_HIST = MINB >= 6 ? MINB - BACON_HIST_MINB_DROP : MINB;
     if (a->cfg.history_capacity > 0 && a->out.hist) return launch_stepper_hist<Stepper, true, MINB_HIST>(a);
+    if constexpr (StepperSuspends<Stepper>::value && MINB >= 6 && ENSEMBLE_BLOCK * (MINB + 1) <= 1024) {
+        if (fits_one_more_warp<Stepper, MINB>(a)) return launch_stepper_hist<Stepper, false, MINB + 1>(a);
+    }
     return launch_stepper_hist<Stepper, false, MINB>(a);
 }
 

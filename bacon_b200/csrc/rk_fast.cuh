@@ -183,6 +183,8 @@ template <class Rhs, class Tab> struct RkFastStepper {
         const uint32_t left = cap - n, room = CHECK_EVERY - tick;
         next_check = tick + (left < room ? left : room);
     }
+    // the next checkpoint in at most k calls (the driver shortens the spacing at the end of the ensemble: drive.cuh)
+    __device__ __forceinline__ void hurry(uint32_t k) { next_check = next_check < tick + k ? next_check : tick + k; }
     __device__ __forceinline__ uint32_t n_att() const { return tick - tick0; }
     __device__ __forceinline__ void reset(const bacon_launch_args& a, unsigned long long idx, bool live) {
         t = t_start;

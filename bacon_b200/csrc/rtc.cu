@@ -116,7 +116,7 @@ const char* tab_name(int method) { return (method == BACON_RK45) ? "bacon::TabRK
 // what launch.cuh would instantiate for this call: stepper type, CTA size, resident CTAs per SM the kernel is compiled
 // for, and the exchange buffer of the end-of-ensemble regrouping (drive.cuh)
 struct Plan { std::string stepper; int minb; int block; size_t smem; int state_doubles; };
-int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist, Plan* p) {
+int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist, bool fit, Plan* p) {
     const std::string T = r.type_name;
     const bool newton = (c.flags & BACON_FLAG_BDF_NEWTON) != 0;
     p->state_doubles = 0;
@@ -159,6 +159,7 @@ int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
             return BACON_E_BAD_ARGUMENT;
     }
     if (hist && p->minb >= 6) p->minb -= 1;  // MINB_HIST (launch.cuh)
+    if (fit && !hist && p->state_doubles > 0 && p->minb >= 6 && p->minb < 8) p->minb += 1;  // fits_one_more_warp (launch.cuh)
     // launch_stepper_hist (launch.cuh): steppers that suspend run as one wide CTA per SM when its exchange buffer fits
     p->block = 128;
     p->smem = 0;
@@ -173,10 +174,10 @@ int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
     return 0;
 }
 
-int compile_program(RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist, int cc_major, int cc_minor, Compiled* out) {
+int compile_program(RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist, bool fit, int cc_major, int cc_minor, Compiled* out) {
     Api& A = api();
     Plan plan;
-    if (const int rc = make_plan(r, c, strict, hist, &plan))
+    if (const int rc = make_plan(r, c, strict, hist, fit, &plan))
         return rtc_fail(rc, "rhs '%s': method %d / semantics %d / flags 0x%x has no %s kernel", r.name.c_str(), c.method,
                         c.semantics, c.flags, strict ? "strict" : "fast");
     std::string src = "#include \"drive.cuh\"\n#include \"rk_fast.cuh\"\n#include \"rk_strict.cuh\"\n#include \"adams.cuh\"\n";
@@ -266,16 +267,24 @@ int rtc_launch(int slot, bacon_launch_args* a) {
     {
         std::lock_guard<std::mutex> lk(r->mu);
         const int newton = (c.flags & BACON_FLAG_BDF_NEWTON) ? 1 : 0;
-        const std::vector<int> key = {dev, (int)c.method, strict ? 1 : 0, newton, hist ? 1 : 0};
+        // the window of sizes served by the kernel compiled for one more warp per sub-partition (fits_one_more_warp, launch.cuh)
+        bool fit = false;
+        if (!strict && !hist && (c.method == BACON_RK45 || c.method == BACON_RK23) && a->grid_override <= 0 && !getenv("BACON_IVP_NO_FIT")) {
+            Plan base;
+            if (make_plan(*r, c, strict, hist, false, &base) == 0 && base.block >= 768 && base.block + 128 <= 1024 &&
+                (size_t)(base.state_doubles + 1) * 8 * (base.block + 128) <= 160 * 1024)
+                fit = a->n > (unsigned long long)a->sm_count * base.block && a->n <= (unsigned long long)a->sm_count * (base.block + 128);
+        }
+        const std::vector<int> key = {dev, (int)c.method, strict ? 1 : 0, newton, hist ? 1 : 0, fit ? 1 : 0};
         auto it = r->variants.find(key);
         if (it == r->variants.end()) {
             cudaDeviceProp prop;
             if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return BACON_E_CUDA;
-            const std::vector<int> pkey = {prop.major * 10 + prop.minor, (int)c.method, strict ? 1 : 0, newton, hist ? 1 : 0};
+            const std::vector<int> pkey = {prop.major * 10 + prop.minor, (int)c.method, strict ? 1 : 0, newton, hist ? 1 : 0, fit ? 1 : 0};
             auto pit = r->programs.find(pkey);
             if (pit == r->programs.end()) {
                 Compiled cp;
-                if (const int rc = compile_program(*r, c, strict, hist, prop.major, prop.minor, &cp)) return rc;
+                if (const int rc = compile_program(*r, c, strict, hist, fit, prop.major, prop.minor, &cp)) return rc;
                 pit = r->programs.emplace(pkey, std::move(cp)).first;
             }
             Variant nv;
@@ -468,7 +477,7 @@ extern "C" int bacon_rhs_register_source(const char* name, const char* type_name
         RtcRhs& r = *g_rtc[slot];
         std::lock_guard<std::mutex> lk(r.mu);
         Compiled cp;
-        if (const int rc = compile_program(r, c, false, false, major, minor, &cp)) {
+        if (const int rc = compile_program(r, c, false, false, false, major, minor, &cp)) {
             std::lock_guard<std::mutex> lk2(g_mu);
             if ((int)g_rtc.size() == slot + 1) g_rtc.back()->source.clear();  // (the slot stays: trampolines are positional)
             return -rc;

@@ -2,8 +2,8 @@
 
 The path has no exchange step: trajectory i belongs to rank i mod G (round-robin, so parameter sweeps
 such as the Van der Pol mu-sweep stay balanced), every rank integrates its shard independently, and
-the only collectives are at the very end: all-gather of the final states and all-reduce of the
-statistics.  Backend-agnostic (`nccl` on the GPU box, `gloo` in the CPU tests).
+the only collectives are at the very end: all-gather of the per-trajectory records (final state, end
+time, status, counters) and all-reduce of the statistics.  Backend-agnostic (`nccl` on the GPU box, `gloo` in the CPU tests).
 """
 import numpy as np
 import torch
@@ -19,6 +19,19 @@ def shard_size(n_global, rank, world):
     return (n_global - rank + world - 1) // world if rank < n_global else 0
 
 
+def _interleave(buf, n_global):
+    """(world, F, n_max) gathered shards -> (F, n_global) in global trajectory order: trajectory k of rank r is global
+    index k * world + r, so the answer is ONE permuted copy (the padding of the shorter shards lands at the very end)."""
+    world, f, n_max = buf.shape
+    return buf.permute(1, 2, 0).reshape(f, n_max * world)[:, :n_global]
+
+
+def _pad(x, n_max):
+    if x.shape[-1] == n_max:
+        return x.contiguous()
+    return torch.cat([x, x.new_zeros(*x.shape[:-1], n_max - x.shape[-1])], dim=-1)
+
+
 def gather_final_states(y_end_local, n_global, world=None):
     """All-gather the (dim, n_local) final states of every rank and interleave them back into global
     trajectory order: returns (dim, n_global) on every rank.  Shards may differ in size by one."""
@@ -26,19 +39,38 @@ def gather_final_states(y_end_local, n_global, world=None):
         world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:
         return y_end_local
-    dim, n_loc = y_end_local.shape
+    dim, _ = y_end_local.shape
     n_max = (n_global + world - 1) // world
-    pad = y_end_local
-    if n_loc < n_max:
-        pad = torch.cat([y_end_local, y_end_local.new_zeros(dim, n_max - n_loc)], dim=1)
     flat = y_end_local.new_empty((world * dim, n_max))  # ranks concatenated along dim 0 (what gloo and nccl both accept)
-    dist.all_gather_into_tensor(flat, pad.contiguous())
-    buf = flat.view(world, dim, n_max)
-    out = y_end_local.new_empty((dim, n_global))
-    for r in range(world):
-        m = shard_size(n_global, r, world)
-        out[:, r::world] = buf[r, :, :m]
-    return out
+    dist.all_gather_into_tensor(flat, _pad(y_end_local, n_max))
+    return _interleave(flat.view(world, dim, n_max), n_global)
+
+
+def gather_records(out, n_global, world=None):
+    """The whole per-trajectory record of SURVEY.md section 8e on every rank, in global trajectory order:
+    {y_end (dim, n), t_end (n), status, n_accept, n_reject, n_rhs (n)} from each rank's local result (a dict of tensors
+    as returned by solve_ivp_ensemble_device, or anything with those keys).  Two collectives (one per element width:
+    the float64 rows and the 32-bit rows) and two permuted copies, whatever the number of ranks."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    ints = ("status", "n_accept", "n_reject", "n_rhs")
+    if world == 1:
+        return {k: out[k] for k in ("y_end", "t_end") + ints}
+    y = out["y_end"]
+    dim = y.shape[0]
+    n_max = (n_global + world - 1) // world
+    f64 = torch.cat([y, out["t_end"].reshape(1, -1)], dim=0)                      # (dim + 1, n_local)
+    i32 = torch.stack([out[k].to(torch.int32) for k in ints], dim=0)              # (4, n_local)
+    g64 = f64.new_empty((world * (dim + 1), n_max))
+    g32 = i32.new_empty((world * 4, n_max))
+    dist.all_gather_into_tensor(g64, _pad(f64, n_max))
+    dist.all_gather_into_tensor(g32, _pad(i32, n_max))
+    a = _interleave(g64.view(world, dim + 1, n_max), n_global)
+    b = _interleave(g32.view(world, 4, n_max), n_global)
+    res = {"y_end": a[:dim], "t_end": a[dim]}
+    for j, k in enumerate(ints):
+        res[k] = b[j]
+    return res
 
 
 def reduce_stats_device(n_accept, n_reject, n_rhs, status):

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from bacon_b200 import _abi, ensembles as E
-from bacon_b200.shard import gather_final_states, reduce_stats, shard_indices, shard_size
+from bacon_b200.shard import gather_final_states, gather_records, reduce_stats, shard_indices, shard_size
 
 
 def _free_port():
@@ -34,7 +34,10 @@ def _worker(rank, world, port, n_global, out_dir):
     y_glob = gather_final_states(torch.from_numpy(r["y_end"]), n_global)
     stats = reduce_stats(torch.from_numpy(r["n_accept"].astype(np.int64)), torch.from_numpy(r["n_reject"].astype(np.int64)),
                          torch.from_numpy(r["n_rhs"].astype(np.int64)), torch.from_numpy(r["status"]), kernel_ms=10.0 + rank)
+    rec = gather_records({k: torch.from_numpy(np.ascontiguousarray(r[k])) for k in ("y_end", "t_end", "status", "n_accept", "n_reject", "n_rhs")},
+                         n_global)
     np.save(os.path.join(out_dir, f"y_{rank}.npy"), y_glob.numpy())
+    np.savez(os.path.join(out_dir, f"rec_{rank}.npz"), **{k: v.numpy() for k, v in rec.items()})
     np.save(os.path.join(out_dir, f"s_{rank}.npy"), np.array([stats["n_accept"], stats["n_reject"], stats["n_rhs"],
                                                                stats["n_failed"], stats["kernel_ms_max"]]))
     dist.barrier()
@@ -53,6 +56,9 @@ def test_sharded_solve_matches_single_process(oracle, tmp_path, n_global):
         s = np.load(tmp_path / f"s_{rank}.npy")
         assert s[0] == full["n_accept"].sum() and s[1] == full["n_reject"].sum() and s[2] == full["n_rhs"].sum()
         assert s[3] == 0 and s[4] == 11.0  # max over ranks of the per-rank kernel time
+        rec = np.load(tmp_path / f"rec_{rank}.npz")  # the whole section-8e record, every trajectory, in global order
+        for k in ("y_end", "t_end", "status", "n_accept", "n_reject", "n_rhs"):
+            assert np.array_equal(rec[k], full[k]), k
 
 
 def test_shard_arithmetic():

@@ -476,3 +476,27 @@ def test_concurrent_solves_on_two_streams_lose_nothing(cuda, engine):
             assert (got["status"] == _abi.OK).all()
             for k in ("y_end", "t_end", "dt_end", "n_accept", "n_reject"):
                 assert torch.equal(got[k], ref[k]), k
+
+
+@pytest.mark.parametrize("n", [700, 769, 1000, 1536, 1537, 2000, 2305, 5000])
+def test_regrouping_edges_on_one_cta(cuda, engine, monkeypatch, n):
+    """One wide CTA (BACON_IVP_GRID=1) and ensembles around the sizes where the driver changes regime (drive.cuh): fewer
+    trajectories than lanes (ragged last bundle, regrouping only), one more than the lanes (a single refill), around
+    two per lane, several per lane.  Every trajectory must be finished exactly once, with the bits of the same solve
+    on the full grid (one trajectory per lane)."""
+    y0 = E.lorenz_y0(np.arange(n))
+    for hist in (0, 40):
+        s = make_solver(engine, "RK45", 3, rhs="lorenz", t_end=0.12, history=hist, **LOR)
+        monkeypatch.delenv("BACON_IVP_GRID", raising=False)
+        ref = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+        monkeypatch.setenv("BACON_IVP_GRID", "1")
+        got = s.solve_ivp_ensemble(y0, LOR_P, shared_params=True)
+        assert engine.last_launch()["grid"] == 1
+        assert (got.status == ref.status).all() and (got.status != -1).all()
+        for k in ("y_end", "t_end", "dt_end"):
+            assert np.array_equal(getattr(got, k).view(np.uint64), getattr(ref, k).view(np.uint64)), (k, hist)
+        for k in ("n_accept", "n_reject", "n_rhs"):
+            np.testing.assert_array_equal(getattr(got, k), getattr(ref, k), err_msg=k)
+        if hist:
+            np.testing.assert_array_equal(got.hist_len, ref.hist_len)
+            assert np.array_equal(got.hist_y.view(np.uint64), ref.hist_y.view(np.uint64))

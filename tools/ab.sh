@@ -7,7 +7,7 @@ import json, sys
 try:
     d = json.load(open(f"gpurun_out/ab_{sys.argv[1]}.json"))
     r = d["roofline"]
-    print(f"{sys.argv[1]:>16}: {d['value']:.4e} steps/s  frac {r['frac']:.4f}  kernel {r['kernel_ms_per_launch']:.3f} ms  e2e {d['e2e']['value']:.4e}  regs {d['config']['regs_per_thread']} grid {d['config']['grid']}")
+    print(f"{sys.argv[1]:>16}: {d['value']:.4e} steps/s  frac {r['frac']:.4f}  kernel {r['kernel_ms_per_launch']:.3f} ms  e2e {d['e2e']['value']:.4e}  regs {d['arm']['regs_per_thread']} grid {d['arm']['grid']}x{d['arm']['block']}")
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
