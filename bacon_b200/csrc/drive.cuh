@@ -13,6 +13,9 @@
 #pragma once
 #include "hist_stage.cuh"
 #include "ivp_common.cuh"
+#ifdef BACON_DRIVE_TRACE
+#include <cstdio>
+#endif
 
 namespace bacon {
 
@@ -97,44 +100,95 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// Regrouping, control side (see ensemble_kernel).  Everything warp- or CTA-collective lives in three functions that
-// are NOT inlined, for two reasons.  (1) The lanes of one warp come here along different paths — live lanes from the
+// Regrouping, control side (see ensemble_kernel).  Everything warp- or CTA-collective lives in functions that are NOT
+// inlined, for two reasons.  (1) The lanes of one warp come here along different paths — live lanes from the
 // persistent loop, lanes that hold nothing from idle_until_regrouped — and must meet at the SAME vote / shuffle /
 // barrier instructions.  (2) ptxas keeps the tableau in uniform registers across the persistent loop only while the
 // loop's function holds no other loop: with the waiting loop inlined it re-loads all coefficients from the constant
 // bank on every attempt (28 LDCU per pair of attempts, tools/sass_count.py).
+struct RegroupCtl {  // one per CTA, in shared memory
+    int live;        // lanes of the CTA that hold a trajectory (kept by the lanes that run out of work: atomicSub)
+    int request;     // != 0: a regrouping is asked for; every running warp comes to the meeting at its next checkpoint
+    int dry;         // != 0: the launch's work counter has been seen dry (it stays dry)
+    int sorts;       // exchanges so far that dealt the trajectories sorted by remaining time
+    int cnt[32];     // per warp, during a meeting: its live lanes
+};
 struct RegroupPlan {
-    int action;    // RG_CARRY_ON, RG_EXIT, RG_EXCHANGE or RG_NOTHING_TO_FREE
+    int action;    // RG_EXIT, RG_EXCHANGE or RG_NOTHING_TO_FREE
+    int sort;      // RG_EXCHANGE: deal the trajectories sorted by remaining time (else: compacted, order kept)
     int slot;      // RG_EXCHANGE, live lanes: where this lane's state goes in the compacted order
     int total;     // live trajectories of the CTA
     int w_active;  // in: warps of the CTA that are running; out (regroup_meet): the same after this regrouping
 };
-constexpr int RG_CARRY_ON = 0, RG_EXIT = 1, RG_EXCHANGE = 2, RG_NOTHING_TO_FREE = 3;
+constexpr int RG_EXIT = 1, RG_EXCHANGE = 2, RG_NOTHING_TO_FREE = 3;
 
-// Called by all 32 lanes of a running warp when its live lanes are at a checkpoint and the counter is dry (the vote is
-// the warp's meeting point).  Posts the warp's live count; if the CTA's live trajectories (as posted: other warps'
-// numbers may be stale — too high, never too low) fit in fewer warps than are running, asks for a regrouping; if one
-// is asked for, meets the CTA's running warps at the named barrier (every one of them arrives within CHECK_EVERY
-// attempts) and plans the exchange on exact counts.
-static __device__ __noinline__ void regroup_plan(RegroupPlan* p, int* live_cnt, int* req_word, bool live) {
+#ifdef BACON_DRIVE_TRACE  // (diagnosis: the regroupings of CTA 0 on a time axis; read back with bacon_debug_trace, rhs_builtin.cu)
+static __device__ unsigned long long g_trace[3 * 4096];
+static __device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace_put(unsigned long long a, unsigned long long b) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    const unsigned k = atomicAdd(&g_trace_n, 1u);
+    if (k < 4096) {
+        g_trace[3 * k] = ns;
+        g_trace[3 * k + 1] = a;
+        g_trace[3 * k + 2] = b;
+    }
+}
+#endif
+
+// How many exchanges of a launch deal the trajectories SORTED by remaining time (the others keep the order, which a
+// sorted deal leaves sorted): the lanes of a warp then end together, whole warps fall silent one after the other and
+// little is left to compact.  (tools/sorted_probe.py: an ensemble sorted by step count beforehand runs 9 % faster than
+// in seeded order at 131072 per GPU, with or without regrouping: that is the ceiling of any regrouping.)
+#ifndef BACON_REGROUP_SORTS
+#define BACON_REGROUP_SORTS 1
+#endif
+// Regroup when this many lanes of the CTA hold nothing: a meeting costs every warp up to CHECK_EVERY_DRY attempts of
+// waiting, an empty lane costs its share of a warp instruction; 64 = two warps freed per meeting.
+#ifndef BACON_REGROUP_AT
+#define BACON_REGROUP_AT 96
+#endif
+
+// A lane ran out of work: count it out, and ask for a regrouping once enough lanes of the CTA hold nothing (or its
+// live trajectories fit in one warp fewer and that is all there is to gain).
+static __device__ __noinline__ void regroup_count_out(RegroupCtl* ctl, int w_active) {
+    const int left = atomicSub(&ctl->live, 1) - 1;
+    const int empty = 32 * w_active - left;
+#ifdef BACON_NO_REGROUP  // (A/B switch for measurements: the warps meet once, when the CTA has nothing left)
+    if (left == 0) *(volatile int*)&ctl->request = 1;
+#else
+    if (empty >= BACON_REGROUP_AT || (empty >= 32 && w_active <= 4) || left == 0) *(volatile int*)&ctl->request = 1;
+#endif
+}
+
+// Has the launch's work counter handed out everything?  One shared-memory load once somebody in the CTA has seen it.
+// (Not inlined: inlined, the persistent loop carries four more register moves per pair of attempts.)
+static __device__ __noinline__ bool counter_dry(RegroupCtl* ctl, const unsigned long long* counter, unsigned long long n_rest) {
+    if (*(volatile int*)&ctl->dry != 0) return true;
+    if (*(volatile const unsigned long long*)counter < n_rest) return false;
+    *(volatile int*)&ctl->dry = 1;
+    return true;
+}
+
+// First meeting of a regrouping.  The vote is the warp's meeting point: lanes that hold nothing have been waiting HERE
+// (blocked, not spinning) since they ran out of work; the live lanes of the warp come when they find ctl->request set
+// at a checkpoint.  Then the CTA's running warps meet at the named barrier (every one of them arrives within
+// CHECK_EVERY_DRY attempts) and the exchange is planned on exact counts.
+static __device__ __noinline__ void regroup_plan(RegroupPlan* p, RegroupCtl* ctl, bool live) {
     const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
     const int w_active = p->w_active;
-    volatile int* cnt = live_cnt;
+    volatile int* cnt = ctl->cnt;
     const unsigned live_mask = __ballot_sync(FULL_MASK, live);
-    const int mine = __popc(live_mask);
-    if (lane == 0) cnt[warp] = mine;
-    int c = lane < w_active ? (lane == warp ? mine : cnt[lane]) : 0;
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) c += __shfl_xor_sync(FULL_MASK, c, m);
-    if (((c + 31) >> 5) < w_active && lane == 0) *(volatile int*)req_word = 1;
-    __syncwarp();
-    int req = 0;  // (read by one lane: the whole warp must take the same side)
-    if (lane == 0) req = *(volatile int*)req_word;
-    p->action = RG_CARRY_ON;
-    if (__shfl_sync(FULL_MASK, req, 0) == 0) return;
-
+#ifdef BACON_DRIVE_TRACE
+    if (blockIdx.x == 0 && lane == 0) trace_put(1001, warp);
+#endif
+    if (lane == 0) {
+        cnt[warp] = __popc(live_mask);
+        *(volatile int*)&ctl->request = 1;  // (it is: set again so that a meeting can never be one-sided)
+    }
     named_barrier(1, w_active * 32);
-    c = lane < w_active ? cnt[lane] : 0;  // exact now
+    const int c = lane < w_active ? cnt[lane] : 0;
     int incl = c;
 #pragma unroll
     for (int m = 1; m < 32; m <<= 1) {
@@ -143,40 +197,68 @@ static __device__ __noinline__ void regroup_plan(RegroupPlan* p, int* live_cnt, 
     }
     const int total = __shfl_sync(FULL_MASK, incl, 31);
     const int my_off = __shfl_sync(FULL_MASK, incl - c, warp);
+#ifdef BACON_DRIVE_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_put(w_active, total);
+#endif
     p->total = total;
     p->slot = my_off + __popc(live_mask & lanemask_lt());
     p->action = total == 0 ? RG_EXIT : (((total + 31) >> 5) < w_active ? RG_EXCHANGE : RG_NOTHING_TO_FREE);
+    p->sort = *(volatile int*)&ctl->sorts < BACON_REGROUP_SORTS;
+}
+// One more meeting of the running warps (all 32 lanes of a warp come together, whichever way they came)
+static __device__ __noinline__ void regroup_sync(int w_active) {
+    __syncwarp();
+    named_barrier(1, w_active * 32);
+}
+// Rank of a trajectory among the CTA's `total` live ones, longest remaining time first (ties: compacted order).
+// keys[] = remaining times as float bit patterns (monotone for the non-negative values that matter), in compacted
+// order, padded with INT_MIN to a multiple of 4.
+static __device__ __noinline__ int regroup_rank(const int* keys, int total, int key, int slot) {
+    int r = 0;
+    const int4* k4 = reinterpret_cast<const int4*>(keys);
+    for (int j = 0; j < total; j += 4) {
+        const int4 k = k4[j >> 2];
+        r += (k.x > key || (k.x == key && j < slot)) ? 1 : 0;
+        r += (k.y > key || (k.y == key && j + 1 < slot)) ? 1 : 0;
+        r += (k.z > key || (k.z == key && j + 2 < slot)) ? 1 : 0;
+        r += (k.w > key || (k.w == key && j + 3 < slot)) ? 1 : 0;
+    }
+    return r;
 }
 // Second meeting of a regrouping: the live lanes' states are in shared memory (or there was nothing to exchange).
 // Afterwards the lowest ceil(total / 32) warps go on: lane l of warp w owns slot 32 w + l.
-static __device__ __noinline__ void regroup_meet(RegroupPlan* p, int* live_cnt, int* req_word) {
-    if (threadIdx.x == 0) *(volatile int*)req_word = 0;
+static __device__ __noinline__ void regroup_meet(RegroupPlan* p, RegroupCtl* ctl) {
+    if (threadIdx.x == 0) {  // (nobody is stepping: every running warp is between the two meetings)
+        *(volatile int*)&ctl->request = 0;
+        *(volatile int*)&ctl->live = p->total;
+        if (p->action == RG_EXCHANGE && p->sort) *(volatile int*)&ctl->sorts = *(volatile int*)&ctl->sorts + 1;
+    }
     __syncwarp();
     named_barrier(1, p->w_active * 32);
-    if (p->action == RG_EXCHANGE) {
-        const int warp = (int)(threadIdx.x >> 5);
-        p->w_active = (p->total + 31) >> 5;
-        const int left = p->total - warp * 32;
-        if ((threadIdx.x & 31) == 0 && warp < p->w_active) *(volatile int*)&live_cnt[warp] = left < 32 ? left : 32;
-    }
+    if (p->action == RG_EXCHANGE) p->w_active = (p->total + 31) >> 5;
 }
 // A lane that holds nothing waits for the regrouping that gives it a trajectory: returns its slot in the exchange
 // buffer, or -1 when its warp is freed (or the CTA is finished).
-static __device__ __noinline__ int idle_until_regrouped(RegroupPlan* p, int* live_cnt, int* req_word) {
+static __device__ __noinline__ int idle_until_regrouped(RegroupPlan* p, RegroupCtl* ctl) {
     for (;;) {
-        regroup_plan(p, live_cnt, req_word, false);
-        if (p->action == RG_CARRY_ON) {  // the others ran another CHECK_EVERY attempts (a warp that holds nothing at all
-            __nanosleep(256);            // comes straight back: it must not eat the issue slots of the running warps)
-            continue;
-        }
+        regroup_plan(p, ctl, false);  // (blocks until the next regrouping)
         if (p->action == RG_EXIT) return -1;
-        regroup_meet(p, live_cnt, req_word);
+        if (p->action == RG_EXCHANGE && p->sort) regroup_sync(p->w_active);  // (the live lanes post their keys)
+        regroup_meet(p, ctl);
         if (p->action != RG_EXCHANGE) continue;
         const int warp = (int)(threadIdx.x >> 5), slot = (int)threadIdx.x;  // = 32 warp + lane
         if (warp >= p->w_active) return -1;
         if (slot < p->total) return slot;
     }
 }
+
+// steppers whose next checkpoint can be brought forward (RkFastStepper::hurry)
+template <class S, class = void> struct StepperRetimes { static constexpr bool value = false; };
+template <class S> struct StepperRetimes<S, decltype(void(&S::hurry))> { static constexpr bool value = true; };
+#ifndef BACON_CHECK_EVERY_DRY
+#define BACON_CHECK_EVERY_DRY 16
+#endif
+constexpr unsigned CHECK_EVERY_DRY = BACON_CHECK_EVERY_DRY;  // attempts between checkpoints once the work counter is dry
 
 // The kernel.  One CTA of BLOCK lanes; a lane integrates one trajectory at a time.
 //
@@ -191,13 +273,19 @@ static __device__ __noinline__ int idle_until_regrouped(RegroupPlan* p, int* liv
 // warp instruction occupies the FP64 pipe for the same time with 1 active lane as with 32: left alone, every warp
 // would run until its LONGEST lane ends with ever fewer lanes active (measured in round 1: a fixed 1.75 ms per launch,
 // half a trajectory time, whatever the ensemble size; and for an ensemble that fits the grid once, every warp pays
-// max-of-32 instead of the mean step count: +12 % on Lorenz).  So the CTA REGROUPS: every CHECK_EVERY attempts the lanes
-// of a warp report in together (the tick axis of the stepper: nothing is polled per attempt); once the counter is dry
-// the warp posts how many of its lanes still hold a trajectory, and as soon as the CTA's live trajectories fit in fewer
-// warps than are running, all warps meet at a named barrier, the live lanes write their stepper state
-// (Stepper::save, STATE_DOUBLES + 1 words) to shared memory in compacted order, the lowest ceil(live / 32) warps read
-// them back (Stepper::load) and the freed warps exit.  Between two regroupings the warps run freely (no barrier), so a
-// sub-partition that holds one warp fewer simply runs its warps faster.  With one CTA per SM (BLOCK = all resident
+// max-of-32 instead of the mean step count: +12 % on Lorenz).  So the CTA REGROUPS.  A lane that runs out of work counts
+// itself out of the CTA's live total (one shared-memory atomic per trajectory) and waits, blocked at its warp's vote;
+// once BACON_REGROUP_AT lanes of the CTA hold nothing it raises a request flag.  The lanes of a warp pass a checkpoint
+// together every CHECK_EVERY attempts (the tick axis of the stepper: nothing is polled per attempt; every
+// CHECK_EVERY_DRY once the counter is dry, so that a meeting gathers quickly): there they read the flag — one
+// shared-memory load — and if it is set all running warps meet at a named barrier, the live lanes write their stepper
+// state (Stepper::save, STATE_DOUBLES + 1 words) to shared memory in compacted order, the lowest ceil(live / 32) warps
+// read them back (Stepper::load) and the freed warps exit.  Between two regroupings the warps run freely (no
+// barrier), so a sub-partition that holds one warp fewer simply runs its warps faster.  What the regrouping buys is
+// measured by tools/tau_probe.py: the time of one attempt of a warp grows with the warps resident on its
+// sub-partition (0.27 us alone, 0.47 with three, 0.89 with six: the FP64 pipe is saturated from four), so every
+// half-empty warp that is folded away speeds up all the others; what it costs is the wait of the early arrivals at a
+// meeting, at most CHECK_EVERY_DRY attempts (profiles/r02_strong_scaling.md).  With one CTA per SM (BLOCK = all resident
 // lanes of the SM) this is an SM-wide re-deal; per-SM work is even by the law of large numbers (886 trajectories per SM
 // at 131072 per GPU: 0.3 % spread).  A trajectory's numbers do not depend on where it ran
 // (tests/test_gpu_rk.py::test_regrouping_and_dense_output_do_not_change_a_trajectory: bitwise).
@@ -211,8 +299,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
 
     extern __shared__ double xch[];  // MIGRATE: [STATE_DOUBLES + 1][BLOCK] exchange buffer of a regrouping
     __shared__ unsigned long long wq_words[NW];
-    __shared__ int live_cnt[32];     // MIGRATE: live lanes per warp, as last posted
-    __shared__ int regroup_req;
+    __shared__ RegroupCtl ctl;  // MIGRATE
+    __shared__ __align__(16) int rg_keys[MIGRATE ? BLOCK + 4 : 4];  // MIGRATE: sort keys of an exchange
 
     Stepper s(a);
     HistStage<D, HIST> hist(a);
@@ -228,14 +316,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
         const unsigned long long mine = (bundles - blockIdx.x + gridDim.x - 1) / gridDim.x;
         w_active = mine < (unsigned long long)NW ? (int)mine : NW;
     }
+    unsigned long long idx = ((unsigned long long)warp * gridDim.x + blockIdx.x) * 32 + lane;
+    bool live = (int)warp < w_active && idx < n;
     if constexpr (MIGRATE) {
-        if (threadIdx.x < 32) live_cnt[threadIdx.x] = 32;
-        if (threadIdx.x == 0) regroup_req = 0;
+        if (threadIdx.x == 0) {
+            ctl.request = 0;
+            ctl.dry = 0;
+            ctl.sorts = 0;
+            // live lanes of the CTA after the first deal: its bundles are full except the ensemble's last one
+            const unsigned long long last = bundles - 1;  // (bundles >= 1: n >= 1)
+            int cta_live = 32 * w_active;
+            if (w_active > 0 && last % gridDim.x == blockIdx.x && n < lanes) cta_live -= (int)(32 * bundles - n);
+            ctl.live = cta_live;
+        }
         __syncthreads();
     }
     if ((int)warp >= w_active) return;
-    unsigned long long idx = ((unsigned long long)warp * gridDim.x + blockIdx.x) * 32 + lane;
-    bool live = idx < n;
 
 #ifndef BACON_WQ_DIV
 #define BACON_WQ_DIV 1  // block size = remaining / (BACON_WQ_DIV x warps of the grid), clamped to [1, 32]
@@ -255,7 +351,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
         hist.push(yielded, n_acc_before, s.out_t(), s.out_y());
         if (raw != RAW_RUNNING) {  // rare
             if (raw == RAW_CHECKPOINT) {
-                if (MIGRATE && (HIST ? wq.dry() : *(volatile unsigned long long*)a.work_counter >= n_rest)) return true;
+                if constexpr (MIGRATE) {
+                    if (HIST ? wq.dry() : counter_dry(&ctl, a.work_counter, n_rest)) {
+                        if constexpr (StepperRetimes<Stepper>::value) s.hurry(CHECK_EVERY_DRY);
+                        if (*(volatile int*)&ctl.request != 0) return true;  // the warp goes to the meeting
+                    }
+                }
             } else {
                 const uint32_t n_acc = Codec::acc(s, raw);
                 hist.retire(idx, n_acc);
@@ -266,6 +367,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
                 idx = HIST ? wq.fetch() : lanes + atomicAdd(a.work_counter, 1ull);
                 if (idx >= n) {
                     live = false;
+                    if constexpr (MIGRATE) regroup_count_out(&ctl, w_active);
                     return true;
                 }
                 s.reset(a, idx, true);
@@ -274,8 +376,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
         }
         return false;
     };
-    // the warp reports in (its live lanes are at a checkpoint and the counter is dry, the others hold nothing); true =
-    // this lane leaves the kernel.  (No loop in here: see RegroupPlan.)
+    // A regrouping is asked for (live lanes: they are at a checkpoint), or this lane holds nothing; true = the lane
+    // leaves the kernel.  (No loop in here: see above.)
     auto report = [&]() -> bool {
         if constexpr (!MIGRATE) {
             return true;  // (the lane has nothing left to run)
@@ -285,17 +387,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
             plan.w_active = w_active;
             int slot = -1;
             if (live) {
-                regroup_plan(&plan, live_cnt, &regroup_req, true);
-                if (plan.action == RG_CARRY_ON) return false;
+                regroup_plan(&plan, &ctl, true);
                 if (plan.action == RG_EXIT) return true;
                 if (plan.action == RG_EXCHANGE) {
+                    int dst = plan.slot;
+                    if (plan.sort) {
+                        const int key = __float_as_int((float)s.remaining());
+                        rg_keys[plan.slot] = key;
+                        if (plan.slot == plan.total - 1)  // pad to a multiple of 4 (no loop in this function: see RegroupCtl)
+                            rg_keys[plan.total] = rg_keys[plan.total + 1] = rg_keys[plan.total + 2] = (int)0x80000000;
+                        regroup_sync(plan.w_active);
+                        dst = regroup_rank(rg_keys, plan.total, key, plan.slot);
+                    }
                     double st[W];
                     s.save(st);
                     st[W - 1] = __longlong_as_double((long long)idx);
 #pragma unroll
-                    for (int w = 0; w < W; ++w) xch[w * BLOCK + plan.slot] = st[w];
+                    for (int w = 0; w < W; ++w) xch[w * BLOCK + dst] = st[w];
                 }
-                regroup_meet(&plan, live_cnt, &regroup_req);
+                regroup_meet(&plan, &ctl);
                 if (plan.action != RG_EXCHANGE) return false;
                 w_active = plan.w_active;
                 if ((int)warp >= w_active) return true;  // freed
@@ -303,7 +413,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
                 if (live) slot = (int)threadIdx.x;
             }
             if (!live) {
-                slot = idle_until_regrouped(&plan, live_cnt, &regroup_req);
+                slot = idle_until_regrouped(&plan, &ctl);
                 if (slot < 0) return true;
                 w_active = plan.w_active;
                 live = true;
@@ -313,6 +423,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
             for (int w = 0; w < W; ++w) st[w] = xch[w * BLOCK + slot];
             idx = (unsigned long long)__double_as_longlong(st[W - 1]);
             s.load(st);
+            if constexpr (StepperRetimes<Stepper>::value) s.hurry(CHECK_EVERY_DRY);
             hist.begin(idx);
             return false;
         }

@@ -43,3 +43,17 @@ int register_linear32() {
 const int bacon_rhs_id_linear32 = register_linear32();
 }  // namespace
 #endif
+
+#if defined(BACON_DRIVE_TRACE) && !defined(BACON_SKIP_RK) && !defined(BACON_STRICT_FP)
+// (diagnosis build only) the regrouping events CTA 0 recorded since the last call: (ns, tag or running warps, value)
+extern "C" int bacon_debug_trace(unsigned long long* out, int cap) {
+    unsigned int n = 0;
+    cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n));
+    if ((int)n > cap) n = (unsigned)cap;
+    if (n > 4096) n = 4096;
+    cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 3 * n);
+    const unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
+    return (int)n;
+}
+#endif
