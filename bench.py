@@ -207,38 +207,60 @@ def ours(args):
         idx = np.arange(n, dtype=np.uint64) * np.uint64(world) + np.uint64(rank)  # trajectory i -> rank i mod N
         y0_host = torch.from_numpy(E.lorenz_y0(idx)).pin_memory()
         y0 = y0_host.to(dev)
-        state = {"out": None}
+        # Two result buffers: the collectives of pass k (side stream) read buffer k & 1 while pass k + 1 (main stream)
+        # writes the other.  The persistent kernel fills every SM, so the side stream's small kernels (packing, NCCL)
+        # get their turn as the kernel's warps retire at the end of a pass: the hand-over of one pass overlaps the
+        # thinning end of the next.  Timing: window k opens (event) before pass k is launched and closes after pass k
+        # AND the collectives of pass k - 1 are done; a last window holds the collectives of the last pass.  The L2
+        # flushes sit between the windows.  value = K passes / sum of the K + 1 windows.
+        outs = [None, None]
+        side = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        state = {}
 
-        def step():
-            out = solver.solve_ivp_ensemble_device(y0, p, shared_params=True, out=state["out"])
-            state["out"] = out
+        def collect(out):
             state["stats"] = reduce_stats_device(out["n_accept"], out["n_reject"], out["n_rhs"], out["status"])
             state["rec"] = gather_records(out, n_glob, world)
 
-        for _ in range(max(args.warmup, 3)):
-            step()
+        def run_passes(k_passes, timed):
+            ev, kev = [], []
+            done = [None, None]
+            for k in range(k_passes + 1):
+                if timed:
+                    flush.fill_(k & 0xFF)  # L2 flush between timed windows (outside the event pairs)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(main)
+                if k > 0:  # the collectives of pass k - 1, on the side stream, inside window k
+                    side.wait_event(e0)
+                    with torch.cuda.stream(side):
+                        collect(outs[(k - 1) & 1])
+                        done[(k - 1) & 1] = torch.cuda.Event()
+                        done[(k - 1) & 1].record(side)
+                if k < k_passes:
+                    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    k0.record(main)
+                    outs[k & 1] = solver.solve_ivp_ensemble_device(y0, p, shared_params=True, out=outs[k & 1])
+                    k1.record(main)
+                    kev.append((k0, k1))
+                if k > 0:
+                    main.wait_event(done[(k - 1) & 1])
+                e1.record(main)
+                ev.append((e0, e1))
+            return ev, kev
+
+        run_passes(max(args.warmup, 3), False)
         barrier()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         if sampler:
             sampler.start()
         barrier()
         t_wall0 = time.perf_counter()
-        for k in range(args.steps):
-            flush.fill_(k & 0xFF)  # L2 flush between timed iterations (outside the event pairs)
-            ev[k][0].record()
-            kev[k][0].record()
-            out = solver.solve_ivp_ensemble_device(y0, p, shared_params=True, out=state["out"])
-            kev[k][1].record()
-            state["stats"] = reduce_stats_device(out["n_accept"], out["n_reject"], out["n_rhs"], out["status"])
-            state["rec"] = gather_records(out, n_glob, world)
-            ev[k][1].record()
+        ev, kev = run_passes(args.steps, True)
         barrier()
         t_wall = time.perf_counter() - t_wall0
         if sampler:
             sampler.stop_flag = True
             sampler.join()
-        dev_ms = sum(a.elapsed_time(b) for a, b in ev)    # whole passes (kernel + stats + collectives), this rank
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)    # all windows: K passes + their stats and collectives, this rank
         ker_ms = sum(a.elapsed_time(b) for a, b in kev)   # the ensemble kernel alone
         tmax = torch.tensor([dev_ms, ker_ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -271,6 +293,7 @@ def ours(args):
             "kernel_ms_per_launch": ker_ms / args.steps, "kernel_ms_each_rank0": [round(a.elapsed_time(b), 3) for a, b in kev],
             "tflops_per_gpu": flops_step * args.steps / (ker_ms * 1e-3) / 1e12,  # kernel time = max over ranks
             "accepted": acc_total, "rejected": rej_total, "wall_s": t_wall, "launch": launch,
+            "windows_ms_rank0": [round(a.elapsed_time(b), 3) for a, b in ev],
             "e2e": {"value": float(r.n_accept.sum()) * world * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": y0_np.nbytes + p_np.nbytes,
                     "d2h_bytes_per_step": sum(getattr(r, k).nbytes for k in ("y_end", "t_end", "dt_end", "status", "n_accept",

@@ -10,8 +10,8 @@
 
 constexpr int N = 32;
 
-template <int ROWS, int COLS>
-__global__ void __launch_bounds__(128, 4) probe(const double* __restrict__ Aglob, double* out, int iters, double h) {
+template <int ROWS, int COLS, int CHAINS = 4, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) probe(const double* __restrict__ Aglob, double* out, int iters, double h) {
     constexpr int LR = N / ROWS;   // lanes along rows
     constexpr int LC = N / COLS;   // lanes along columns (these lanes reduce)
     static_assert(LR * LC == 32, "one warp");
@@ -36,7 +36,34 @@ __global__ void __launch_bounds__(128, 4) probe(const double* __restrict__ Aglob
 #pragma unroll
         for (int a = 0; a < ROWS; ++a) acc[a] = 0.0;
         const double2* v = reinterpret_cast<const double2*>(sy + COLS * c);
-        if constexpr (ROWS == 1) {
+        if constexpr (ROWS == 1 && CHAINS == 8) {  // eight independent chains of four
+            double c[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c[q] = 0.0;
+#pragma unroll
+            for (int j8 = 0; j8 < COLS / 8; ++j8) {
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2) {
+                    const double2 pp = v[4 * j8 + q2];
+                    c[2 * q2] = fma(A[0][8 * j8 + 2 * q2], pp.x, c[2 * q2]);
+                    c[2 * q2 + 1] = fma(A[0][8 * j8 + 2 * q2 + 1], pp.y, c[2 * q2 + 1]);
+                }
+            }
+            acc[0] = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+        } else if constexpr (ROWS == 2 && CHAINS == 4) {  // two rows, two chains each
+            double c[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int b2 = 0; b2 < COLS / 2; ++b2) {
+                const double2 pp = v[b2];
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    c[a][0] = fma(A[a][2 * b2], pp.x, c[a][0]);
+                    c[a][1] = fma(A[a][2 * b2 + 1], pp.y, c[a][1]);
+                }
+            }
+            acc[0] = c[0][0] + c[0][1];
+            acc[1] = c[1][0] + c[1][1];
+        } else if constexpr (ROWS == 1) {
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
             for (int j4 = 0; j4 < COLS / 4; ++j4) {
@@ -91,16 +118,16 @@ __global__ void __launch_bounds__(128, 4) probe(const double* __restrict__ Aglob
     out[traj * N + lane] = y;
 }
 
-template <int ROWS, int COLS> void run(const double* A, double* out, int sm, int blocks_per_sm) {
+template <int ROWS, int COLS, int CHAINS = 4, int MINB = 4> void run(const double* A, double* out, int sm, int blocks_per_sm) {
     const int iters = 4096, grid = sm * blocks_per_sm;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    probe<ROWS, COLS><<<grid, 128>>>(A, out, 64, 1e-9);
+    probe<ROWS, COLS, CHAINS, MINB><<<grid, 128>>>(A, out, 64, 1e-9);
     float best = 1e30f;
     for (int k = 0; k < 3; ++k) {
         cudaEventRecord(e0);
-        probe<ROWS, COLS><<<grid, 128>>>(A, out, iters, 1e-9);
+        probe<ROWS, COLS, CHAINS, MINB><<<grid, 128>>>(A, out, iters, 1e-9);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
@@ -109,8 +136,8 @@ template <int ROWS, int COLS> void run(const double* A, double* out, int sm, int
     }
     const double flops = 2.0 * N * N * (double)iters * grid * 4;
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, probe<ROWS, COLS>);
-    printf("block %2d x %2d per lane, %d CTAs/SM (%d warps/SMSP), %3d regs: %7.3f TFLOP/s = %5.1f %% of 37.2 (%.3f ms)\n", ROWS, COLS,
+    cudaFuncGetAttributes(&fa, probe<ROWS, COLS, CHAINS, MINB>);
+    printf("block %2d x %2d per lane, %d chains, %d CTAs/SM (%d warps/SMSP), %3d regs: %7.3f TFLOP/s = %5.1f %% of 37.2 (%.3f ms)\n", ROWS, COLS, CHAINS,
            blocks_per_sm, blocks_per_sm, fa.numRegs, flops / (best * 1e-3) / 1e12, 100 * flops / (best * 1e-3) / 37.2e12, best);
 }
 
@@ -118,15 +145,20 @@ int main() {
     int sm = 0;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
     double *A, *out;
-    const size_t traj = (size_t)sm * 4 * 4;
+    const size_t traj = (size_t)sm * 5 * 4;
     cudaMalloc(&A, traj * N * N * 8);
     cudaMalloc(&out, traj * N * 8);
     cudaMemset(A, 0, traj * N * N * 8);
     for (int bps : {4, 3, 2}) {
         run<1, 32>(A, out, sm, bps);
-        run<2, 16>(A, out, sm, bps);
+        run<1, 32, 8>(A, out, sm, bps);
+        run<2, 16, 2>(A, out, sm, bps);
+        run<2, 16, 4>(A, out, sm, bps);
         run<4, 8>(A, out, sm, bps);
         run<8, 4>(A, out, sm, bps);
     }
+    run<2, 16, 4, 5>(A, out, sm, 5);
+    run<2, 16, 2, 5>(A, out, sm, 5);
+    run<4, 8, 4, 5>(A, out, sm, 5);
     return 0;
 }
