@@ -1,7 +1,7 @@
 """ctypes mirror of include/bacon_ivp.h (structs, enums).  No logic here."""
 import ctypes as C
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # bacon_method  (rk.rs:561, rk.rs:656, bdf.rs:706, bdf.rs:762)
 RK45, RK23, BDF6, BDF2, ADAMS5, ADAMS3, EULER = 0, 1, 2, 3, 4, 5, 6
@@ -29,13 +29,15 @@ E_HISTORY_OVERFLOW = 15
 E_CUDA = 16
 E_BAD_ARGUMENT = 17
 E_UNSUPPORTED = 18
+STOPPED_AT_EVENT = 19  # per-trajectory, not an error: the integration stopped at a terminal event
+DIM_DYN = 0            # the `Dyn` type parameter of bacon_solver_new_static / bacon_solver_new_dyn
 
 STATUS_NAMES = {
     0: "Ok", 1: "MissingParameters", 2: "UserError", 3: "ToleranceOOB", 4: "TimeDeltaOOB",
     5: "TimeEndOOB", 6: "TimeStartOOB", 7: "FromPrimitiveFailure", 8: "MinimumTimeDeltaExceeded",
     9: "MaximumIterationsExceeded", 10: "SingularMatrix", 11: "DynamicOnStatic",
     12: "StaticOnDynamic", 13: "NonFinite", 14: "MaxAttempts", 15: "HistoryOverflow",
-    16: "CudaError", 17: "BadArgument", 18: "Unsupported",
+    16: "CudaError", 17: "BadArgument", 18: "Unsupported", 19: "StoppedAtEvent",
 }
 
 SEM_CORRECTED, SEM_LITERAL = 0, 1
@@ -49,6 +51,7 @@ class Config(C.Structure):
         ("semantics", C.c_int32), ("flags", C.c_uint32), ("history_capacity", C.c_int32),
         ("dt_min", C.c_double), ("dt_max", C.c_double), ("tol", C.c_double),
         ("t_start", C.c_double), ("t_end", C.c_double), ("max_attempts", C.c_uint64),
+        ("dt_init", C.c_double),
     ]
 
 
@@ -58,6 +61,15 @@ class Result(C.Structure):
         ("y_end", C.c_void_p), ("t_end", C.c_void_p), ("dt_end", C.c_void_p),
         ("status", C.c_void_p), ("n_accept", C.c_void_p), ("n_reject", C.c_void_p),
         ("n_rhs", C.c_void_p), ("hist", C.c_void_p), ("hist_len", C.c_void_p),
+        ("t_start", C.c_void_p),
+    ]
+
+
+class Options(C.Structure):
+    """bacon_ivp_options — optional inputs of a solve (restart record, terminal event)."""
+    _fields_ = [
+        ("t_start_each", C.c_void_p), ("dt_start_each", C.c_void_p), ("event_w", C.c_void_p),
+        ("event_c", C.c_double), ("event_direction", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -82,4 +94,6 @@ EXPORTED_SYMBOLS = [
     "bacon_status_name", "bacon_fp64_peak_tflops", "bacon_device_sm_count", "bacon_host_alloc", "bacon_host_free",
     "bacon_ivp_sample_paths", "bacon_ivp_sample_paths_device", "bacon_ivp_locate_events",
     "bacon_ivp_locate_events_device",
+    "bacon_solver_new_static", "bacon_solver_new_dyn", "bacon_solver_with_initial_dt",
+    "bacon_ivp_solve_ensemble_ex", "bacon_ivp_solve_ensemble_device_ex",
 ]

@@ -28,10 +28,15 @@ def lib():
             "(or `make -C bacon_b200/csrc`). There is no CPU fallback.")
     L = C.CDLL(LIB_PATH)
     vp, i32, u32, u64, dbl, sz = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_double, C.c_size_t
-    cfgp, resp = C.POINTER(_abi.Config), C.POINTER(_abi.Result)
+    cfgp, resp, optp = C.POINTER(_abi.Config), C.POINTER(_abi.Result), C.POINTER(_abi.Options)
     sig = {
         "bacon_abi_version": (i32, []),
         "bacon_solver_new": (vp, [i32, i32]),
+        "bacon_solver_new_static": (i32, [i32, i32, C.POINTER(vp)]),
+        "bacon_solver_new_dyn": (i32, [i32, i32, i32, C.POINTER(vp)]),
+        "bacon_solver_with_initial_dt": (i32, [vp, dbl]),
+        "bacon_ivp_solve_ensemble_ex": (i32, [cfgp, i32, sz, vp, vp, optp, resp, i32]),
+        "bacon_ivp_solve_ensemble_device_ex": (i32, [cfgp, i32, sz, vp, vp, optp, resp, vp]),
         "bacon_solver_free": (None, [vp]),
         "bacon_solver_with_tolerance": (i32, [vp, dbl]),
         "bacon_solver_with_maximum_dt": (i32, [vp, dbl]),

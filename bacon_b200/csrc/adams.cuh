@@ -89,6 +89,7 @@ template <int N> __device__ __forceinline__ double sfu_root(double x) {
 }
 
 template <class Rhs, class Coef, bool STRICT> struct AdamsStepper {
+    using RhsT = Rhs;
     static constexpr int D = Rhs::DIM;
     static constexpr int P = Rhs::NPARAM;
     static constexpr int O = Coef::O;
@@ -141,6 +142,10 @@ template <class Rhs, class Coef, bool STRICT> struct AdamsStepper {
     __device__ __forceinline__ void reset(const bacon_launch_args& a, unsigned long long idx, bool live) {
         reset_scalars();
         if (live) load_problem<D, P>(a, idx, y, p);
+    }
+    __device__ __forceinline__ void apply_restart(const bacon_launch_args& a, unsigned long long idx) {
+        trajectory_start(a, idx, dt_min, dt_max, t, dt);
+        ot = t;
     }
     __device__ __forceinline__ uint32_t n_rhs() const { return n_f; }
     __device__ __forceinline__ double out_t() const { return ot; }
@@ -341,6 +346,7 @@ template <class Rhs, class Coef, bool STRICT> struct AdamsStepper {
 // EulerSolver::step (ivp.rs:320-338): fixed dt (clamped on the last step), yields the OLD (t, y).
 // cfg.dt_max carries the builder's dt (ivp.rs:396-421).
 template <class Rhs, bool STRICT> struct EulerStepper {
+    using RhsT = Rhs;
     static constexpr int D = Rhs::DIM;
     static constexpr int P = Rhs::NPARAM;
     using A = Ar<STRICT>;
@@ -370,6 +376,10 @@ template <class Rhs, bool STRICT> struct EulerStepper {
         dt = dt0;
         n_acc = n_rej = n_att = 0;
         if (live) load_problem<D, P>(a, idx, y, p);
+    }
+    __device__ __forceinline__ void apply_restart(const bacon_launch_args& a, unsigned long long idx) {
+        if (a.t0_each) t = a.t0_each[idx];  // (Euler's dt is the builder's, the record's is not used)
+        ot = t;
     }
     __device__ __forceinline__ uint32_t n_rhs() const { return n_acc; }
     __device__ __forceinline__ double out_t() const { return ot; }

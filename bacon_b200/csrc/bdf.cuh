@@ -112,6 +112,186 @@ template <int D, bool STRICT> __device__ __forceinline__ bool inverse_lu_partial
     return ok;
 }
 
+// swap rows i and j (j > i, predicated over the static candidates: no dynamic register indexing)
+template <int D> __device__ __forceinline__ void swap_rows(double (&m)[D][D], int i_static, int j) {
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+        if (r > i_static && r == j) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) { const double t = m[i_static][c]; m[i_static][c] = m[r][c]; m[r][c] = t; }
+        }
+}
+template <int D> __device__ __forceinline__ void swap_cols(double (&m)[D][D], int i_static, int j) {
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+        if (c > i_static && c == j) {
+#pragma unroll
+            for (int r = 0; r < D; ++r) { const double t = m[r][i_static]; m[r][i_static] = m[r][c]; m[r][c] = t; }
+        }
+}
+// L U X = B in place, column by column of B (nalgebra solve.rs; oracle: lu_solve_inplace).  false = zero diagonal.
+template <int D, bool STRICT> __device__ __forceinline__ bool lu_solve_inplace(const double (&lu)[D][D], double (&b)[D][D]) {
+    using A = Ar<STRICT>;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+        for (int i = 0; i < D - 1; ++i) {
+            const double coeff = b[i][k];
+#pragma unroll
+            for (int r = i + 1; r < D; ++r) b[r][k] = A::madd(-coeff, lu[r][i], b[r][k]);
+        }
+#pragma unroll
+        for (int i = D - 1; i >= 0; --i) {
+            const double diag = lu[i][i];
+            if (diag == 0.0) ok = false;
+            const double coeff = A::div(b[i][k], diag);
+            b[i][k] = coeff;
+#pragma unroll
+            for (int r = 0; r < i; ++r) b[r][k] = A::madd(-coeff, lu[r][i], b[r][k]);
+        }
+    }
+    return ok;
+}
+
+// jac.full_piv_lu().try_inverse() (bdf.rs:433-434), the second link of the reference's inversion chain: complete
+// pivoting on the first largest |x| of the trailing block in column-major scan order (nalgebra icamax_full), the same
+// gauss step, then  P, L, U solves and the inverse column permutation.  Reached only when the partially pivoted LU hit an
+// exactly zero pivot — which REF_LITERAL's Jacobian `(above + below) / 2h` (rank one up to rounding) does.
+template <int D, bool STRICT> __device__ __noinline__ bool inverse_lu_full(const double (&a)[D][D], double (&inv)[D][D]) {
+    using A = Ar<STRICT>;
+    double lu[D][D];
+    int cperm[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+        cperm[r] = -1;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            lu[r][c] = a[r][c];
+            inv[r][c] = (r == c) ? 1.0 : 0.0;
+        }
+    }
+    bool stopped = false;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        int pr = i, pc = i;
+        double best = -1.0, pivot = 0.0;
+#pragma unroll
+        for (int c = i; c < D; ++c)
+#pragma unroll
+            for (int r = i; r < D; ++r) {
+                const double v = fabs(lu[r][c]);
+                if (!stopped && v > best) { best = v; pr = r; pc = c; pivot = lu[r][c]; }
+            }
+        if (pivot == 0.0) stopped = true;  // "the remaining of the matrix is zero": the loop ends here
+        if (!stopped) {
+            if (pc != i) {
+                cperm[i] = pc;
+                swap_cols<D>(lu, i, pc);
+            }
+            if (pr != i) {
+                swap_rows<D>(lu, i, pr);
+                swap_rows<D>(inv, i, pr);  // (P's swaps applied in order to the identity)
+            }
+            const double inv_diag = A::div(1.0, lu[i][i]);
+#pragma unroll
+            for (int r = i + 1; r < D; ++r) lu[r][i] = A::mul(lu[r][i], inv_diag);
+#pragma unroll
+            for (int c = i + 1; c < D; ++c) {
+                const double prc = lu[i][c];
+#pragma unroll
+                for (int r = i + 1; r < D; ++r) lu[r][c] = A::madd(-prc, lu[r][i], lu[r][c]);
+            }
+        }
+    }
+    if (!lu_solve_inplace<D, STRICT>(lu, inv)) return false;
+#pragma unroll
+    for (int k = D - 1; k >= 0; --k)  // q.inv_permute_rows(b)
+        if (cperm[k] >= 0) swap_rows<D>(inv, k, cperm[k]);
+    return true;
+}
+
+// jac.qr().try_inverse() (bdf.rs:437-438), the last link: Householder QR, then R X = Q^T (oracle: inverse_qr).
+template <int D, bool STRICT> __device__ __noinline__ bool inverse_qr(const double (&a)[D][D], double (&inv)[D][D]) {
+    using A = Ar<STRICT>;
+    double r[D][D], qt[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            r[i][c] = a[i][c];
+            qt[i][c] = (i == c) ? 1.0 : 0.0;
+        }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double nrm = 0.0;
+#pragma unroll
+        for (int i = k; i < D; ++i) nrm = A::madd(r[i][k], r[i][k], nrm);
+        nrm = sqrt(nrm);
+        if (nrm == 0.0) ok = false;
+        if (ok) {
+            const double alpha = (r[k][k] >= 0.0) ? -nrm : nrm;
+            double v[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) v[i] = i >= k ? r[i][k] : 0.0;
+            v[k] = A::sub(v[k], alpha);
+            double vn = 0.0;
+#pragma unroll
+            for (int i = k; i < D; ++i) vn = A::madd(v[i], v[i], vn);
+            if (vn != 0.0) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    double dot = 0.0;
+#pragma unroll
+                    for (int i = k; i < D; ++i) dot = A::madd(v[i], r[i][c], dot);
+                    const double f = A::div(A::mul(2.0, dot), vn);
+#pragma unroll
+                    for (int i = k; i < D; ++i) r[i][c] = A::sub(r[i][c], A::mul(f, v[i]));
+                    double dq = 0.0;
+#pragma unroll
+                    for (int i = k; i < D; ++i) dq = A::madd(v[i], qt[i][c], dq);
+                    const double fq = A::div(A::mul(2.0, dq), vn);
+#pragma unroll
+                    for (int i = k; i < D; ++i) qt[i][c] = A::sub(qt[i][c], A::mul(fq, v[i]));
+                }
+            }
+        }
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+        if (r[i][i] == 0.0) ok = false;
+    if (!ok) return false;
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+        for (int i = D - 1; i >= 0; --i) {
+            const double coeff = A::div(qt[i][c], r[i][i]);
+            qt[i][c] = coeff;
+#pragma unroll
+            for (int rr = 0; rr < i; ++rr) qt[rr][c] = A::madd(-coeff, r[rr][i], qt[rr][c]);
+        }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int c = 0; c < D; ++c) inv[i][c] = qt[i][c];
+    return true;
+}
+
+// The reference's inversion chain (bdf.rs:429-444): LU with partial pivoting, else with full pivoting, else QR, else
+// SingularMatrix.  The strict build runs the whole chain (bit-exact with the oracle also where a pivot is exactly zero);
+// the fast build stops after the first link (the others only matter on an exactly singular Jacobian).
+template <int D, bool STRICT> __device__ __forceinline__ bool inverse_chain(const double (&a)[D][D], double (&inv)[D][D]) {
+    if (inverse_lu_partial<D, STRICT>(a, inv)) return true;
+    if constexpr (STRICT) {
+        if (inverse_lu_full<D, STRICT>(a, inv)) return true;
+        return inverse_qr<D, STRICT>(a, inv);
+    } else {
+        return false;
+    }
+}
+
 // 1/x for the Newton path's pivots: SFU seed (2^-23) + two Newton steps, 5 instructions against the ~20 of an IEEE
 // division; relative error ~1e-14 on normal x (a Newton iteration's linear solve needs far less), 0 or inf for
 // zero / overflow like the division.
@@ -168,6 +348,7 @@ template <int D> __device__ __forceinline__ bool lu_solve(double (&M)[D][D], dou
 }
 
 template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
+    using RhsT = Rhs;
     static constexpr int D = Rhs::DIM;
     static constexpr int P = Rhs::NPARAM;
     static constexpr int O = Coef::O;
@@ -182,6 +363,11 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
     double oy[D], ot;        // the point of the last Ok(...)
     double t, dt;
     bool have;
+    // REF_LITERAL (the source as written; strict Broyden build only): FD Jacobian `above + below`
+    // (bdf.rs:407), the lower formula summed with the HIGHER coefficients (:568), g evaluated at t_n (:403-454), and the
+    // warm-up rollback `time -= dt - order` (:622).  Every reference BDF test ends with an empty path in this mode.
+    bool literal;
+    __device__ __forceinline__ bool lit() const { return (STRICT && !NEWTON) ? literal : false; }
     uint32_t ym;             // yield_memory (bdf.rs:119)
     uint32_t n_acc, n_rej, n_att, n_f;
 
@@ -193,6 +379,7 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
         tol = a.cfg.tol;
         dt0 = A::mul(A::add(dt_max, dt_min), 0.5);  // bdf.rs:302
         order = (double)O;                           // bdf.rs:293
+        literal = STRICT && !NEWTON && a.cfg.semantics == BACON_SEM_LITERAL;
         cap = (a.cfg.max_attempts == 0 || a.cfg.max_attempts > 0xFFFFFFFEull) ? 0xFFFFFFFEu
                                                                                : (uint32_t)a.cfg.max_attempts;
         reset_scalars();
@@ -216,6 +403,10 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
     __device__ __forceinline__ void reset(const bacon_launch_args& a, unsigned long long idx, bool live) {
         reset_scalars();
         if (live) load_problem<D, P>(a, idx, y, p);
+    }
+    __device__ __forceinline__ void apply_restart(const bacon_launch_args& a, unsigned long long idx) {
+        trajectory_start(a, idx, dt_min, dt_max, t, dt);
+        ot = t;
     }
     __device__ __forceinline__ uint32_t n_rhs() const { return n_f; }
     __device__ __forceinline__ double out_t() const { return ot; }
@@ -274,7 +465,11 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
             static_for<1, O>([&](auto I) {
                 constexpr int ind = decltype(I)::value;
                 constexpr double c = HIGHER ? Coef::higher(ind) : Coef::lower(ind);
-                if constexpr (STRICT || c != 0.0) sp = A::madd(hy[O - ind][d], c, sp);
+                if constexpr (STRICT && !NEWTON && !HIGHER) {
+                    sp = A::madd(hy[O - ind][d], lit() ? Coef::higher(ind) : c, sp);  // bdf.rs:568 (D5)
+                } else if constexpr (STRICT || c != 0.0) {
+                    sp = A::madd(hy[O - ind][d], c, sp);
+                }
             });
             out[d] = A::add(sp, x[d]);
         }
@@ -282,7 +477,7 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
 
     // roots::secant as embedded in bdf.rs:414-475.  Returns a bacon_status.
     template <bool HIGHER> __device__ __forceinline__ int broyden(double (&res)[D]) {
-        const double tg = A::add(t, dt);
+        const double tg = lit() ? t : A::add(t, dt);  // bdf.rs:403,405,423,454 pass self.time (D7)
         double guess[D], g[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) guess[d] = y[d];
@@ -300,10 +495,11 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
                 g_eval<HIGHER>(tg, guess, below);
                 guess[ind] = A::add(guess[ind], h);
 #pragma unroll
-                for (int r = 0; r < D; ++r) jac[r][ind] = A::mul(A::sub(above[r], below[r]), denom);
+                for (int r = 0; r < D; ++r)  // bdf.rs:407: `(above + below) * denom` as written (D4)
+                    jac[r][ind] = A::mul(lit() ? A::add(above[r], below[r]) : A::sub(above[r], below[r]), denom);
             }
         }
-        if (!inverse_lu_partial<D, STRICT>(jac, jinv)) return BACON_E_SINGULAR;
+        if (!inverse_chain<D, STRICT>(jac, jinv)) return BACON_E_SINGULAR;  // bdf.rs:429-444
         double shift[D];
         neg_matvec(jinv, g, shift);
 #pragma unroll
@@ -516,7 +712,7 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
         }
         n_rej++;
         if (ym == (uint32_t)O + 1) {  // :620-624 (intent: undo the O warm-up steps, D6)
-            t = A::sub(t, A::mul(dt, order));
+            t = lit() ? A::sub(t, A::sub(dt, order)) : A::sub(t, A::mul(dt, order));  // :622 as written (D6)
 #pragma unroll
             for (int d = 0; d < D; ++d) y[d] = save[d];
         }

@@ -13,6 +13,7 @@
 #pragma once
 #include "hist_stage.cuh"
 #include "ivp_common.cuh"
+#include "path_query.cuh"
 #ifdef BACON_DRIVE_TRACE
 #include <cstdio>
 #endif
@@ -260,6 +261,67 @@ template <class S> struct StepperRetimes<S, decltype(void(&S::hurry))> { static 
 #endif
 constexpr unsigned CHECK_EVERY_DRY = BACON_CHECK_EVERY_DRY;  // attempts between checkpoints once the work counter is dry
 
+// Terminal event (bacon_ivp_options::event_w; NOT in the reference): the kernels instantiated with EVENT watch
+// g(y) = w . y - c on the points a trajectory yields, knot 0 being its initial condition.  When g changes sign between the
+// last knot and the point just yielded (same rule as the events query on stored paths, path_query.cuh:
+// event_crossing), the crossing is located on the cubic Hermite interpolant of that interval with the right-hand
+// side's own slopes (hermite_root: the very function the path query uses, so `stop at the first event` and `first
+// event of the stored path` agree bit for bit in the strict build), and the trajectory retires there:
+// status BACON_STOPPED_AT_EVENT, t_end = t*, y_end = y(t*); the point that crossed is not yielded.  D + 2 more doubles per
+// lane (the last knot), D FMAs and a compare per yielded point: a separate instantiation, so the plain kernels
+// pay nothing; event kernels run as 128-lane CTAs without regrouping (the last knot would have to migrate too).
+// The same instantiation serves the other optional input, the restart record (per-trajectory start time and first dt:
+// Stepper::apply_restart): even two more launch constants read inside the plain kernels' refill path cost the fast RK
+// loop a uniform register pair, i.e. one constant re-load per attempt (tools/sass_count.py).
+template <int D, bool ON> struct EventWatch {
+    __device__ __forceinline__ void begin(const bacon_launch_args&, double, const double (&)[D]) {}
+};
+template <int D> struct EventWatch<D, true> {
+    double gp, tp, yp[D];  // the last knot: g, time, state
+    __device__ __forceinline__ double g_of(const bacon_launch_args& a, const double (&y)[D]) const {
+        double s = a.ev_w[0] * y[0];
+#pragma unroll
+        for (int d = 1; d < D; ++d) s += a.ev_w[d] * y[d];
+        return s - a.ev_c;
+    }
+    __device__ __forceinline__ void begin(const bacon_launch_args& a, double t0, const double (&y0)[D]) {
+        tp = t0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) yp[d] = y0[d];
+        gp = g_of(a, y0);
+    }
+    // the point (t, y) was yielded: true = g crossed on the way here (the knot is kept); else (t, y) is the new knot
+    __device__ __forceinline__ bool crossed(const bacon_launch_args& a, double t, const double (&y)[D], double& g_new) {
+        if (!a.ev_on) return false;  // (this launch only carries a restart record)
+        g_new = g_of(a, y);
+        if (event_crossing(gp, g_new, a.ev_direction)) return true;
+        gp = g_new;
+        tp = t;
+#pragma unroll
+        for (int d = 0; d < D; ++d) yp[d] = y[d];
+        return false;
+    }
+    // the event point between the knot and (tb, yb): same operations, same order as locate_event (path_query.cuh)
+    template <class Rhs, int P>
+    __device__ __noinline__ void locate(const bacon_launch_args& a, const double (&p)[P], double tb, const double (&yb)[D],
+                                        double gb, double& te, double (&ye)[D]) const {
+        double fa[D], fb[D];
+        const Rhs rhs{};
+        rhs(tp, yp, p, fa);
+        rhs(tb, yb, p, fb);
+        const double h = tb - tp;
+        double da = a.ev_w[0] * fa[0], db = a.ev_w[0] * fb[0];
+#pragma unroll
+        for (int d = 1; d < D; ++d) {
+            da += a.ev_w[d] * fa[d];
+            db += a.ev_w[d] * fb[d];
+        }
+        const double th = hermite_root(gp, gb, h * da, h * db);
+        hermite_eval<D>(th, h, yp, yb, fa, fb, ye);
+        te = tp + th * h;
+    }
+};
+
 // The kernel.  One CTA of BLOCK lanes; a lane integrates one trajectory at a time.
 //
 // First deal (static): bundle j = 32 consecutive trajectories; warp w of CTA b starts on bundle w * gridDim.x + b, so a
@@ -289,10 +351,11 @@ constexpr unsigned CHECK_EVERY_DRY = BACON_CHECK_EVERY_DRY;  // attempts between
 // lanes of the SM) this is an SM-wide re-deal; per-SM work is even by the law of large numbers (886 trajectories per SM
 // at 131072 per GPU: 0.3 % spread).  A trajectory's numbers do not depend on where it ran
 // (tests/test_gpu_rk.py::test_regrouping_and_dense_output_do_not_change_a_trajectory: bitwise).
-template <class Stepper, bool HIST, int BLOCK, int MINB>
+template <class Stepper, bool HIST, int BLOCK, int MINB, bool EVENT = false>
 __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_constant__ bacon_launch_args a) {
     constexpr int D = Stepper::D;
     constexpr bool MIGRATE = StepperMigrates<Stepper, BLOCK>::value;
+    static_assert(!(EVENT && MIGRATE), "event kernels do not regroup");
     constexpr int NW = BLOCK / 32;
     static_assert(BLOCK % 32 == 0 && NW <= 32, "a CTA is at most 32 warps");
     using Codec = StepperCodec<Stepper>;
@@ -304,6 +367,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
 
     Stepper s(a);
     HistStage<D, HIST> hist(a);
+    [[maybe_unused]] EventWatch<D, EVENT> ev;
     const unsigned long long n = a.n;
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned long long lanes = (unsigned long long)gridDim.x * BLOCK;
@@ -343,11 +407,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
     if (live) {
         s.reset(a, idx, true);
         hist.begin(idx);
+        if constexpr (EVENT) {
+            s.apply_restart(a, idx);
+            ev.begin(a, s.t, s.end_y());
+        }
     }
     auto step = [&]() -> bool {  // one IVPIterator::next; true = this lane leaves the loop (nothing to run, or its warp reports in)
         bool yielded = false;
-        const uint32_t n_acc_before = HIST ? Codec::acc_running(s) : 0u;
+        const uint32_t n_acc_before = (HIST || EVENT) ? Codec::acc_running(s) : 0u;
         const int raw = s.attempt(yielded);
+        if constexpr (EVENT) {
+            double g_new;
+            if (yielded && ev.crossed(a, s.out_t(), s.out_y(), g_new)) {  // rare: the trajectory ends at the event
+                double te, ye[D];
+                ev.template locate<typename Stepper::RhsT>(a, s.p, s.out_t(), s.out_y(), g_new, te, ye);
+                hist.retire(idx, n_acc_before);
+                store_result<D>(a.out, n, idx, ye, te, s.dt, BACON_STOPPED_AT_EVENT, n_acc_before, s.n_rej, s.n_rhs());
+                idx = HIST ? wq.fetch() : lanes + atomicAdd(a.work_counter, 1ull);
+                if (idx >= n) {
+                    live = false;
+                    return true;
+                }
+                s.reset(a, idx, true);
+                hist.begin(idx);
+                s.apply_restart(a, idx);
+                ev.begin(a, s.t, s.end_y());
+                return false;
+            }
+        }
         hist.push(yielded, n_acc_before, s.out_t(), s.out_y());
         if (raw != RAW_RUNNING) {  // rare
             if (raw == RAW_CHECKPOINT) {
@@ -372,6 +459,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
                 }
                 s.reset(a, idx, true);
                 hist.begin(idx);
+                if constexpr (EVENT) {
+            s.apply_restart(a, idx);
+            ev.begin(a, s.t, s.end_y());
+        }
             }
         }
         return false;

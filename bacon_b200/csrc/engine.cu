@@ -14,9 +14,12 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -64,10 +67,11 @@ struct RhsEntry {
     int dim, n_params;
     bacon_launch_fn launch[2][BACON_N_METHODS];
     bacon_path_fn path_query[2];
+    bacon_launch_fn launch_event[2][BACON_N_METHODS];
 };
 struct Registry {
     std::mutex mu;
-    std::vector<RhsEntry> entries;
+    std::deque<RhsEntry> entries;  // (a deque: bacon_rhs_info hands out name.c_str(), which must survive later registrations)
 };
 Registry& registry() {
     static Registry* r = new Registry();  // leaked on purpose: RHS translation units register during static init
@@ -81,6 +85,7 @@ struct DeviceCtx {
     int sm_count = 0;
     unsigned long long* counters = nullptr;  // ring of work counters, one per in-flight launch
     int next_counter = 0;
+    std::mutex use;                          // held by a host-buffer solve while it uses stream / events / staging below
     cudaStream_t stream = nullptr;           // used by the host-buffer entry points
     cudaStream_t copy_stream = nullptr;      // background DMA of the late inputs (zero-copy path)
     cudaEvent_t ev[4] = {};
@@ -176,17 +181,48 @@ struct Carve {
 struct ShardLayout {
     double* y0;
     double* params;
+    double* t0;   // bacon_ivp_options::t_start_each / dt_start_each of the shard, when given
+    double* dt0;
     bacon_ivp_result out;
     size_t bytes;
 };
 
+// the caller's current device is restored on every way out of a multi-device call
+struct DeviceGuard {
+    int dev = 0;
+    bool ok;
+    DeviceGuard() { ok = cudaGetDevice(&dev) == cudaSuccess; }
+    ~DeviceGuard() {
+        if (ok) cudaSetDevice(dev);
+    }
+};
+
+// run fn(task) for task in [0, n_tasks) on up to `max_threads` host threads (packing / scattering strided shards)
+void parallel_for(size_t n_tasks, const std::function<void(size_t)>& fn, unsigned max_threads = 16) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    const size_t nt = std::min<size_t>(std::min<size_t>(hw, max_threads), n_tasks);
+    if (nt <= 1) {
+        for (size_t t = 0; t < n_tasks; ++t) fn(t);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (size_t w = 0; w < nt; ++w)
+        pool.emplace_back([&, w] {
+            for (size_t t = w; t < n_tasks; t += nt) fn(t);
+        });
+    for (auto& th : pool) th.join();
+}
+
 // which outputs the caller asked for decides what is allocated and copied back
 ShardLayout layout_shard(void* base, const bacon_ivp_config& cfg, size_t n, bool shared_params,
-                         const bacon_ivp_result& want) {
+                         const bacon_ivp_result& want, const bacon_ivp_options* opts) {
     Carve c(base);
     ShardLayout L{};
     L.y0 = c.take<double>((size_t)cfg.dim * n);
     L.params = cfg.n_params > 0 ? c.take<double>(shared_params ? (size_t)cfg.n_params : (size_t)cfg.n_params * n) : nullptr;
+    L.t0 = (opts && opts->t_start_each) ? c.take<double>(n) : nullptr;
+    L.dt0 = (opts && opts->dt_start_each) ? c.take<double>(n) : nullptr;
     L.out.y_end = c.take<double>((size_t)cfg.dim * n);
     L.out.t_end = want.t_end ? c.take<double>(n) : nullptr;
     L.out.dt_end = want.dt_end ? c.take<double>(n) : nullptr;
@@ -202,7 +238,7 @@ ShardLayout layout_shard(void* base, const bacon_ivp_config& cfg, size_t n, bool
 }
 
 int check_common(const bacon_ivp_config* cfg, int rhs_id, const double* y0, const double* params,
-                 const bacon_ivp_result* out, RhsEntry* entry, bacon_launch_fn* fn) {
+                 const bacon_ivp_options* opts, const bacon_ivp_result* out, RhsEntry* entry, bacon_launch_fn* fn) {
     if (!cfg || !out) return fail(BACON_E_BAD_ARGUMENT, "cfg and out must not be NULL");
     const int v = bacon_ivp_validate(cfg);
     if (v != 0) return v;
@@ -212,6 +248,8 @@ int check_common(const bacon_ivp_config* cfg, int rhs_id, const double* y0, cons
         if (rhs_id < 0 || rhs_id >= (int)r.entries.size()) return fail(BACON_E_BAD_ARGUMENT, "unknown rhs id %d", rhs_id);
         *entry = r.entries[rhs_id];
     }
+    // (the reference has no counterpart of this failure: a solver and a derivative of different dimensions do not
+    // type-check there, or panic inside nalgebra, ivp.rs:178; the Dimension errors 11 / 12 belong to the constructors)
     if (cfg->dim != entry->dim)
         return fail(BACON_E_BAD_ARGUMENT, "cfg.dim=%d but rhs '%s' has DIM=%d", cfg->dim, entry->name.c_str(), entry->dim);
     if (cfg->n_params != entry->n_params)
@@ -223,15 +261,35 @@ int check_common(const bacon_ivp_config* cfg, int rhs_id, const double* y0, cons
         return fail(BACON_E_BAD_ARGUMENT, "history_capacity > 0 needs out.hist ([n][capacity][1 + dim])");
     // REF_LITERAL is the source as written, operation order included: only the strict kernels implement it
     const int strict = ((cfg->flags & BACON_FLAG_STRICT_FP) || cfg->semantics == BACON_SEM_LITERAL) ? 1 : 0;
-    *fn = entry->launch[strict][cfg->method];
+    // any optional input (restart record, terminal event) selects the kernels compiled for them (drive.cuh: EVENT)
+    const bool with_opts = cfg->dt_init > 0.0 || (opts && (opts->event_w || opts->t_start_each || opts->dt_start_each));
+    if (opts && opts->event_w) {
+        if (cfg->dim > 32) return fail(BACON_E_UNSUPPORTED, "terminal events: dim <= 32");
+        if (opts->event_direction < -1 || opts->event_direction > 1)
+            return fail(BACON_E_BAD_ARGUMENT, "event_direction must be -1, 0 or +1");
+    }
+    *fn = with_opts ? entry->launch_event[strict][cfg->method] : entry->launch[strict][cfg->method];
     if (!*fn)
-        return fail(BACON_E_UNSUPPORTED, "rhs '%s' was not built for method %d (%s)", entry->name.c_str(), cfg->method,
-                    strict ? "strict" : "fast");
+        return fail(BACON_E_UNSUPPORTED, "rhs '%s' was not built for method %d (%s%s)", entry->name.c_str(), cfg->method,
+                    strict ? "strict" : "fast", with_opts ? ", optional inputs" : "");
     return 0;
 }
 
-// What every launch needs: the problem, the stream, and a zeroed work counter from the context's ring.  The caller
-// holds g_ctx_mu.
+// the optional inputs of a launch; t0 / dt0 are DEVICE pointers here
+void apply_options(bacon_launch_args& a, const bacon_ivp_options* opts, const double* d_t0, const double* d_dt0) {
+    if (!opts) return;
+    a.t0_each = d_t0;
+    a.dt0_each = d_dt0;
+    if (opts->event_w) {
+        a.ev_on = 1;
+        a.ev_direction = opts->event_direction;
+        a.ev_c = opts->event_c;
+        for (int d = 0; d < a.cfg.dim && d < 32; ++d) a.ev_w[d] = opts->event_w[d];
+    }
+}
+
+// What every launch needs: the problem, the stream, and a zeroed work counter from the context's ring (the ring's
+// cursor is guarded by g_ctx_mu; fill_args_locked is for callers that hold it already).
 int fill_args_locked(bacon_launch_args& a, const bacon_ivp_config* cfg, size_t n, const double* y0, const double* params,
                      const bacon_ivp_result& out, cudaStream_t stream, DeviceCtx& ctx) {
     a = bacon_launch_args{};
@@ -248,14 +306,22 @@ int fill_args_locked(bacon_launch_args& a, const bacon_ivp_config* cfg, size_t n
     return 0;
 }
 
+int fill_args(bacon_launch_args& a, const bacon_ivp_config* cfg, size_t n, const double* y0, const double* params,
+              const bacon_ivp_result& out, cudaStream_t stream, DeviceCtx& ctx) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    return fill_args_locked(a, cfg, n, y0, params, out, stream, ctx);
+}
+
 int launch_on_device(const bacon_ivp_config* cfg, bacon_launch_fn fn, size_t n, const double* d_y0,
-                     const double* d_params, const bacon_ivp_result* d_out, cudaStream_t stream, int dev,
-                     DeviceCtx& ctx, cudaEvent_t ev_start, cudaEvent_t ev_stop, bacon_launch_args* filled) {
+                     const double* d_params, const bacon_ivp_options* opts, const bacon_ivp_result* d_out,
+                     cudaStream_t stream, int dev, DeviceCtx& ctx, cudaEvent_t ev_start, cudaEvent_t ev_stop,
+                     bacon_launch_args* filled) {
     bacon_launch_args a;
     {
         std::lock_guard<std::mutex> lk(g_ctx_mu);
         if (const int rc = fill_args_locked(a, cfg, n, d_y0, d_params, *d_out, stream, ctx)) return rc;
     }
+    apply_options(a, opts, opts ? opts->t_start_each : nullptr, opts ? opts->dt_start_each : nullptr);
     (void)dev;
     if (ev_start) CUDA_TRY(cudaEventRecord(ev_start, stream));
     g_last_error.clear();
@@ -279,8 +345,9 @@ const char* bacon_status_name(int s) {
     static const char* names[] = {"Ok", "MissingParameters", "UserError", "ToleranceOOB", "TimeDeltaOOB", "TimeEndOOB",
                                   "TimeStartOOB", "FromPrimitiveFailure", "MinimumTimeDeltaExceeded",
                                   "MaximumIterationsExceeded", "SingularMatrix", "DynamicOnStatic", "StaticOnDynamic",
-                                  "NonFinite", "MaxAttempts", "HistoryOverflow", "CudaError", "BadArgument", "Unsupported"};
-    if (s < 0 || s > BACON_E_UNSUPPORTED) return "Unknown";
+                                  "NonFinite", "MaxAttempts", "HistoryOverflow", "CudaError", "BadArgument", "Unsupported",
+                                  "StoppedAtEvent"};
+    if (s < 0 || s > BACON_STOPPED_AT_EVENT) return "Unknown";
     return names[s];
 }
 
@@ -295,7 +362,29 @@ struct bacon_solver {
     uint64_t max_attempts;
     bool has_euler_dt;  // Euler keeps ONE dt: the first bound given, then averaged with later ones (ivp.rs:396-421)
     double euler_dt;
+    double dt_init;     // bacon_solver_with_initial_dt; 0 = the reference's (dt_max + dt_min)/2
 };
+
+// IVPSolver::new / new_dyn with the reference's Dimension check (lib.rs:53-76): dim_type >= 1 is Const<C>, BACON_DIM_DYN is Dyn
+int bacon_solver_new_static(int method, int dim_type, bacon_solver** out) {
+    if (!out) return fail(BACON_E_BAD_ARGUMENT, "NULL out");
+    *out = nullptr;
+    if (dim_type == BACON_DIM_DYN)  // Dyn::dim() (lib.rs:69-71)
+        return fail(BACON_E_STATIC_ON_DYNAMIC, "attempted to build a static solver with dynamic dimension");
+    if (dim_type < 0) return fail(BACON_E_BAD_ARGUMENT, "dim_type must be a dimension >= 1 or BACON_DIM_DYN");
+    *out = bacon_solver_new(method, dim_type);  // Const<C>::dim() (lib.rs:59-61)
+    return *out ? 0 : BACON_E_BAD_ARGUMENT;
+}
+int bacon_solver_new_dyn(int method, int dim_type, int size, bacon_solver** out) {
+    if (!out) return fail(BACON_E_BAD_ARGUMENT, "NULL out");
+    *out = nullptr;
+    if (dim_type != BACON_DIM_DYN) {  // Const<C>::dim_dyn(size) (lib.rs:63-65)
+        if (dim_type < 0) return fail(BACON_E_BAD_ARGUMENT, "dim_type must be a dimension >= 1 or BACON_DIM_DYN");
+        return fail(BACON_E_DYNAMIC_ON_STATIC, "attempted to build a dynamic solver with static dimension");
+    }
+    *out = bacon_solver_new(method, size);  // Dyn::dim_dyn(size) (lib.rs:73-75)
+    return *out ? 0 : BACON_E_BAD_ARGUMENT;
+}
 
 bacon_solver* bacon_solver_new(int method, int dim) {
     if (method < 0 || method >= BACON_N_METHODS) {
@@ -362,6 +451,12 @@ int bacon_solver_with_ending_time(bacon_solver* s, double ending) {
     if (s->has_t0 && s->t0 >= ending) return fail(BACON_E_TIME_END_OOB, "ending time must be after the initial time");
     return 0;
 }
+int bacon_solver_with_initial_dt(bacon_solver* s, double dt) {
+    if (!s) return fail(BACON_E_BAD_ARGUMENT, "NULL solver");
+    if (!(dt > 0.0)) return fail(BACON_E_TIME_DELTA_OOB, "initial dt must be > 0");
+    s->dt_init = dt;
+    return 0;
+}
 int bacon_solver_with_semantics(bacon_solver* s, int semantics) {
     if (!s || (semantics != BACON_SEM_CORRECTED && semantics != BACON_SEM_LITERAL))
         return fail(BACON_E_BAD_ARGUMENT, "bad semantics");
@@ -417,6 +512,7 @@ int bacon_solver_config(const bacon_solver* s, bacon_ivp_config* out) {
     out->t_start = s->t0;
     out->t_end = s->t1;
     out->max_attempts = s->max_attempts;
+    out->dt_init = s->dt_init;
     return 0;
 }
 
@@ -431,6 +527,7 @@ int bacon_ivp_validate(const bacon_ivp_config* c) {
     if (c->dt_max <= 0.0 || c->dt_min <= 0.0) return fail(BACON_E_TIME_DELTA_OOB, "dt bounds must be > 0");
     if (c->dt_min > c->dt_max) return fail(BACON_E_TIME_DELTA_OOB, "dt_min > dt_max");
     if (c->t_end <= c->t_start) return fail(BACON_E_TIME_END_OOB, "t_end must be after t_start");
+    if (!(c->dt_init >= 0.0)) return fail(BACON_E_TIME_DELTA_OOB, "dt_init must be > 0 (or 0 = the default)");
     return 0;
 }
 
@@ -448,6 +545,9 @@ int bacon_rhs_register(const bacon_rhs_desc* d) {
                     if (d->launch[s][m]) e.launch[s][m] = d->launch[s][m];
             for (int s = 0; s < 2; ++s)
                 if (d->path_query[s]) e.path_query[s] = d->path_query[s];
+            for (int s = 0; s < 2; ++s)
+                for (int m = 0; m < BACON_N_METHODS; ++m)
+                    if (d->launch_event[s][m]) e.launch_event[s][m] = d->launch_event[s][m];
             return (int)i;
         }
     }
@@ -457,6 +557,7 @@ int bacon_rhs_register(const bacon_rhs_desc* d) {
     e.n_params = d->n_params;
     std::memcpy(e.launch, d->launch, sizeof(e.launch));
     std::memcpy(e.path_query, d->path_query, sizeof(e.path_query));
+    std::memcpy(e.launch_event, d->launch_event, sizeof(e.launch_event));
     r.entries.push_back(e);
     return (int)r.entries.size() - 1;
 }
@@ -484,11 +585,12 @@ int bacon_rhs_info(int id, const char** name, int* dim, int* n_params) {
 }
 
 // ---------------------------------------------------------------- solves
-int bacon_ivp_solve_ensemble_device(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* d_y0,
-                                    const double* d_params, const bacon_ivp_result* d_out, void* stream) {
+int bacon_ivp_solve_ensemble_device_ex(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* d_y0,
+                                       const double* d_params, const bacon_ivp_options* opts,
+                                       const bacon_ivp_result* d_out, void* stream) {
     RhsEntry entry;
     bacon_launch_fn fn = nullptr;
-    int rc = check_common(cfg, rhs_id, d_y0, d_params, d_out, &entry, &fn);
+    int rc = check_common(cfg, rhs_id, d_y0, d_params, opts, d_out, &entry, &fn);
     if (rc != 0) return rc;
     if (cfg->history_capacity > 0 && (reinterpret_cast<uintptr_t>(d_out->hist) & 31u))
         return fail(BACON_E_BAD_ARGUMENT, "d_out.hist must be 32-byte aligned (records are written with 256-bit stores)");
@@ -507,7 +609,7 @@ int bacon_ivp_solve_ensemble_device(const bacon_ivp_config* cfg, int rhs_id, siz
         CUDA_TRY(cudaEventCreate(&g_tl.stop[dev]));
     }
     bacon_launch_args filled{};
-    rc = launch_on_device(cfg, fn, n, d_y0, d_params, d_out, (cudaStream_t)stream, dev, *ctx, g_tl.start[dev],
+    rc = launch_on_device(cfg, fn, n, d_y0, d_params, opts, d_out, (cudaStream_t)stream, dev, *ctx, g_tl.start[dev],
                           g_tl.stop[dev], &filled);
     if (rc != 0) return rc;
     g_tl.last_dev = dev;
@@ -518,20 +620,30 @@ int bacon_ivp_solve_ensemble_device(const bacon_ivp_config* cfg, int rhs_id, siz
     g_last_launch.n_kernels = filled.n_kernels;
     return 0;
 }
+int bacon_ivp_solve_ensemble_device(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* d_y0,
+                                    const double* d_params, const bacon_ivp_result* d_out, void* stream) {
+    return bacon_ivp_solve_ensemble_device_ex(cfg, rhs_id, n, d_y0, d_params, nullptr, d_out, stream);
+}
 
 int bacon_ivp_solve_ensemble(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0, const double* params,
                              const bacon_ivp_result* out) {
-    return bacon_ivp_solve_ensemble_multi(cfg, rhs_id, n, y0, params, out, 1);
+    return bacon_ivp_solve_ensemble_ex(cfg, rhs_id, n, y0, params, nullptr, out, 1);
+}
+int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0,
+                                   const double* params, const bacon_ivp_result* out, int n_gpus) {
+    return bacon_ivp_solve_ensemble_ex(cfg, rhs_id, n, y0, params, nullptr, out, n_gpus);
 }
 
 // Round-robin sharding (trajectory i -> GPU i mod G): parameter
 // sweeps stay balanced, no data-path collective.  With G == 1 the shard IS the
-// caller's buffer and no repacking happens.
-int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0,
-                                   const double* params, const bacon_ivp_result* out, int n_gpus) {
+// caller's buffer and no repacking happens.  Concurrency: a call holds the `use` mutex of every device it runs on
+// (taken in device order), so host solves on different devices of one process run side by side.
+int bacon_ivp_solve_ensemble_ex(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0,
+                                const double* params, const bacon_ivp_options* opts, const bacon_ivp_result* out,
+                                int n_gpus) {
     RhsEntry entry;
     bacon_launch_fn fn = nullptr;
-    int rc = check_common(cfg, rhs_id, y0, params, out, &entry, &fn);
+    int rc = check_common(cfg, rhs_id, y0, params, opts, out, &entry, &fn);
     if (rc != 0) return rc;
     g_last_launch = bacon_ivp_launch_info{};
     g_tl.pending = false;
@@ -539,29 +651,41 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
     int have = 0;
     CUDA_TRY(cudaGetDeviceCount(&have));
     if (n_gpus < 1 || n_gpus > have) return fail(BACON_E_BAD_ARGUMENT, "n_gpus=%d but %d device(s) visible", n_gpus, have);
-    int dev0 = 0;
-    CUDA_TRY(cudaGetDevice(&dev0));
+    DeviceGuard restore;  // the caller's current device comes back on every way out
+    if (!restore.ok) return fail(BACON_E_CUDA, "cudaGetDevice failed");
+    const int dev0 = restore.dev;
     const int G = n_gpus;
     const bool shared = (cfg->flags & BACON_FLAG_SHARED_PARAMS) != 0;
     const int D = cfg->dim, P = cfg->n_params;
     const size_t cap = cfg->history_capacity > 0 ? (size_t)cfg->history_capacity : 0;
+    const bool has_opts = cfg->dt_init > 0.0 || (opts && (opts->t_start_each || opts->dt_start_each || opts->event_w));
 
     struct Shard {
-        int dev;
-        size_t n;
-        DeviceCtx* ctx;
-        ShardLayout dl, hl;  // device / pinned-host layouts
-        bacon_launch_args filled;
+        int dev = 0;
+        size_t n = 0;
+        DeviceCtx* ctx = nullptr;
+        ShardLayout dl{}, hl{};  // device / pinned-host layouts
+        bacon_launch_args filled{};
     };
     std::vector<Shard> shards(G);
-    std::lock_guard<std::mutex> lk_all(g_ctx_mu);  // host-buffer solves are serialised per process
+    for (int g = 0; g < G; ++g) {
+        Shard& s = shards[g];
+        s.dev = (G == 1) ? dev0 : g;
+        s.n = (n + G - 1 - g) / G;  // indices g, g+G, ...
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        CUDA_TRY(cudaSetDevice(s.dev));
+        rc = get_ctx(s.dev, &s.ctx);
+        if (rc != 0) return rc;
+    }
+    std::vector<std::unique_lock<std::mutex>> held;  // (device order: G == 1 holds one, G > 1 holds 0 .. G-1)
+    for (int g = 0; g < G; ++g) held.emplace_back(shards[g].ctx->use);
 
     // Zero-copy: per-trajectory I/O is a few dozen bytes against thousands of register-only steps, so with
     // page-locked caller buffers the persistent kernel can read its initial conditions and post its
     // retirement records over the host link itself; nothing is staged and nothing is left to copy at the end.
     // (Not for large per-trajectory parameter blocks: those are streamed once by DMA instead.)
     const size_t in_doubles = (size_t)D + (shared ? 0 : (size_t)P);
-    if (G == 1 && cap == 0 && in_doubles <= 32 && (cfg->flags & BACON_FLAG_ZERO_COPY)) {
+    if (G == 1 && cap == 0 && !has_opts && in_doubles <= 32 && (cfg->flags & BACON_FLAG_ZERO_COPY)) {
         void *zy0 = nullptr, *zp = nullptr;
         bacon_ivp_result z{};
         bool ok = pinned_device_pointer(y0, &zy0) && pinned_device_pointer(P > 0 ? params : nullptr, &zp);
@@ -578,17 +702,15 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
         ZC(n_rhs, uint32_t);
 #undef ZC
         if (ok) {
-            DeviceCtx* ctx = nullptr;
-            rc = get_ctx(dev0, &ctx);
-            if (rc != 0) return rc;
+            DeviceCtx* ctx = shards[0].ctx;
             cudaStream_t st = ctx->stream;
             bacon_launch_args a;
-            rc = fill_args_locked(a, cfg, n, (const double*)zy0, (const double*)zp, z, st, *ctx);
+            rc = fill_args(a, cfg, n, (const double*)zy0, (const double*)zp, z, st, *ctx);
             if (rc != 0) return rc;
             // A refill over the host link costs a lane ~2 us and its 31 warp-mates wait at the loop's latch, ~9 times per
             // lane: 0.6 ms of a 31 ms launch.  So only the FIRST trajectory of every lane is read from the caller's
             // memory (nothing to wait for); meanwhile a DMA copies all inputs into device memory on a second stream
-            // and then raises a flag the refills check.
+            // and then raises a flag the refills check (with a bounded wait: ivp_common.cuh, wait_until_set).
             const size_t y0_bytes = sizeof(double) * (size_t)D * n, p_bytes = (shared || P == 0) ? 0 : sizeof(double) * (size_t)P * n;
             rc = ensure_device_buf(*ctx, y0_bytes + p_bytes + 256);
             if (rc != 0) return rc;
@@ -623,33 +745,44 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
 
     for (int g = 0; g < G; ++g) {
         Shard& s = shards[g];
-        s.dev = (G == 1) ? dev0 : g;
-        s.n = (n + G - 1 - g) / G;  // indices g, g+G, ...
         if (s.n == 0) continue;
         CUDA_TRY(cudaSetDevice(s.dev));
-        rc = get_ctx(s.dev, &s.ctx);
-        if (rc != 0) return rc;
-        s.dl = layout_shard(nullptr, *cfg, s.n, shared, *out);
+        s.dl = layout_shard(nullptr, *cfg, s.n, shared, *out, opts);
         rc = ensure_device_buf(*s.ctx, s.dl.bytes);
         if (rc != 0) return rc;
-        s.dl = layout_shard(s.ctx->d_buf, *cfg, s.n, shared, *out);
+        s.dl = layout_shard(s.ctx->d_buf, *cfg, s.n, shared, *out, opts);
         if (G > 1) {
             rc = ensure_host_buf(*s.ctx, s.dl.bytes);
             if (rc != 0) return rc;
-            s.hl = layout_shard(s.ctx->h_buf, *cfg, s.n, shared, *out);
-            // pack the strided shard (i = g + k*G) into pinned memory
+            s.hl = layout_shard(s.ctx->h_buf, *cfg, s.n, shared, *out, opts);
+        }
+    }
+    if (G > 1) {
+        // pack the strided shards (i = g + k*G) into pinned memory: (shard, chunk of trajectories) tasks on host threads
+        constexpr size_t CHUNK = 1 << 16;
+        const size_t chunks = (shards[0].n + CHUNK - 1) / CHUNK;
+        parallel_for((size_t)G * chunks, [&](size_t task) {
+            const int g = (int)(task / chunks);
+            const Shard& s = shards[g];
+            const size_t k0 = (task % chunks) * CHUNK, k1 = std::min(s.n, k0 + CHUNK);
             for (int d = 0; d < D; ++d)
-                for (size_t k = 0; k < s.n; ++k) s.hl.y0[(size_t)d * s.n + k] = y0[(size_t)d * n + g + k * G];
-            if (P > 0) {
-                if (shared) std::memcpy(s.hl.params, params, sizeof(double) * P);
-                else if (cfg->flags & BACON_FLAG_PARAMS_AOS)
-                    for (size_t k = 0; k < s.n; ++k)
+                for (size_t k = k0; k < k1; ++k) s.hl.y0[(size_t)d * s.n + k] = y0[(size_t)d * n + g + k * G];
+            if (P > 0 && !shared) {
+                if (cfg->flags & BACON_FLAG_PARAMS_AOS)
+                    for (size_t k = k0; k < k1; ++k)
                         std::memcpy(s.hl.params + k * P, params + (g + k * G) * (size_t)P, sizeof(double) * P);
                 else
                     for (int p = 0; p < P; ++p)
-                        for (size_t k = 0; k < s.n; ++k) s.hl.params[(size_t)p * s.n + k] = params[(size_t)p * n + g + k * G];
+                        for (size_t k = k0; k < k1; ++k) s.hl.params[(size_t)p * s.n + k] = params[(size_t)p * n + g + k * G];
             }
-        }
+            if (s.hl.t0)
+                for (size_t k = k0; k < k1; ++k) s.hl.t0[k] = opts->t_start_each[g + k * G];
+            if (s.hl.dt0)
+                for (size_t k = k0; k < k1; ++k) s.hl.dt0[k] = opts->dt_start_each[g + k * G];
+        });
+        if (P > 0 && shared)
+            for (int g = 0; g < G; ++g)
+                if (shards[g].n) std::memcpy(shards[g].hl.params, params, sizeof(double) * P);
     }
 
     // enqueue H2D -> kernel -> D2H on every device's own stream, then wait for all
@@ -665,10 +798,15 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
         if (P > 0)
             CUDA_TRY(cudaMemcpyAsync(s.dl.params, src_p, sizeof(double) * (shared ? (size_t)P : (size_t)P * s.n),
                                      cudaMemcpyHostToDevice, st));
+        if (s.dl.t0)
+            CUDA_TRY(cudaMemcpyAsync(s.dl.t0, (G == 1) ? opts->t_start_each : s.hl.t0, sizeof(double) * s.n, cudaMemcpyHostToDevice, st));
+        if (s.dl.dt0)
+            CUDA_TRY(cudaMemcpyAsync(s.dl.dt0, (G == 1) ? opts->dt_start_each : s.hl.dt0, sizeof(double) * s.n, cudaMemcpyHostToDevice, st));
         {
-            bacon_launch_args a;  // (g_ctx_mu is held: lk_all)
-            rc = fill_args_locked(a, cfg, s.n, s.dl.y0, s.dl.params, s.dl.out, st, *s.ctx);
+            bacon_launch_args a;
+            rc = fill_args(a, cfg, s.n, s.dl.y0, s.dl.params, s.dl.out, st, *s.ctx);
             if (rc != 0) return rc;
+            apply_options(a, opts, s.dl.t0, s.dl.dt0);
             if (cap)  // slots beyond hist_len read as zero on the host (the staging buffer is reused between calls)
                 CUDA_TRY(cudaMemsetAsync(s.dl.out.hist, 0, sizeof(double) * s.n * cap * (D + 1), st));
             CUDA_TRY(cudaEventRecord(s.ctx->ev[1], st));
@@ -711,13 +849,20 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
         h2d_ms = a > h2d_ms ? a : h2d_ms;
         k_ms = b > k_ms ? b : k_ms;  // max over devices
         d2h_ms = c > d2h_ms ? c : d2h_ms;
-        if (G > 1) {  // scatter the shard back into the caller's arrays
+    }
+    if (G > 1) {  // scatter the shards back into the caller's arrays (same tasks as the packing)
+        constexpr size_t CHUNK = 1 << 16;
+        const size_t chunks = (shards[0].n + CHUNK - 1) / CHUNK;
+        parallel_for((size_t)G * chunks, [&](size_t task) {
+            const int g = (int)(task / chunks);
+            const Shard& s = shards[g];
+            const size_t k0 = (task % chunks) * CHUNK, k1 = std::min(s.n, k0 + CHUNK);
             const bacon_ivp_result& h = s.hl.out;
             for (int d = 0; d < D; ++d)
-                for (size_t k = 0; k < s.n; ++k) out->y_end[(size_t)d * n + g + k * G] = h.y_end[(size_t)d * s.n + k];
+                for (size_t k = k0; k < k1; ++k) out->y_end[(size_t)d * n + g + k * G] = h.y_end[(size_t)d * s.n + k];
 #define SCATTER(field)                                                       \
     if (out->field && h.field)                                               \
-        for (size_t k = 0; k < s.n; ++k) out->field[g + k * G] = h.field[k]
+        for (size_t k = k0; k < k1; ++k) out->field[g + k * G] = h.field[k]
             SCATTER(t_end);
             SCATTER(dt_end);
             SCATTER(status);
@@ -727,13 +872,12 @@ int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config* cfg, int rhs_id, size
             if (cap) {
                 SCATTER(hist_len);
                 const size_t path = cap * (size_t)(D + 1);  // doubles per trajectory
-                for (size_t k = 0; k < s.n; ++k)
+                for (size_t k = k0; k < k1; ++k)
                     std::memcpy(out->hist + (g + k * G) * path, h.hist + k * path, sizeof(double) * path);
             }
 #undef SCATTER
-        }
+        });
     }
-    CUDA_TRY(cudaSetDevice(dev0));
     g_last_launch.kernel_ms = k_ms;
     g_last_launch.h2d_ms = h2d_ms;
     g_last_launch.d2h_ms = d2h_ms;
@@ -821,6 +965,9 @@ int path_query_device(const bacon_ivp_config* cfg, int rhs_id, size_t n, const d
         a.t_end = d_solved->t_end;
         a.y_end = d_solved->y_end;
     }
+    a.n_accept = d_solved->n_accept;
+    a.status = d_solved->status;
+    a.t_start_each = d_solved->t_start;
     a.op = q.op;
     a.n_times = q.n_times;
     a.times = q.times;
@@ -873,7 +1020,7 @@ int path_query_host(const bacon_ivp_config* cfg, int rhs_id, size_t n, const dou
     if (rc != 0) return rc;
     if (n == 0 || (q.op == BACON_PATH_SAMPLE && q.n_times == 0)) return 0;
     const size_t dim = (size_t)cfg->dim, cap = (size_t)cfg->history_capacity, np = (size_t)cfg->n_params;
-    DevBlock b_y0, b_par, b_hist, b_len, b_tend, b_yend, b_times, b_out, b_cnt;
+    DevBlock b_y0, b_par, b_hist, b_len, b_tend, b_yend, b_times, b_out, b_cnt, b_acc, b_stat, b_t0;
     if ((rc = b_y0.put(y0, 8 * dim * n))) return rc;
     if (np > 0 && (rc = b_par.put(params, 8 * np * ((cfg->flags & BACON_FLAG_SHARED_PARAMS) ? 1 : n)))) return rc;
     if ((rc = b_hist.put(solved->hist, 8 * n * cap * (1 + dim)))) return rc;
@@ -886,6 +1033,18 @@ int path_query_host(const bacon_ivp_config* cfg, int rhs_id, size_t n, const dou
         if ((rc = b_yend.put(solved->y_end, 8 * dim * n))) return rc;
         d.t_end = (double*)b_tend.p;
         d.y_end = (double*)b_yend.p;
+    }
+    if (solved->n_accept) {
+        if ((rc = b_acc.put(solved->n_accept, 4 * n))) return rc;
+        d.n_accept = (uint32_t*)b_acc.p;
+    }
+    if (solved->status) {
+        if ((rc = b_stat.put(solved->status, 4 * n))) return rc;
+        d.status = (int32_t*)b_stat.p;
+    }
+    if (solved->t_start) {
+        if ((rc = b_t0.put(solved->t_start, 8 * n))) return rc;
+        d.t_start = (const double*)b_t0.p;
     }
     PathQuery dq = q;
     size_t out_bytes = 0;

@@ -58,10 +58,13 @@ template <int BLOCK, class K> inline int persistent_grid(K kernel, bacon_launch_
 template <class Stepper, class = void> struct StepperSuspends { static constexpr bool value = false; };
 template <class Stepper> struct StepperSuspends<Stepper, decltype(void(Stepper::STATE_DOUBLES))> { static constexpr bool value = true; };
 
-template <class Stepper, bool HIST, int MINB> inline int launch_stepper_hist(bacon_launch_args* a) {
-    constexpr bool WIDE = StepperSuspends<Stepper>::value && StepperMigrates<Stepper, ENSEMBLE_BLOCK * MINB>::value;
+// EVENT: the instantiation that watches a terminal event (drive.cuh: EventWatch); 128-lane CTAs, no regrouping.
+// EVENT is part of every launcher's template signature: the plain and the event launchers of one stepper may be
+// compiled in different translation units and must not share a symbol.
+template <class Stepper, bool HIST, int MINB, bool EVENT = false> inline int launch_stepper_hist(bacon_launch_args* a) {
+    constexpr bool WIDE = !EVENT && StepperSuspends<Stepper>::value && StepperMigrates<Stepper, ENSEMBLE_BLOCK * MINB>::value;
     constexpr int BLOCK = WIDE ? ENSEMBLE_BLOCK * MINB : ENSEMBLE_BLOCK;
-    auto kernel = ensemble_kernel<Stepper, HIST, BLOCK, (WIDE ? 1 : MINB)>;
+    auto kernel = ensemble_kernel<Stepper, HIST, BLOCK, (WIDE ? 1 : MINB), EVENT>;
     constexpr size_t smem = ensemble_smem_bytes<Stepper, BLOCK>();
     if (const int rc = persistent_grid<BLOCK>(kernel, a, smem)) return rc;
     a->n_kernels = 1;
@@ -90,18 +93,18 @@ template <class Stepper, int MINB> inline bool fits_one_more_warp(const bacon_la
     }
 }
 
-template <class Stepper, int MINB> inline int launch_stepper(bacon_launch_args* a) {
+template <class Stepper, int MINB, bool EVENT = false> inline int launch_stepper(bacon_launch_args* a) {
     // Dense output: one resident CTA fewer when the budget is tight (6 -> 5: 80 -> 96 registers, no re-loads of launch
     // constants inside the loop).  Measured 1-2 % faster than 6 (profiles/r01i_dense_output.md).
 #ifndef BACON_HIST_MINB_DROP
 #define BACON_HIST_MINB_DROP 1
 #endif
     constexpr int MINB_HIST = MINB >= 6 ? MINB - BACON_HIST_MINB_DROP : MINB;
-    if (a->cfg.history_capacity > 0 && a->out.hist) return launch_stepper_hist<Stepper, true, MINB_HIST>(a);
-    if constexpr (StepperSuspends<Stepper>::value && MINB >= 6 && ENSEMBLE_BLOCK * (MINB + 1) <= 1024) {
+    if (a->cfg.history_capacity > 0 && a->out.hist) return launch_stepper_hist<Stepper, true, MINB_HIST, EVENT>(a);
+    if constexpr (!EVENT && StepperSuspends<Stepper>::value && MINB >= 6 && ENSEMBLE_BLOCK * (MINB + 1) <= 1024) {
         if (fits_one_more_warp<Stepper, MINB>(a)) return launch_stepper_hist<Stepper, false, MINB + 1>(a);
     }
-    return launch_stepper_hist<Stepper, false, MINB>(a);
+    return launch_stepper_hist<Stepper, false, MINB, EVENT>(a);
 }
 
 // ---- fast (FMA, compile-time tableau), REF_CORRECTED only
@@ -114,18 +117,19 @@ template <class Rhs, class Tab> constexpr int rk_fast_minb() {
     return Rhs::DIM * (Tab::O + 1) + Rhs::NPARAM <= 28 ? 6 : 4;
 #endif
 }
-template <class Rhs, class Tab, int MINB = rk_fast_minb<Rhs, Tab>()> int launch_rk_fast(bacon_launch_args* a) {
+template <class Rhs, class Tab, bool EVENT = false, int MINB = rk_fast_minb<Rhs, Tab>()> int launch_rk_fast(bacon_launch_args* a) {
     if (a->cfg.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;
-    return launch_stepper<RkFastStepper<Rhs, Tab>, MINB>(a);
+    return launch_stepper<RkFastStepper<Rhs, Tab>, MINB, EVENT>(a);
 }
 
 // ---- strict (oracle operation order, runtime tableau in __constant__), either semantics
-template <class Rhs, class Tab, int MINB = 1> int launch_rk_strict(bacon_launch_args* a) {
+template <class Rhs, class Tab, bool EVENT = false, int MINB = 1> int launch_rk_strict(bacon_launch_args* a) {
     RkTableauRt T;
     fill_runtime_tableau<Tab>(T, a->cfg.semantics == BACON_SEM_LITERAL);
-    if (cudaMemcpyToSymbolAsync(c_rk_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, (cudaStream_t)a->stream) != cudaSuccess)
+    if (cudaMemcpyToSymbolAsync(c_rk_tabs, &T, sizeof(T), sizeof(T) * rk_tab_slot(Tab::O, a->cfg.semantics),
+                                cudaMemcpyHostToDevice, (cudaStream_t)a->stream) != cudaSuccess)
         return BACON_E_CUDA;
-    return launch_stepper<RkStrictStepper<Rhs, Tab::O>, MINB>(a);
+    return launch_stepper<RkStrictStepper<Rhs, Tab::O>, MINB, EVENT>(a);
 }
 
 // ---- BDF (Broyden as in the reference, or Newton + in-register LU with BACON_FLAG_BDF_NEWTON)
@@ -133,29 +137,54 @@ template <class Rhs, class Tab, int MINB = 1> int launch_rk_strict(bacon_launch_
 // cold paths) — the kernel is latency-bound (ncu: 3 warps per sub-partition at 168 registers, 45 % of stalls are
 // fixed-latency waits), measured 7.38e10 steps/s against 7.00e10 at 3 and 7.09e10 at 5.  The reference's Broyden
 // iteration keeps two D x D matrices alive and stays at 2.
-template <class Rhs, class Coef, bool STRICT, int MINB = 2, int MINB_NEWTON = 4> int launch_bdf(bacon_launch_args* a) {
-    if (a->cfg.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;  // REF_LITERAL BDF: CPU oracle only
+template <class Rhs, class Coef, bool STRICT, bool EVENT = false, int MINB = 2, int MINB_NEWTON = 4> int launch_bdf(bacon_launch_args* a) {
+    // REF_LITERAL (bdf.rs:407, :568, :622 as written) is the reference's own Broyden iteration in the strict build
+    if (a->cfg.semantics != BACON_SEM_CORRECTED && !(STRICT && !(a->cfg.flags & BACON_FLAG_BDF_NEWTON))) return BACON_E_UNSUPPORTED;
     if (a->cfg.flags & BACON_FLAG_BDF_NEWTON) {
         // the strict build is the reference's own (Broyden) iteration.  `if constexpr`: a strict translation
         // unit (-fmad=false) must not instantiate a kernel that a fast one also defines under the same name.
         if constexpr (STRICT) return BACON_E_UNSUPPORTED;
-        else return launch_stepper<BdfStepper<Rhs, Coef, false, true>, MINB_NEWTON>(a);
+        else return launch_stepper<BdfStepper<Rhs, Coef, false, true>, MINB_NEWTON, EVENT>(a);
     }
-    return launch_stepper<BdfStepper<Rhs, Coef, STRICT, false>, MINB>(a);
+    return launch_stepper<BdfStepper<Rhs, Coef, STRICT, false>, MINB, EVENT>(a);
 }
 
 // ---- Adams predictor-corrector and Euler.  No D1-D9 defect on these paths:
 // both semantics run the same kernel.
-template <class Rhs, class Coef, bool STRICT, int MINB = 2> int launch_adams(bacon_launch_args* a) {
-    return launch_stepper<AdamsStepper<Rhs, Coef, STRICT>, MINB>(a);
+template <class Rhs, class Coef, bool STRICT, bool EVENT = false, int MINB = 2> int launch_adams(bacon_launch_args* a) {
+    return launch_stepper<AdamsStepper<Rhs, Coef, STRICT>, MINB, EVENT>(a);
 }
-template <class Rhs, bool STRICT, int MINB = 4> int launch_euler(bacon_launch_args* a) {
-    return launch_stepper<EulerStepper<Rhs, STRICT>, MINB>(a);
+template <class Rhs, bool STRICT, bool EVENT = false, int MINB = 4> int launch_euler(bacon_launch_args* a) {
+    return launch_stepper<EulerStepper<Rhs, STRICT>, MINB, EVENT>(a);
 }
 
 // ---- registration: fills the launcher table of one RHS for THIS translation unit's build
 // flavour (fast, or strict when compiled with -DBACON_STRICT_FP -fmad=false) and hands it
 // to the engine through the C ABI (bacon_rhs_register merges the two flavours by name).
+template <class Rhs, int S, bool EVENT> void fill_launchers(bacon_launch_fn (&t)[2][BACON_N_METHODS]) {
+#ifndef BACON_SKIP_RK
+    // `if constexpr`, not `?:` — a conditional expression would instantiate BOTH launchers in BOTH builds, and the
+    // two objects would then carry same-named kernels compiled with different -fmad settings (one of which the
+    // runtime picks arbitrarily).  Each kernel must exist in exactly one object: tests/test_abi.py checks it.
+    if constexpr (S) {
+        t[S][BACON_RK45] = &launch_rk_strict<Rhs, TabRKF45, EVENT>;
+        t[S][BACON_RK23] = &launch_rk_strict<Rhs, TabBS23, EVENT>;
+    } else {
+        t[S][BACON_RK45] = &launch_rk_fast<Rhs, TabRKF45, EVENT>;
+        t[S][BACON_RK23] = &launch_rk_fast<Rhs, TabBS23, EVENT>;
+    }
+#endif
+#ifndef BACON_SKIP_BDF
+    t[S][BACON_BDF6] = &launch_bdf<Rhs, CoefBDF6, S != 0, EVENT>;
+    t[S][BACON_BDF2] = &launch_bdf<Rhs, CoefBDF2, S != 0, EVENT>;
+#endif
+#ifndef BACON_SKIP_ADAMS
+    t[S][BACON_ADAMS5] = &launch_adams<Rhs, CoefAdams5, S != 0, EVENT>;
+    t[S][BACON_ADAMS3] = &launch_adams<Rhs, CoefAdams3, S != 0, EVENT>;
+    t[S][BACON_EULER] = &launch_euler<Rhs, S != 0, EVENT>;
+#endif
+}
+
 template <class Rhs> int register_rhs(const char* name) {
     bacon_rhs_desc d{};
     d.name = name;
@@ -166,26 +195,18 @@ template <class Rhs> int register_rhs(const char* name) {
 #else
     constexpr int S = 0;
 #endif
+    // The library's own build compiles the plain kernels (-DBACON_SKIP_EVENTS) and the terminal-event kernels
+    // (-DBACON_ONLY_EVENTS) in separate objects, and the families -DBACON_SKIP_RK / _BDF / _ADAMS leave out, only to
+    // compile them in parallel; a user translation unit defines none of these and gets everything.
+#ifndef BACON_ONLY_EVENTS
+    fill_launchers<Rhs, S, false>(d.launch);
 #ifndef BACON_SKIP_RK
-    // `if constexpr`, not `?:` — a conditional expression would instantiate BOTH launchers in BOTH builds, and the
-    // two objects would then carry same-named kernels compiled with different -fmad settings (one of which the
-    // runtime picks arbitrarily).  Each kernel must exist in exactly one object: tests/test_abi.py checks it.
-    if constexpr (S) {
-        d.launch[S][BACON_RK45] = &launch_rk_strict<Rhs, TabRKF45>;
-        d.launch[S][BACON_RK23] = &launch_rk_strict<Rhs, TabBS23>;
-    } else {
-        d.launch[S][BACON_RK45] = &launch_rk_fast<Rhs, TabRKF45>;
-        d.launch[S][BACON_RK23] = &launch_rk_fast<Rhs, TabBS23>;
-    }
     // queries on stored paths (path_query.cuh) serve every method; they live in the object that holds the RK kernels
     d.path_query[S] = &launch_path_query<Rhs, S != 0>;
 #endif
-#ifndef BACON_SKIP_BDF
-    d.launch[S][BACON_BDF6] = &launch_bdf<Rhs, CoefBDF6, S != 0>;
-    d.launch[S][BACON_BDF2] = &launch_bdf<Rhs, CoefBDF2, S != 0>;
-    d.launch[S][BACON_ADAMS5] = &launch_adams<Rhs, CoefAdams5, S != 0>;
-    d.launch[S][BACON_ADAMS3] = &launch_adams<Rhs, CoefAdams3, S != 0>;
-    d.launch[S][BACON_EULER] = &launch_euler<Rhs, S != 0>;
+#endif
+#ifndef BACON_SKIP_EVENTS
+    fill_launchers<Rhs, S, true>(d.launch_event);
 #endif
     return bacon_rhs_register(&d);
 }

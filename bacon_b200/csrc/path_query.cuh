@@ -43,6 +43,9 @@ struct bacon_path_args {
     const uint32_t* hist_len;   // [n]
     const double* t_end;        // [n] or NULL
     const double* y_end;        // [dim][n] or NULL (both or neither)
+    const uint32_t* n_accept;   // [n] or NULL: points the solve yielded (> capacity: the stored path was cut short)
+    const int32_t* status;      // [n] or NULL (used when n_accept is not given)
+    const double* t_start_each; // [n] or NULL: per-trajectory start times (a resumed leg, bacon_ivp_options); else cfg.t_start
     int32_t op;                 // BACON_PATH_SAMPLE / BACON_PATH_EVENTS
     // sampling
     unsigned long long n_times;
@@ -176,10 +179,13 @@ template <int D> struct PathView {
         y_end = a.y_end;
         const uint32_t len = a.hist_len[i];
         m = len < cap ? len : cap;
-        t0 = a.cfg.t_start;
+        t0 = a.t_start_each ? a.t_start_each[i] : a.cfg.t_start;
         closing = false;
         tc = 0.0;
-        if (a.t_end && a.y_end) {
+        // A path that overflowed its capacity ENDS at its last record: (t_end, y_end) lies a whole unrecorded span
+        // later, and one cubic must not bridge it — times past the last record give NaN, as the header promises.
+        const bool cut = a.n_accept ? a.n_accept[i] > cap : (a.status ? a.status[i] == BACON_E_HISTORY_OVERFLOW : false);
+        if (a.t_end && a.y_end && !cut) {
             tc = a.t_end[i];
             closing = tc > (m > 0 ? rec[(size_t)(m - 1) * R] : t0);
         }

@@ -2,8 +2,9 @@
 // sides.  Compiled twice: as is (fast: FMA contraction, compile-time tableaux) and with
 // -DBACON_STRICT_FP -fmad=false (strict: the oracle's operation order, no contraction).
 // User RHS go through exactly the same two lines: see INTEGRATION.md.
-// The build splits RK and BDF instantiations into separate objects (-DBACON_SKIP_BDF / -DBACON_SKIP_RK)
-// only to compile them in parallel; the registry merges launcher tables by RHS name.
+// The build splits the instantiations into separate objects (families -DBACON_SKIP_RK / _BDF / _ADAMS, plain kernels
+// -DBACON_SKIP_EVENTS against terminal-event kernels -DBACON_ONLY_EVENTS: see the Makefile) only to compile them in
+// parallel; the registry merges launcher tables by RHS name.
 #include "launch.cuh"
 #include "rhs_builtin.cuh"
 #include "path_query_warp.cuh"
@@ -21,7 +22,7 @@ BACON_REGISTER_RHS(RhsCos, "cos");
 BACON_REGISTER_RHS(RhsHarmonic, "harmonic");
 BACON_REGISTER_RHS(RhsLinear<4>, "linear4");
 
-#ifndef BACON_SKIP_RK
+#if !defined(BACON_SKIP_RK) && !defined(BACON_ONLY_EVENTS)
 // linear32 (BASELINE config 4): warp-per-trajectory kernels (rk_warp_linear.cuh)
 namespace {
 int register_linear32() {
@@ -30,12 +31,12 @@ int register_linear32() {
     d.dim = 32;
     d.n_params = 32 * 32;
 #ifdef BACON_STRICT_FP
-    d.launch[1][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, true>;
-    d.launch[1][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, true>;
+    d.launch[1][BACON_RK45] = d.launch_event[1][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, true>;
+    d.launch[1][BACON_RK23] = d.launch_event[1][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, true>;
     d.path_query[1] = &launch_path_query_linear32<true>;
 #else
-    d.launch[0][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, false>;
-    d.launch[0][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, false>;
+    d.launch[0][BACON_RK45] = d.launch_event[0][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, false>;
+    d.launch[0][BACON_RK23] = d.launch_event[0][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, false>;
     d.path_query[0] = &launch_path_query_linear32<false>;
 #endif
     return bacon_rhs_register(&d);

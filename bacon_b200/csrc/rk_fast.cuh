@@ -126,6 +126,7 @@ template <class Tab> __host__ __device__ constexpr bool stage_used(int j) {
 //   bacon_status);  t, dt, n_rej, n_rhs();  accepted count: field n_acc, or acc_running() / acc_of(raw) + status_of(raw)
 //   when attempt() returns an encoded status (StepperCodec, drive.cuh);  out_t()/out_y() = the yielded point;  end_y().
 template <class Rhs, class Tab> struct RkFastStepper {
+    using RhsT = Rhs;
     static constexpr int D = Rhs::DIM;
     static constexpr int P = Rhs::NPARAM;
     static constexpr int O = Tab::O;
@@ -192,6 +193,10 @@ template <class Rhs, class Tab> struct RkFastStepper {
         n_rej = 0;
         rearm(0);
         if (live) load_problem<D, P>(a, idx, y, p);
+    }
+    // restart record (bacon_ivp_options), applied by the kernels compiled with the optional inputs (drive.cuh: EVENT)
+    __device__ __forceinline__ void apply_restart(const bacon_launch_args& a, unsigned long long idx) {
+        trajectory_start(a, idx, dt_min, dt_max, t, dt);
     }
     __device__ __forceinline__ uint32_t n_rhs() const { return n_att() * (uint32_t)O; }
     __device__ __forceinline__ double out_t() const { return t; }

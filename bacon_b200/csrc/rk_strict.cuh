@@ -17,9 +17,13 @@
 
 namespace bacon {
 
-static __constant__ RkTableauRt c_rk_tab;
+// One constant buffer per (tableau, semantics): its content never changes, so strict or LITERAL solves that run
+// concurrently on different streams (the device entry point is asynchronous) cannot overwrite each other's tableau
+// under a running kernel; every launch re-writes its slot with the same bytes.
+static __constant__ RkTableauRt c_rk_tabs[4];
 
 template <class Rhs, int O_> struct RkStrictStepper {
+    using RhsT = Rhs;
     static constexpr int D = Rhs::DIM;
     static constexpr int P = Rhs::NPARAM;
     static constexpr int O = O_;
@@ -30,8 +34,10 @@ template <class Rhs, int O_> struct RkStrictStepper {
     double hs[O][D];  // half_steps columns (rk.rs:323-327)
     double t, dt;
     uint32_t n_acc, n_rej, n_att;
+    int tab_slot;
 
     __device__ __forceinline__ explicit RkStrictStepper(const bacon_launch_args& a) {
+        tab_slot = rk_tab_slot(O, a.cfg.semantics);
         t_start = a.cfg.t_start;
         t_end = a.cfg.t_end;
         dt_min = a.cfg.dt_min;
@@ -54,6 +60,9 @@ template <class Rhs, int O_> struct RkStrictStepper {
             for (int d = 0; d < D; ++d) hs[i][d] = 0.0;
         if (live) load_problem<D, P>(a, idx, y, p);
     }
+    __device__ __forceinline__ void apply_restart(const bacon_launch_args& a, unsigned long long idx) {
+        trajectory_start(a, idx, dt_min, dt_max, t, dt);
+    }
     __device__ __forceinline__ uint32_t n_rhs() const { return n_att * (uint32_t)O; }
     __device__ __forceinline__ double out_t() const { return t; }
     __device__ __forceinline__ const double (&out_y() const)[D] { return y; }
@@ -61,6 +70,7 @@ template <class Rhs, int O_> struct RkStrictStepper {
 
     __device__ __forceinline__ int attempt(bool& yielded) {
         const Rhs rhs{};
+        const RkTableauRt& c_rk_tab = c_rk_tabs[tab_slot];
         yielded = false;
         if (n_att >= cap) return BACON_E_MAX_ATTEMPTS;
         if (t >= t_end) return BACON_OK;                            // rk.rs:362-364

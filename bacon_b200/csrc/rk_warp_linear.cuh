@@ -34,12 +34,14 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
     const double t_start = a.cfg.t_start, t_end = a.cfg.t_end;
     const double dt_min = a.cfg.dt_min, dt_max = a.cfg.dt_max, tol = a.cfg.tol;
     const double tol2 = tol * tol, inv_tol2 = 1.0 / tol2;
-    const double dt0 = STRICT ? __dmul_rn(__dadd_rn(dt_max, dt_min), 0.5) : (dt_max + dt_min) * 0.5;
+    double dt0 = STRICT ? __dmul_rn(__dadd_rn(dt_max, dt_min), 0.5) : (dt_max + dt_min) * 0.5;
+    initial_dt_given(a, dt_min, dt_max, dt0);
     const uint32_t cap = (a.cfg.max_attempts == 0 || a.cfg.max_attempts > 0xFFFFFFFEull) ? 0xFFFFFFFEu
                                                                                          : (uint32_t)a.cfg.max_attempts;
     const uint32_t hcap = (uint32_t)a.cfg.history_capacity;
     const bool aos = (a.cfg.flags & BACON_FLAG_PARAMS_AOS) != 0;
     const bool shared = (a.cfg.flags & BACON_FLAG_SHARED_PARAMS) != 0;
+    [[maybe_unused]] const RkTableauRt& c_rk_tab = c_rk_tabs[rk_tab_slot(O, a.cfg.semantics)];  // (strict only)
 
     // y' = A y : dy_i = sum_j A[i][j] Y[j], Y broadcast from shared memory
     auto matvec = [&](const double (&A)[N], double Yi) -> double {
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
         }
         double y = a.y0[(size_t)lane * n + idx];
         double t = t_start, dt = dt0;
+        trajectory_start(a, idx, dt_min, dt_max, t, dt);  // restart record (bacon_ivp_options)
         uint32_t n_acc = 0, n_rej = 0, n_att = 0;
         int st = -1;
         double k[O];  // strict: half_steps (k_j = f_j*dt, persistent); fast: unscaled f_j
@@ -233,10 +236,12 @@ template <class K> inline int launch_persistent_warp(K kernel, bacon_launch_args
 }
 
 template <class Tab, bool STRICT> int launch_rk_warp_linear32(bacon_launch_args* a) {
+    if (a->ev_on) return BACON_E_UNSUPPORTED;  // (no terminal events in the warp-per-trajectory kernels; restart records: yes)
     if (STRICT) {
         RkTableauRt T;
         fill_runtime_tableau<Tab>(T, a->cfg.semantics == BACON_SEM_LITERAL);
-        if (cudaMemcpyToSymbolAsync(c_rk_tab, &T, sizeof(T), 0, cudaMemcpyHostToDevice, (cudaStream_t)a->stream) != cudaSuccess)
+        if (cudaMemcpyToSymbolAsync(c_rk_tabs, &T, sizeof(T), sizeof(T) * rk_tab_slot(Tab::O, a->cfg.semantics),
+                                    cudaMemcpyHostToDevice, (cudaStream_t)a->stream) != cudaSuccess)
             return BACON_E_CUDA;
     } else if (a->cfg.semantics != BACON_SEM_CORRECTED) {
         return BACON_E_UNSUPPORTED;

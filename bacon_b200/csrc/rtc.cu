@@ -116,7 +116,7 @@ const char* tab_name(int method) { return (method == BACON_RK45) ? "bacon::TabRK
 // what launch.cuh would instantiate for this call: stepper type, CTA size, resident CTAs per SM the kernel is compiled
 // for, and the exchange buffer of the end-of-ensemble regrouping (drive.cuh)
 struct Plan { std::string stepper; int minb; int block; size_t smem; int state_doubles; };
-int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist, bool fit, Plan* p) {
+int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist, bool fit, bool event, Plan* p) {
     const std::string T = r.type_name;
     const bool newton = (c.flags & BACON_FLAG_BDF_NEWTON) != 0;
     p->state_doubles = 0;
@@ -137,7 +137,7 @@ int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
         }
         case BACON_BDF6:
         case BACON_BDF2: {
-            if (c.semantics != BACON_SEM_CORRECTED) return BACON_E_UNSUPPORTED;
+            if (c.semantics != BACON_SEM_CORRECTED && !(strict && !newton)) return BACON_E_UNSUPPORTED;  // launch_bdf
             if (newton && strict) return BACON_E_UNSUPPORTED;
             const char* coef = c.method == BACON_BDF6 ? "bacon::CoefBDF6" : "bacon::CoefBDF2";
             p->stepper = "bacon::BdfStepper<" + T + ", " + coef + ", " + (strict ? "true" : "false") + ", " +
@@ -159,11 +159,12 @@ int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
             return BACON_E_BAD_ARGUMENT;
     }
     if (hist && p->minb >= 6) p->minb -= 1;  // MINB_HIST (launch.cuh)
-    if (fit && !hist && p->state_doubles > 0 && p->minb >= 6 && p->minb < 8) p->minb += 1;  // fits_one_more_warp (launch.cuh)
+    if (fit && !hist && !event && p->state_doubles > 0 && p->minb >= 6 && p->minb < 8) p->minb += 1;  // fits_one_more_warp (launch.cuh)
     // launch_stepper_hist (launch.cuh): steppers that suspend run as one wide CTA per SM when its exchange buffer fits
+    // (terminal-event kernels never do)
     p->block = 128;
     p->smem = 0;
-    if (p->state_doubles > 0) {
+    if (p->state_doubles > 0 && !event) {
         const int wide = 128 * p->minb;
         if (wide >= 256 && (size_t)(p->state_doubles + 1) * 8 * wide <= 160 * 1024) {  // StepperMigrates (drive.cuh)
             p->block = wide;
@@ -174,10 +175,10 @@ int make_plan(const RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
     return 0;
 }
 
-int compile_program(RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist, bool fit, int cc_major, int cc_minor, Compiled* out) {
+int compile_program(RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist, bool fit, bool event, int cc_major, int cc_minor, Compiled* out) {
     Api& A = api();
     Plan plan;
-    if (const int rc = make_plan(r, c, strict, hist, fit, &plan))
+    if (const int rc = make_plan(r, c, strict, hist, fit, event, &plan))
         return rtc_fail(rc, "rhs '%s': method %d / semantics %d / flags 0x%x has no %s kernel", r.name.c_str(), c.method,
                         c.semantics, c.flags, strict ? "strict" : "fast");
     std::string src = "#include \"drive.cuh\"\n#include \"rk_fast.cuh\"\n#include \"rk_strict.cuh\"\n#include \"adams.cuh\"\n";
@@ -185,8 +186,9 @@ int compile_program(RtcRhs& r, const bacon_ivp_config& c, bool strict, bool hist
     src += "static_assert(" + r.type_name + "::DIM == " + std::to_string(r.dim) + " && " + r.type_name +
            "::NPARAM == " + std::to_string(r.n_params) + ", \"DIM / NPARAM of the functor differ from the registration\");\n";
     const std::string h = hist ? "true" : "false", m = std::to_string(plan.minb);
-    const std::string k_main = "&bacon::ensemble_kernel<" + plan.stepper + ", " + h + ", " + std::to_string(plan.block) + ", " + m + ">";
-    const std::string k_tab = "&bacon::c_rk_tab";
+    const std::string k_main = "&bacon::ensemble_kernel<" + plan.stepper + ", " + h + ", " + std::to_string(plan.block) + ", " + m +
+                               (event ? ", true>" : ", false>");
+    const std::string k_tab = "&bacon::c_rk_tabs";
     const bool want_tab = strict && (c.method == BACON_RK45 || c.method == BACON_RK23);
 
     std::vector<const char*> hdr_text, hdr_name;
@@ -260,6 +262,7 @@ int rtc_launch(int slot, bacon_launch_args* a) {
     const bacon_ivp_config& c = a->cfg;
     const bool strict = (c.flags & BACON_FLAG_STRICT_FP) || c.semantics == BACON_SEM_LITERAL;
     const bool hist = c.history_capacity > 0 && a->out.hist;
+    const bool event = a->ev_on != 0 || a->t0_each || a->dt0_each || c.dt_init > 0.0;  // the kernels compiled for the optional inputs
     int dev = 0;
     cudaGetDevice(&dev);
     if (!A.drv_ok) return rtc_fail(BACON_E_UNSUPPORTED, "rhs '%s' cannot be launched: %s", r->name.c_str(), A.why.c_str());
@@ -269,22 +272,22 @@ int rtc_launch(int slot, bacon_launch_args* a) {
         const int newton = (c.flags & BACON_FLAG_BDF_NEWTON) ? 1 : 0;
         // the window of sizes served by the kernel compiled for one more warp per sub-partition (fits_one_more_warp, launch.cuh)
         bool fit = false;
-        if (!strict && !hist && (c.method == BACON_RK45 || c.method == BACON_RK23) && a->grid_override <= 0 && !getenv("BACON_IVP_NO_FIT")) {
+        if (!strict && !hist && !event && (c.method == BACON_RK45 || c.method == BACON_RK23) && a->grid_override <= 0 && !getenv("BACON_IVP_NO_FIT")) {
             Plan base;
-            if (make_plan(*r, c, strict, hist, false, &base) == 0 && base.block >= 768 && base.block + 128 <= 1024 &&
+            if (make_plan(*r, c, strict, hist, false, false, &base) == 0 && base.block >= 768 && base.block + 128 <= 1024 &&
                 (size_t)(base.state_doubles + 1) * 8 * (base.block + 128) <= 160 * 1024)
                 fit = a->n > (unsigned long long)a->sm_count * base.block && a->n <= (unsigned long long)a->sm_count * (base.block + 128);
         }
-        const std::vector<int> key = {dev, (int)c.method, strict ? 1 : 0, newton, hist ? 1 : 0, fit ? 1 : 0};
+        const std::vector<int> key = {dev, (int)c.method, strict ? 1 : 0, newton, hist ? 1 : 0, fit ? 1 : 0, event ? 1 : 0};
         auto it = r->variants.find(key);
         if (it == r->variants.end()) {
             cudaDeviceProp prop;
             if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return BACON_E_CUDA;
-            const std::vector<int> pkey = {prop.major * 10 + prop.minor, (int)c.method, strict ? 1 : 0, newton, hist ? 1 : 0, fit ? 1 : 0};
+            const std::vector<int> pkey = {prop.major * 10 + prop.minor, (int)c.method, strict ? 1 : 0, newton, hist ? 1 : 0, fit ? 1 : 0, event ? 1 : 0};
             auto pit = r->programs.find(pkey);
             if (pit == r->programs.end()) {
                 Compiled cp;
-                if (const int rc = compile_program(*r, c, strict, hist, fit, prop.major, prop.minor, &cp)) return rc;
+                if (const int rc = compile_program(*r, c, strict, hist, fit, event, prop.major, prop.minor, &cp)) return rc;
                 pit = r->programs.emplace(pkey, std::move(cp)).first;
             }
             Variant nv;
@@ -321,7 +324,8 @@ int rtc_launch(int slot, bacon_launch_args* a) {
         if (c.method == BACON_RK45) bacon::fill_runtime_tableau<bacon::TabRKF45>(T, c.semantics == BACON_SEM_LITERAL);
         else bacon::fill_runtime_tableau<bacon::TabBS23>(T, c.semantics == BACON_SEM_LITERAL);
         // (pageable source: the driver stages the bytes before it returns)
-        if (A.cuMemcpyHtoDAsync_v2(v.tableau, &T, sizeof(T), st) != CUDA_SUCCESS) return BACON_E_CUDA;
+        const size_t slot = (size_t)bacon::rk_tab_slot(c.method == BACON_RK45 ? 6 : 4, c.semantics);
+        if (A.cuMemcpyHtoDAsync_v2(v.tableau + slot * sizeof(T), &T, sizeof(T), st) != CUDA_SUCCESS) return BACON_E_CUDA;
     }
     bacon_launch_args args = *a;
     void* p_main[] = {&args};
@@ -477,12 +481,12 @@ extern "C" int bacon_rhs_register_source(const char* name, const char* type_name
         RtcRhs& r = *g_rtc[slot];
         std::lock_guard<std::mutex> lk(r.mu);
         Compiled cp;
-        if (const int rc = compile_program(r, c, false, false, false, major, minor, &cp)) {
+        if (const int rc = compile_program(r, c, false, false, false, false, major, minor, &cp)) {
             std::lock_guard<std::mutex> lk2(g_mu);
             if ((int)g_rtc.size() == slot + 1) g_rtc.back()->source.clear();  // (the slot stays: trampolines are positional)
             return -rc;
         }
-        r.programs.emplace(std::vector<int>{major * 10 + minor, (int)BACON_RK45, 0, 0, 0}, std::move(cp));
+        r.programs.emplace(std::vector<int>{major * 10 + minor, (int)BACON_RK45, 0, 0, 0, 0, 0}, std::move(cp));
         // the path-query program is compiled at the first query; BACON_RTC_EAGER_PATHS=1 compiles it here as well (both
         // flavours), which is how the CPU test suite checks that path_query.cuh goes through NVRTC
         if (getenv("BACON_RTC_EAGER_PATHS")) {
@@ -498,7 +502,7 @@ extern "C" int bacon_rhs_register_source(const char* name, const char* type_name
     d.dim = dim;
     d.n_params = n_params;
     for (int s = 0; s < 2; ++s)
-        for (int m = 0; m < BACON_N_METHODS; ++m) d.launch[s][m] = tramps[slot];
+        for (int m = 0; m < BACON_N_METHODS; ++m) d.launch[s][m] = d.launch_event[s][m] = tramps[slot];  // (rtc_launch reads a->ev_on)
     d.path_query[0] = d.path_query[1] = path_tramps[slot];
     return bacon_rhs_register(&d);
 }

@@ -113,6 +113,11 @@ struct RkTableauRt {
     double safety;
 };
 
+// which of the strict kernels' four constant tableaux (rk_strict.cuh: c_rk_tabs) a (method, semantics) pair uses
+__host__ __device__ inline int rk_tab_slot(int order, int semantics) {
+    return (order == 6 ? 0 : 2) + (semantics == BACON_SEM_LITERAL ? 1 : 0);
+}
+
 template <class Tab> inline void fill_runtime_tableau(RkTableauRt& T, bool literal) {
     constexpr int O = Tab::O;
     for (int i = 0; i < 6; ++i) {

@@ -110,10 +110,18 @@ class EnsembleResult:
     def _solved(self):
         if self.hist is None or self._query is None:
             raise IVPError(_abi.E_BAD_ARGUMENT, "path queries need a dense-output solve (with_history(capacity))")
-        cfg, rid, y0, params = self._query
+        cfg, rid, y0, params = self._query[:4]
         res = _abi.Result(hist=self.hist.ctypes.data, hist_len=self.hist_len.ctypes.data,
-                          t_end=self.t_end.ctypes.data, y_end=self.y_end.ctypes.data)
+                          t_end=self.t_end.ctypes.data, y_end=self.y_end.ctypes.data,
+                          n_accept=self.n_accept.ctypes.data, status=self.status.ctypes.data)
+        if len(self._query) > 4 and self._query[4] is not None:  # a resumed leg: per-trajectory start times
+            res.t_start = self._query[4].ctypes.data
         return cfg, rid, y0, (None if params is None else params.ctypes.data), res
+
+    def restart_record(self):
+        """(y_end, t_end, dt_end): what `solve_ivp_ensemble(..., restart=...)` takes to go on where this solve stopped —
+        the C-ABI form of the reference's in-memory resumable iterator (src/ivp.rs:220-238)."""
+        return self.y_end, self.t_end, self.dt_end
 
     def sample(self, times):
         """The state of every trajectory at `times`: (n, len(times), dim); NaN where a time lies outside a
@@ -147,13 +155,21 @@ class _Solver:
     METHOD = None
     _ORDER = None
 
-    def __init__(self, dim):
-        self._h = lib().bacon_solver_new(self.METHOD, int(dim))
-        if not self._h:
-            raise IVPError(_abi.E_BAD_ARGUMENT, last_error())
-        self._dim = int(dim)
+    def __init__(self, dim, *, dyn=False, dim_type=None):
+        """`dim_type` is the reference's type parameter D: a static dimension C >= 1 (`Const<C>`) or `DYN` (`Dyn`).
+        new(dim) builds Const<dim>; new_dyn(size) builds Dyn with `size`; the mixed-up calls fail like the
+        reference's `Dimension` (src/lib.rs:53-76): see new / new_dyn."""
+        h = C.c_void_p()
+        if dyn:
+            _check(lib().bacon_solver_new_dyn(self.METHOD, _abi.DIM_DYN if dim_type is None else int(dim_type), int(dim),
+                                              C.byref(h)))
+        else:
+            _check(lib().bacon_solver_new_static(self.METHOD, int(dim) if dim_type is None else int(dim_type), C.byref(h)))
+        self._h = h.value
+        self._dim = int(dim) if (dyn or dim_type is None) else int(dim_type)
         self._y0 = None
         self._rhs = None
+        self._event = None
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -163,15 +179,18 @@ class _Solver:
             except Exception:
                 pass
 
-    # ---- IVPSolver::new / new_dyn (ivp.rs:159-163).  Python has no static dimensions:
-    # `new(dim)` == `new_dyn(dim)`.
-    @classmethod
-    def new(cls, dim=1):
-        return cls(dim)
+    # ---- IVPSolver::new / new_dyn (ivp.rs:159-163) with the reference's Dimension check (lib.rs:53-76).  Python has
+    # no type parameters, so the solver's `D` is an argument: new(3) is `RK45::<U3>::new()`, new_dyn(3) is
+    # `RK45::<Dyn>::new_dyn(3)`; new(dim_type=DYN) raises StaticOnDynamic and new_dyn(3, dim_type=3) DynamicOnStatic.
+    DYN = _abi.DIM_DYN
 
     @classmethod
-    def new_dyn(cls, size):
-        return cls(size)
+    def new(cls, dim=1, *, dim_type=None):
+        return cls(dim, dim_type=dim_type)
+
+    @classmethod
+    def new_dyn(cls, size, *, dim_type=None):
+        return cls(size, dyn=True, dim_type=dim_type)
 
     def dim(self):
         return self._dim
@@ -241,6 +260,47 @@ class _Solver:
         _check(lib().bacon_solver_with_max_attempts(self._h, int(cap)))
         return self
 
+    def with_initial_dt(self, dt):
+        """First step size instead of the reference's (dt_max + dt_min)/2 (rk.rs:315); clamped into [dt_min, dt_max]."""
+        _check(lib().bacon_solver_with_initial_dt(self._h, float(dt)))
+        return self
+
+    def with_terminal_event(self, w, c=0.0, direction=0):
+        """Stop every trajectory at the first zero of g(y) = w . y - c (direction +1 rising, -1 falling, 0 both): status
+        STOPPED_AT_EVENT, t_end / y_end = the event point.  `None` removes it.  Not in the reference."""
+        if w is None:
+            self._event = None
+            return self
+        w = np.ascontiguousarray(w, dtype=np.float64).reshape(-1)
+        if w.size != self._dim:
+            raise IVPError(_abi.E_BAD_ARGUMENT, f"w must have {self._dim} entries")
+        if int(direction) not in (-1, 0, 1):
+            raise IVPError(_abi.E_BAD_ARGUMENT, "direction must be -1, 0 or +1")
+        self._event = (w, float(c), int(direction))
+        return self
+
+    def _options(self, n, restart, keep):
+        """bacon_ivp_options for this call (host arrays) or None.  restart = (t_start_each, dt_start_each), either may
+        be None."""
+        if self._event is None and restart is None:
+            return None
+        o = _abi.Options()
+        if self._event is not None:
+            o.event_w = self._event[0].ctypes.data
+            o.event_c = self._event[1]
+            o.event_direction = self._event[2]
+        if restart is not None:
+            t0, dt0 = restart
+            for name, arr in (("t_start_each", t0), ("dt_start_each", dt0)):
+                if arr is None:
+                    continue
+                arr = np.ascontiguousarray(arr, dtype=np.float64)
+                if arr.shape != (n,):
+                    raise IVPError(_abi.E_BAD_ARGUMENT, f"restart {name} must have shape ({n},)")
+                keep.append(arr)
+                setattr(o, name, arr.ctypes.data)
+        return o
+
     # ---- config
     def _config(self, n_params, extra_flags=0):
         cfg = _abi.Config()
@@ -268,14 +328,20 @@ class _Solver:
         if self._y0 is None:
             raise IVPError(_abi.E_MISSING_PARAMETERS, "with_initial_conditions was not called")
         params = None if data is None else np.asarray(data, dtype=np.float64).reshape(-1, 1)
-        self.with_history(capacity)
-        try:
-            res = self.solve_ivp_ensemble(self._y0.reshape(self._dim, 1), params)
-        finally:
-            self.with_history(0)
+        # collect_vec grows its Vec (ivp.rs:209-211); here the path's storage is sized up front, so a path longer
+        # than `capacity` is integrated once more with the capacity it reported (n_accept)
+        for _ in range(2):
+            self.with_history(capacity)
+            try:
+                res = self.solve_ivp_ensemble(self._y0.reshape(self._dim, 1), params)
+            finally:
+                self.with_history(0)
+            if int(res.n_accept[0]) <= capacity:
+                break
+            capacity = int(res.n_accept[0])
         path = res.path(0)
         st = int(res.status[0])
-        if st != _abi.OK:
+        if st not in (_abi.OK, _abi.STOPPED_AT_EVENT):
             err = IVPError(st, "trajectory 0")
             err.path = path
             err.result = res
@@ -287,14 +353,16 @@ class _Solver:
 
     # ---- the new entry point: N initial conditions x N parameter sets
     def solve_ivp_ensemble(self, y0, params=None, *, n_gpus=1, shared_params=False, params_aos=False, rhs=None,
-                           zero_copy=True):
+                           zero_copy=True, restart=None):
         """y0: (dim, n) float64 host array; params: (n_params, n), or (n, ...) = one contiguous block
         per trajectory with params_aos=True, or (n_params,) with shared_params=True.
         Host buffers in, host buffers out (H2D, kernel, D2H).  The result arrays live in page-locked memory
         from the library (`bacon_host_alloc`), so the D2H leg is an asynchronous DMA; inputs made with
         `pinned_empty` get the same treatment.  zero_copy (default; applies on 1 GPU, final state only, when
         every buffer is pinned and the per-trajectory input is small): the kernel reads and writes the host
-        buffers itself, no staging copies; otherwise the staged path runs."""
+        buffers itself, no staging copies; otherwise the staged path runs.
+        restart = (t_start_each, dt_start_each): per-trajectory start time and first dt, e.g. the (t_end, dt_end) a
+        previous solve returned together with its y_end as y0 (EnsembleResult.restart_record)."""
         if rhs is not None:
             self.with_derivative(rhs)
         rid, dim, npar = self._rhs_info()
@@ -343,12 +411,18 @@ class _Solver:
             if cap > 0:
                 arrays["hist_len"].fill(0)
         res = _abi.Result(**{k: v.ctypes.data for k, v in arrays.items()})
-        if n_gpus == 1:
+        keep = []
+        opts = self._options(n, restart, keep)
+        if opts is not None:
+            _check(L.bacon_ivp_solve_ensemble_ex(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(opts), C.byref(res),
+                                                 int(n_gpus)))
+        elif n_gpus == 1:
             _check(L.bacon_ivp_solve_ensemble(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res)))
         else:
             _check(L.bacon_ivp_solve_ensemble_multi(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res), int(n_gpus)))
         out = EnsembleResult(arrays, last_launch())
-        out._query = (cfg, rid, y0, params if npar > 0 else None)
+        t0_each = None if restart is None or restart[0] is None else np.ascontiguousarray(restart[0], dtype=np.float64)
+        out._query = (cfg, rid, y0, params if npar > 0 else None, t0_each)
         return out
 
     # ---- queries on paths resident in HBM (torch CUDA tensors; `out` = what solve_ivp_ensemble_device returned,
@@ -360,7 +434,10 @@ class _Solver:
         if cfg.history_capacity <= 0 or "hist" not in out:
             raise IVPError(_abi.E_BAD_ARGUMENT, "path queries need a dense-output solve (with_history(capacity))")
         res = _abi.Result(hist=out["hist"].data_ptr(), hist_len=out["hist_len"].data_ptr(),
-                          t_end=out["t_end"].data_ptr(), y_end=out["y_end"].data_ptr())
+                          t_end=out["t_end"].data_ptr(), y_end=out["y_end"].data_ptr(),
+                          n_accept=out["n_accept"].data_ptr(), status=out["status"].data_ptr())
+        if out.get("t_start") is not None:  # a resumed leg
+            res.t_start = out["t_start"].data_ptr()
         return cfg, rid, dim, (params.data_ptr() if npar > 0 else None), res
 
     def sample_paths_device(self, y0, params, out, times, *, shared_params=False, params_aos=False, samples=None,
@@ -395,7 +472,7 @@ class _Solver:
 
     # ---- device-resident variant: torch CUDA tensors in, torch CUDA tensors out, no copies
     def solve_ivp_ensemble_device(self, y0, params=None, *, shared_params=False, params_aos=False, out=None,
-                                  stream=None, rhs=None):
+                                  stream=None, rhs=None, restart=None):
         import torch
         if rhs is not None:
             self.with_derivative(rhs)
@@ -437,10 +514,28 @@ class _Solver:
         if cap > 0:  # views of the record array
             out["hist_t"] = out["hist"][:, :, 0]
             out["hist_y"] = out["hist"][:, :, 1:]
+        opts = None
+        if self._event is not None or restart is not None:  # restart = (t_start_each, dt_start_each) CUDA tensors
+            opts = self._options(n, None, [])
+            if opts is None:
+                opts = _abi.Options()
+            if restart is not None:
+                for name, ten in (("t_start_each", restart[0]), ("dt_start_each", restart[1])):
+                    if ten is None:
+                        continue
+                    if not (ten.is_cuda and ten.dtype == torch.float64 and ten.is_contiguous() and ten.numel() == n):
+                        raise IVPError(_abi.E_BAD_ARGUMENT, f"restart {name} must be a contiguous CUDA float64 tensor of {n}")
+                    setattr(opts, name, ten.data_ptr())
+                if restart[0] is not None:
+                    out["t_start"] = restart[0]
         with torch.cuda.device(dev):
             s = torch.cuda.current_stream(dev) if stream is None else stream
-            _check(lib().bacon_ivp_solve_ensemble_device(C.byref(cfg), rid, n, y0.data_ptr(), pptr, C.byref(res),
-                                                         C.c_void_p(s.cuda_stream)))
+            if opts is not None:
+                _check(lib().bacon_ivp_solve_ensemble_device_ex(C.byref(cfg), rid, n, y0.data_ptr(), pptr, C.byref(opts),
+                                                                C.byref(res), C.c_void_p(s.cuda_stream)))
+            else:
+                _check(lib().bacon_ivp_solve_ensemble_device(C.byref(cfg), rid, n, y0.data_ptr(), pptr, C.byref(res),
+                                                             C.c_void_p(s.cuda_stream)))
         return out
 
 

@@ -31,7 +31,7 @@ typedef unsigned long size_t;
 extern "C" {
 #endif
 
-#define BACON_IVP_ABI_VERSION 5
+#define BACON_IVP_ABI_VERSION 6
 
 /* ---- solver families: src/ivp/rk.rs:561 (RungeKutta45), rk.rs:656
  * (RungeKutta23), src/ivp/bdf.rs:706 (BDF6), bdf.rs:762 (BDF2),
@@ -69,7 +69,9 @@ typedef enum bacon_status {
     BACON_E_HISTORY_OVERFLOW = 15,   /* more accepted points than history_capacity */
     BACON_E_CUDA = 16,               /* CUDA runtime error; see bacon_last_error() */
     BACON_E_BAD_ARGUMENT = 17,       /* NULL pointer, unknown rhs/method, dim mismatch */
-    BACON_E_UNSUPPORTED = 18         /* combination not built (e.g. BDF literal on device) */
+    BACON_E_UNSUPPORTED = 18,        /* combination not built (e.g. terminal events for linear32) */
+    BACON_STOPPED_AT_EVENT = 19      /* per-trajectory, not an error: the integration stopped at a terminal event
+                                        (bacon_ivp_options::event_w); t_end / y_end are the event point */
 } bacon_status;
 
 /* ---- semantics: SURVEY.md §8c.  REF_LITERAL reproduces the source as
@@ -101,6 +103,8 @@ typedef struct bacon_ivp_config {
     double tol;               /* with_tolerance                      (ivp.rs:169)        */
     double t_start, t_end;    /* with_initial_time / with_ending_time (ivp.rs:173-174)   */
     uint64_t max_attempts;    /* per-trajectory cap on step() calls; 0 = 2^32-2          */
+    double dt_init;           /* first step size; 0 = the reference's (dt_max + dt_min)/2 (rk.rs:315,
+                                 bdf.rs:302, adams.rs:297); > 0: bacon_solver_with_initial_dt.  Unused by Euler */
 } bacon_ivp_config;
 
 /* Output block.  Any pointer may be NULL (that output is skipped) except
@@ -123,7 +127,30 @@ typedef struct bacon_ivp_result {
     uint32_t* n_rhs;     /* [n] derivative evaluations                                          */
     double* hist;        /* [n][cap][1 + dim], required when history_capacity > 0               */
     uint32_t* hist_len;  /* [n] records written (<= history_capacity)                           */
+    const double* t_start; /* INPUT of the path queries only: [n] per-trajectory start times when the solve was
+                              given bacon_ivp_options::t_start_each (knot 0 of every path); NULL = cfg.t_start */
 } bacon_ivp_result;
+
+/* Optional inputs of a solve (the *_ex entry points); all-zero = the plain solve.
+ *  - restart record: the reference's iterator is resumable in memory (`IVPIterator` keeps the solver, ivp.rs:220-238;
+ *    a caller can stop pulling points and go on later).  Across the C ABI the same thing is the per-trajectory record
+ *    (t_end, y_end, dt_end) a solve returns: pass y_end as y0, t_end as t_start_each and dt_end as dt_start_each and the
+ *    integration goes on where it stopped.  dt is clamped into [dt_min, dt_max] (a finished leg's last, shortened step
+ *    can leave dt_end below dt_min).  Exact for the one-step methods (RK: the stepper's whole state is (t, y, dt));
+ *    the multistep methods (BDF, Adams) restart with their RK4 warm-up, as after any change of dt.
+ *  - terminal event: stop a trajectory where g(y) = w . y - c changes sign between two yielded points (direction +1:
+ *    rising only, -1: falling only, 0: both; a right end exactly on the surface counts, a left end does not).  The crossing
+ *    is located on the cubic Hermite interpolant of that step exactly like bacon_ivp_locate_events; the trajectory ends
+ *    there with status BACON_STOPPED_AT_EVENT, t_end = t*, y_end = y(t*); the step that crossed is not yielded (n_accept
+ *    and the history count the points before it).  NOT in the reference. */
+typedef struct bacon_ivp_options {
+    const double* t_start_each;  /* [n] per-trajectory initial time; NULL = cfg.t_start (host or device as y0)   */
+    const double* dt_start_each; /* [n] per-trajectory first dt; NULL = cfg.dt_init / the reference's default    */
+    const double* event_w;       /* HOST array of dim doubles (both variants); NULL = no terminal event          */
+    double event_c;
+    int32_t event_direction;
+    int32_t reserved;
+} bacon_ivp_options;
 
 /* Launch record filled by the last solve on this thread (timing + totals). */
 typedef struct bacon_ivp_launch_info {
@@ -143,12 +170,25 @@ int bacon_abi_version(void);
 /* IVPSolver::new / new_dyn (ivp.rs:159-163).  Static dimensions are the ones
  * a RHS was compiled for; `dim` is checked against the RHS at solve time. */
 bacon_solver* bacon_solver_new(int method, int dim);
+/* The reference's two constructors with their `Dimension` check (src/lib.rs:53-76, ivp.rs:159-163, rk.rs:136-166):
+ * the solver's type parameter D is either `Const<C>` (dim_type = C >= 1) or `Dyn` (dim_type = BACON_DIM_DYN).
+ *   new()          = bacon_solver_new_static(method, dim_type):   Const<C> -> dimension C;  Dyn -> StaticOnDynamic (12)
+ *   new_dyn(size)  = bacon_solver_new_dyn(method, dim_type, size): Dyn -> dimension `size`;  Const<C> -> DynamicOnStatic (11)
+ * On success *out is the handle (free with bacon_solver_free) and the return code is 0.  Either way the dimension is
+ * checked against the right-hand side's DIM when a solve is called (nalgebra would panic at ivp.rs:178). */
+#define BACON_DIM_DYN 0
+int bacon_solver_new_static(int method, int dim_type, bacon_solver** out);
+int bacon_solver_new_dyn(int method, int dim_type, int size, bacon_solver** out);
 void bacon_solver_free(bacon_solver*);
 int bacon_solver_with_tolerance(bacon_solver*, double tol);            /* rk.rs:168-174 */
 int bacon_solver_with_maximum_dt(bacon_solver*, double max);           /* rk.rs:179-192 */
 int bacon_solver_with_minimum_dt(bacon_solver*, double min);           /* rk.rs:197-210 */
 int bacon_solver_with_initial_time(bacon_solver*, double initial);     /* rk.rs:212-222 */
 int bacon_solver_with_ending_time(bacon_solver*, double ending);       /* rk.rs:224-234 */
+/* Not in the reference (its first dt is always (dt_max + dt_min)/2, rk.rs:315): the first step size, so that a
+ * restart record's dt can be handed back (see bacon_ivp_options).  TimeDeltaOOB unless dt > 0; a value outside
+ * [dt_min, dt_max] is clamped at solve time. */
+int bacon_solver_with_initial_dt(bacon_solver*, double dt);
 int bacon_solver_with_semantics(bacon_solver*, int semantics);
 int bacon_solver_with_flags(bacon_solver*, uint32_t flags);
 int bacon_solver_with_history(bacon_solver*, int capacity);
@@ -179,6 +219,8 @@ typedef struct bacon_rhs_desc {
     bacon_launch_fn launch[2][BACON_N_METHODS];
     /* [strict_fp 0/1]: the path queries below (sampling, events) for this RHS; NULL = not built */
     bacon_path_fn path_query[2];
+    /* the same kernels compiled with the terminal-event test (bacon_ivp_options::event_w); NULL = not built */
+    bacon_launch_fn launch_event[2][BACON_N_METHODS];
 } bacon_rhs_desc;
 
 int bacon_rhs_register(const bacon_rhs_desc*); /* returns rhs id >= 0, or -bacon_status */
@@ -214,6 +256,14 @@ int bacon_ivp_solve_ensemble_device(const bacon_ivp_config*, int rhs_id, size_t 
  * n_gpus visible devices of this process (one stream per device). */
 int bacon_ivp_solve_ensemble_multi(const bacon_ivp_config*, int rhs_id, size_t n, const double* y0,
                                    const double* params, const bacon_ivp_result* out, int n_gpus);
+
+/* The same three solves with optional inputs (restart record, terminal event): see bacon_ivp_options.  NULL options =
+ * the plain call.  n_gpus as in bacon_ivp_solve_ensemble_multi (1 = the current device). */
+int bacon_ivp_solve_ensemble_ex(const bacon_ivp_config*, int rhs_id, size_t n, const double* y0, const double* params,
+                                const bacon_ivp_options* options, const bacon_ivp_result* out, int n_gpus);
+int bacon_ivp_solve_ensemble_device_ex(const bacon_ivp_config*, int rhs_id, size_t n, const double* d_y0,
+                                       const double* d_params, const bacon_ivp_options* options,
+                                       const bacon_ivp_result* d_out, void* stream);
 
 /* ---- queries on stored paths: the continuous extension.
  * NOT in the reference — its `Path` is the accepted points and nothing between them (src/ivp.rs:203-211); this is the

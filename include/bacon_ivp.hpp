@@ -40,7 +40,7 @@ struct EnsembleResult {
     // what the path queries below need of the solve (kept by solve_ivp_ensemble)
     bacon_ivp_config cfg{};
     int rhs = -1;
-    std::vector<double> y0, params;
+    std::vector<double> y0, params, t_start;
     double y(size_t i, int d) const { return y_end[(size_t)d * n + i]; }
     Path path(size_t i) const {
         Path p;
@@ -59,6 +59,9 @@ struct EnsembleResult {
         o.hist_len = const_cast<uint32_t*>(hist_len.data());
         o.t_end = const_cast<double*>(t_end.data());
         o.y_end = const_cast<double*>(y_end.data());
+        o.n_accept = const_cast<uint32_t*>(n_accept.data());  // a path cut short by its capacity has no closing knot
+        o.status = const_cast<int32_t*>(status.data());
+        if (!t_start.empty()) o.t_start = t_start.data();     // a resumed leg: per-trajectory start times
         return o;
     }
     // the state of every trajectory at `times`: [n][times.size()][dim], NaN outside a trajectory's path
@@ -84,22 +87,54 @@ struct EnsembleResult {
     }
 };
 
-template <int METHOD> class Solver {
-    bacon_solver* h_;
-    int dim_;
+// The restart record of a solve (t_end, dt_end per trajectory; y_end is the next leg's y0): the C-ABI form of the
+// reference's in-memory resumable iterator (src/ivp.rs:220-238).  Either pointer may be null.
+struct Restart {
+    const double* t_start_each = nullptr;
+    const double* dt_start_each = nullptr;
+};
+
+constexpr int Dyn = BACON_DIM_DYN;  // the `Dyn` type parameter (src/lib.rs:68)
+
+// D is the reference's type parameter: a static dimension C >= 1 (`Const<C>`, e.g. RungeKutta45<3>) or Dyn.
+template <int METHOD, int D = Dyn> class Solver {
+    bacon_solver* h_ = nullptr;
+    int dim_ = 0;
     int rhs_ = -1;
     std::vector<double> y0_;
+    std::vector<double> ev_w_;
+    double ev_c_ = 0.0;
+    int ev_dir_ = 0;
+
+    Solver() = default;
 
   public:
+    // (round-1 form: a run-time dimension, no Dimension check; the same as `Solver<M, Dyn>::new_dyn(dim)`)
     explicit Solver(int dim) : h_(bacon_solver_new(METHOD, dim)), dim_(dim) {
         if (!h_) throw IVPError(BACON_E_BAD_ARGUMENT, bacon_last_error());
     }
     ~Solver() { bacon_solver_free(h_); }
     Solver(const Solver&) = delete;
     Solver& operator=(const Solver&) = delete;
-    Solver(Solver&& o) noexcept : h_(o.h_), dim_(o.dim_), rhs_(o.rhs_), y0_(std::move(o.y0_)) { o.h_ = nullptr; }
+    Solver(Solver&& o) noexcept
+        : h_(o.h_), dim_(o.dim_), rhs_(o.rhs_), y0_(std::move(o.y0_)), ev_w_(std::move(o.ev_w_)), ev_c_(o.ev_c_), ev_dir_(o.ev_dir_) {
+        o.h_ = nullptr;
+    }
 
-    static Solver new_dyn(int size) { return Solver(size); }  // ivp.rs:163
+    // IVPSolver::new (ivp.rs:159): Const<C> -> a solver of dimension C; Dyn -> throws StaticOnDynamic (lib.rs:69-71)
+    static Solver make() {
+        Solver s;
+        check(bacon_solver_new_static(METHOD, D, &s.h_));
+        s.dim_ = D;
+        return s;
+    }
+    // IVPSolver::new_dyn (ivp.rs:163): Dyn -> a solver of dimension `size`; Const<C> -> throws DynamicOnStatic (lib.rs:63-65)
+    static Solver new_dyn(int size) {
+        Solver s;
+        check(bacon_solver_new_dyn(METHOD, D, size, &s.h_));
+        s.dim_ = size;
+        return s;
+    }
     int dim() const { return dim_; }
 
     Solver& with_tolerance(double tol) { check(bacon_solver_with_tolerance(h_, tol)); return *this; }          // rk.rs:168
@@ -138,6 +173,17 @@ template <int METHOD> class Solver {
     Solver& with_flags(uint32_t f) { check(bacon_solver_with_flags(h_, f)); return *this; }
     Solver& with_history(int cap) { check(bacon_solver_with_history(h_, cap)); return *this; }
     Solver& with_max_attempts(uint64_t cap) { check(bacon_solver_with_max_attempts(h_, cap)); return *this; }
+    // first step size instead of (dt_max + dt_min)/2 (rk.rs:315); clamped into [dt_min, dt_max] at solve time
+    Solver& with_initial_dt(double dt) { check(bacon_solver_with_initial_dt(h_, dt)); return *this; }
+    // stop every trajectory at the first zero of w . y - c (direction +1 rising, -1 falling, 0 both): status
+    // BACON_STOPPED_AT_EVENT, t_end / y_end = the event point.  An empty w removes it.  Not in the reference.
+    Solver& with_terminal_event(const std::vector<double>& w, double c = 0.0, int direction = 0) {
+        if (!w.empty() && (int)w.size() != dim_) throw IVPError(BACON_E_BAD_ARGUMENT, "w must have dim() entries");
+        ev_w_ = w;
+        ev_c_ = c;
+        ev_dir_ = direction;
+        return *this;
+    }
 
     bacon_ivp_config config() const {
         bacon_ivp_config c;
@@ -147,7 +193,7 @@ template <int METHOD> class Solver {
 
     // N initial conditions x N parameter sets.  y0: [dim][n]; params: [n_params][n] (or [n_params] shared).
     EnsembleResult solve_ivp_ensemble(size_t n, const double* y0, const double* params, bool shared_params = false,
-                                      int n_gpus = 1) const {
+                                      int n_gpus = 1, Restart restart = {}) const {
         if (rhs_ < 0) throw IVPError(BACON_E_MISSING_PARAMETERS, "with_derivative was not called");
         bacon_ivp_config c = config();
         int d = 0, np = 0;
@@ -179,8 +225,17 @@ template <int METHOD> class Solver {
             o.hist = r.hist.data();
             o.hist_len = r.hist_len.data();
         }
-        check(bacon_ivp_solve_ensemble_multi(&c, rhs_, n, y0, params, &o, n_gpus));
+        bacon_ivp_options opt{};
+        opt.t_start_each = restart.t_start_each;
+        opt.dt_start_each = restart.dt_start_each;
+        if (!ev_w_.empty()) {
+            opt.event_w = ev_w_.data();
+            opt.event_c = ev_c_;
+            opt.event_direction = ev_dir_;
+        }
+        check(bacon_ivp_solve_ensemble_ex(&c, rhs_, n, y0, params, &opt, &o, n_gpus));
         check(bacon_ivp_last_launch(&r.launch));
+        if (restart.t_start_each) r.t_start.assign(restart.t_start_each, restart.t_start_each + n);
         if (c.history_capacity > 0) {  // for the path queries
             r.cfg = c;
             r.rhs = rhs_;
@@ -193,10 +248,18 @@ template <int METHOD> class Solver {
     // solve(data) + collect_vec (rk.rs:249-343, ivp.rs:209-211): the single trajectory set by with_initial_conditions
     Path solve(const std::vector<double>& data = {}, int capacity = 1 << 16) {
         if (y0_.empty()) throw IVPError(BACON_E_MISSING_PARAMETERS, "with_initial_conditions was not called");
-        with_history(capacity);
-        EnsembleResult r = solve_ivp_ensemble(1, y0_.data(), data.empty() ? nullptr : data.data());
-        with_history(0);
-        if (r.status[0] != BACON_OK) throw IVPError(r.status[0], "trajectory failed after " + std::to_string(r.hist_len[0]) + " point(s)");
+        // collect_vec grows its Vec (ivp.rs:209-211): a path longer than `capacity` is integrated once more with the
+        // capacity the first pass reported
+        EnsembleResult r;
+        for (int pass = 0; pass < 2; ++pass) {
+            with_history(capacity);
+            r = solve_ivp_ensemble(1, y0_.data(), data.empty() ? nullptr : data.data());
+            with_history(0);
+            if ((int64_t)r.n_accept[0] <= (int64_t)capacity) break;
+            capacity = (int)r.n_accept[0];
+        }
+        if (r.status[0] != BACON_OK && r.status[0] != BACON_STOPPED_AT_EVENT)
+            throw IVPError(r.status[0], "trajectory failed after " + std::to_string(r.hist_len[0]) + " point(s)");
         return r.path(0);
     }
     Path solve_ivp(const std::string& rhs_name, const std::vector<double>& data = {}) {  // README.md:40
@@ -204,14 +267,15 @@ template <int METHOD> class Solver {
     }
 };
 
-using RungeKutta45 = Solver<BACON_RK45>;  // rk.rs:561
-using RungeKutta23 = Solver<BACON_RK23>;  // rk.rs:656
-using BDF6 = Solver<BACON_BDF6>;          // bdf.rs:706
-using BDF2 = Solver<BACON_BDF2>;          // bdf.rs:762
-using Adams5 = Solver<BACON_ADAMS5>;      // adams.rs:633
-using Adams3 = Solver<BACON_ADAMS3>;      // adams.rs:693
-using Euler = Solver<BACON_EULER>;        // ivp.rs:269 (with_tolerance is a no-op, dt = average of the bounds given)
-using RK45 = RungeKutta45;                // README.md:24
-using RK23 = RungeKutta23;
+// `RungeKutta45<3>` is the reference's `RungeKutta45<'a, f64, U3, T>`; `RungeKutta45<>` its `Dyn` form
+template <int D = Dyn> using RungeKutta45 = Solver<BACON_RK45, D>;  // rk.rs:561
+template <int D = Dyn> using RungeKutta23 = Solver<BACON_RK23, D>;  // rk.rs:656
+template <int D = Dyn> using BDF6 = Solver<BACON_BDF6, D>;          // bdf.rs:706
+template <int D = Dyn> using BDF2 = Solver<BACON_BDF2, D>;          // bdf.rs:762
+template <int D = Dyn> using Adams5 = Solver<BACON_ADAMS5, D>;      // adams.rs:633
+template <int D = Dyn> using Adams3 = Solver<BACON_ADAMS3, D>;      // adams.rs:693
+template <int D = Dyn> using Euler = Solver<BACON_EULER, D>;        // ivp.rs:269 (with_tolerance is a no-op, dt = average of the bounds given)
+template <int D = Dyn> using RK45 = RungeKutta45<D>;                // README.md:24
+template <int D = Dyn> using RK23 = RungeKutta23<D>;
 
 }  // namespace bacon

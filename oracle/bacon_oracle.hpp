@@ -68,7 +68,7 @@ template <int N> inline double det_root(double x) {
 // status codes shared with include/bacon_ivp.h (bacon_status)
 enum : int {
     ST_OK = 0, ST_USER = 2, ST_MIN_DT = 8, ST_MAX_ITER = 9, ST_SINGULAR = 10,
-    ST_NONFINITE = 13, ST_MAX_ATTEMPTS = 14, ST_HISTORY_OVERFLOW = 15
+    ST_NONFINITE = 13, ST_MAX_ATTEMPTS = 14, ST_HISTORY_OVERFLOW = 15, ST_STOPPED_AT_EVENT = 19
 };
 
 // result of one IVPStepper::step call (src/ivp.rs:96, :20-28)
@@ -968,6 +968,47 @@ template <int D, class Rhs> struct EulerSolver {
 };
 
 // ------------------------------------------------------------------------
+// Cubic Hermite interpolant between two knots and the zero of a scalar Hermite cubic: CPU statement of
+// bacon_b200/csrc/path_query.cuh (hermite_eval, hermite_root), operation for operation.  NOT in the reference
+// (its Path is the accepted points, ivp.rs:203-211); used by the path queries (oracle_capi.cpp) and by the
+// terminal event of the drive loop below.
+// ------------------------------------------------------------------------
+template <int D>
+inline void hermite_eval(double th, double h, const double* ya, const double* yb, const double* fa, const double* fb,
+                         double* out) {
+    const double om = 1.0 - th, tt = th * (th - 1.0), c0 = 1.0 - 2.0 * th, c1 = th - 1.0;
+    for (int d = 0; d < D; ++d) {
+        const double dy = yb[d] - ya[d];
+        const double v = (c0 * dy + c1 * (h * fa[d])) + th * (h * fb[d]);
+        out[d] = (om * ya[d] + th * yb[d]) + tt * v;
+    }
+}
+
+// zero in [0, 1] of the scalar Hermite cubic: safeguarded Newton, as path_query.cuh (hermite_root)
+inline double hermite_root(double ga, double gb, double A, double B) {
+    if (gb == 0.0) return 1.0;
+    const double dg = gb - ga, vs = (A + B) - 2.0 * dg;
+    double lo = 0.0, hi = 1.0;
+    double th = ga / (ga - gb);
+    for (int it = 0; it < 60; ++it) {
+        const double tm1 = th - 1.0;
+        const double v = ((1.0 - 2.0 * th) * dg + tm1 * A) + th * B;
+        const double val = ((1.0 - th) * ga + th * gb) + (th * tm1) * v;
+        if (val == 0.0) break;
+        if ((val < 0.0) == (ga < 0.0)) lo = th;
+        else hi = th;
+        const double der = (dg + (2.0 * th - 1.0) * v) + (th * tm1) * vs;
+        double tn = th - val / der;
+        if (!(tn > lo && tn < hi)) tn = 0.5 * (lo + hi);
+        const double moved = std::fabs(tn - th);
+        th = tn;
+        if (moved <= 1e-15) break;
+    }
+    return th;
+}
+
+
+// ------------------------------------------------------------------------
 // IVPIterator drive loop (ivp.rs:220-238) + collect_vec (ivp.rs:209-211)
 // ------------------------------------------------------------------------
 template <int D> struct Solution {
@@ -980,15 +1021,74 @@ template <int D> struct Solution {
     std::vector<Vec<D>> path_y;        // yielded states
 };
 
-template <int D, class Stepper, class Yield>
-inline void drive(Stepper& s, uint64_t max_attempts, bool keep_path, Solution<D>& sol, Yield&& yielded) {
+// Optional inputs of a solve (include/bacon_ivp.h: bacon_ivp_config::dt_init, bacon_ivp_options): a first dt other
+// than the reference's (dt_max + dt_min)/2 — clamped into [dt_min, dt_max] — and a terminal event g(y) = w . y - c.
+// NOT in the reference; the statement of what the device kernels compiled for them do (drive.cuh: EventWatch).
+struct DriveOpts {
+    bool set_dt = false;
+    double dt = 0.0;
+    const double* ev_w = nullptr;
+    double ev_c = 0.0;
+    int ev_dir = 0;
+};
+inline double clamp_first_dt(double d, double dt_min, double dt_max) {
+    return !(d >= dt_min) ? dt_min : (d > dt_max ? dt_max : d);
+}
+
+// `point(s, t, y)` reads the point a step() == Ok yielded.
+template <int D, class Stepper, class Point>
+inline void drive(Stepper& s, uint64_t max_attempts, bool keep_path, Solution<D>& sol, Point&& point,
+                  const DriveOpts* o = nullptr) {
     const uint64_t cap = max_attempts ? max_attempts : 0xFFFFFFFEull;
     sol.status = ST_OK;
+    const bool ev = o && o->ev_w;
+    auto g_of = [&](const Vec<D>& y) {
+        double acc = o->ev_w[0] * y[0];
+        for (int d = 1; d < D; ++d) acc += o->ev_w[d] * y[d];
+        return acc - o->ev_c;
+    };
+    double tp = s.time, gp = 0.0;  // the last knot (knot 0 = the initial condition)
+    Vec<D> yp = s.state;
+    if (ev) gp = g_of(yp);
     for (;;) {
         if (s.cnt.n_steps >= cap) { sol.status = ST_MAX_ATTEMPTS; break; }
         const StepKind k = s.step();
         if (k == StepKind::Ok) {
-            if (keep_path) yielded(s);
+            double t;
+            Vec<D> y;
+            point(s, t, y);
+            if (ev) {
+                const double gb = g_of(y);
+                const bool rising = gp < 0.0 && gb >= 0.0, falling = gp > 0.0 && gb <= 0.0;
+                if (o->ev_dir > 0 ? rising : (o->ev_dir < 0 ? falling : (rising || falling))) {
+                    // the trajectory ends at the crossing, located on the Hermite cubic of this interval; the point that
+                    // crossed is not yielded
+                    double fa[D], fb[D];
+                    s.rhs(tp, yp.data(), s.params, fa);
+                    s.rhs(t, y.data(), s.params, fb);
+                    const double h = t - tp;
+                    double da = o->ev_w[0] * fa[0], db = o->ev_w[0] * fb[0];
+                    for (int d = 1; d < D; ++d) {
+                        da += o->ev_w[d] * fa[d];
+                        db += o->ev_w[d] * fb[d];
+                    }
+                    const double th = hermite_root(gp, gb, h * da, h * db);
+                    hermite_eval<D>(th, h, yp.data(), y.data(), fa, fb, sol.y_end.data());
+                    sol.t_end = tp + th * h;
+                    sol.dt_end = s.dt;
+                    sol.cnt = s.cnt;
+                    sol.cnt.n_accept -= 1;
+                    sol.status = ST_STOPPED_AT_EVENT;
+                    return;
+                }
+                gp = gb;
+                tp = t;
+                yp = y;
+            }
+            if (keep_path) {
+                sol.path_t.push_back(t);
+                sol.path_y.push_back(y);
+            }
             continue;
         }
         if (k == StepKind::Redo) continue;
@@ -1005,13 +1105,14 @@ inline void drive(Stepper& s, uint64_t max_attempts, bool keep_path, Solution<D>
 template <int D, int O, class Rhs>
 inline Solution<D> solve_rk(const RkTableau<O>& T, Rhs rhs, const double* params, const double* y0,
                             double t0, double t1, double dtmin, double dtmax, double tol,
-                            PowMode pm, uint64_t max_attempts, bool keep_path) {
+                            PowMode pm, uint64_t max_attempts, bool keep_path, const DriveOpts* o = nullptr) {
     RungeKuttaSolver<D, O, Rhs> s(T, rhs, params, y0, t0, t1, dtmin, dtmax, tol, pm);
+    if (o && o->set_dt) s.dt = clamp_first_dt(o->dt, dtmin, dtmax);
     Solution<D> sol;
-    drive<D>(s, max_attempts, keep_path, sol, [&](RungeKuttaSolver<D, O, Rhs>& st) {
-        sol.path_t.push_back(st.time);    // rk.rs:419
-        sol.path_y.push_back(st.state);
-    });
+    drive<D>(s, max_attempts, keep_path, sol, [](RungeKuttaSolver<D, O, Rhs>& st, double& t, Vec<D>& y) {
+        t = st.time;    // rk.rs:419
+        y = st.state;
+    }, o);
     return sol;
 }
 
@@ -1019,42 +1120,44 @@ template <int D, int O, class Rhs>
 inline Solution<D> solve_bdf(const BdfCoefficients<O>& C, Rhs rhs, const double* params,
                              const double* y0, double t0, double t1, double dtmin, double dtmax,
                              double tol, Mode mode, uint64_t max_attempts, bool keep_path,
-                             bool newton = false) {
+                             bool newton = false, const DriveOpts* o = nullptr) {
     BDFSolver<D, O, Rhs> s(C, rhs, params, y0, t0, t1, dtmin, dtmax, tol, mode);
     s.newton = newton;
+    if (o && o->set_dt) s.dt = clamp_first_dt(o->dt, dtmin, dtmax);
     Solution<D> sol;
-    drive<D>(s, max_attempts, keep_path, sol, [&](BDFSolver<D, O, Rhs>& st) {
-        sol.path_t.push_back(st.out_t);
-        sol.path_y.push_back(st.out_y);
-    });
+    drive<D>(s, max_attempts, keep_path, sol, [](BDFSolver<D, O, Rhs>& st, double& t, Vec<D>& y) {
+        t = st.out_t;
+        y = st.out_y;
+    }, o);
     return sol;
 }
 
 template <int D, int O, class Rhs>
 inline Solution<D> solve_adams(const AdamsCoefficients<O>& C, Rhs rhs, const double* params, const double* y0,
                                double t0, double t1, double dtmin, double dtmax, double tol, PowMode pm,
-                               Mode mode, uint64_t max_attempts, bool keep_path) {
+                               Mode mode, uint64_t max_attempts, bool keep_path, const DriveOpts* o = nullptr) {
     AdamsSolver<D, O, Rhs> s(C, rhs, params, y0, t0, t1, dtmin, dtmax, tol, pm);
     s.mode = mode;
+    if (o && o->set_dt) s.dt = clamp_first_dt(o->dt, dtmin, dtmax);
     Solution<D> sol;
-    drive<D>(s, max_attempts, keep_path, sol, [&](AdamsSolver<D, O, Rhs>& st) {
-        sol.path_t.push_back(st.out_t);
-        sol.path_y.push_back(st.out_y);
-    });
+    drive<D>(s, max_attempts, keep_path, sol, [](AdamsSolver<D, O, Rhs>& st, double& t, Vec<D>& y) {
+        t = st.out_t;
+        y = st.out_y;
+    }, o);
     return sol;
 }
 
 // Euler: `dt` is what the builder arrives at (ivp.rs:396-421); the C API passes (dt_max + dt_min)/2 when both
-// were given, or the one that was.
+// were given, or the one that was.  (A first dt in DriveOpts is not used: Euler's step is the builder's.)
 template <int D, class Rhs>
 inline Solution<D> solve_euler(Rhs rhs, const double* params, const double* y0, double t0, double t1, double dt,
-                               uint64_t max_attempts, bool keep_path) {
+                               uint64_t max_attempts, bool keep_path, const DriveOpts* o = nullptr) {
     EulerSolver<D, Rhs> s(rhs, params, y0, t0, t1, dt);
     Solution<D> sol;
-    drive<D>(s, max_attempts, keep_path, sol, [&](EulerSolver<D, Rhs>& st) {
-        sol.path_t.push_back(st.out_t);
-        sol.path_y.push_back(st.out_y);
-    });
+    drive<D>(s, max_attempts, keep_path, sol, [](EulerSolver<D, Rhs>& st, double& t, Vec<D>& y) {
+        t = st.out_t;
+        y = st.out_y;
+    }, o);
     return sol;
 }
 

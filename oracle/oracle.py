@@ -48,6 +48,10 @@ def lib():
             C.POINTER(_abi.Config), C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
             C.POINTER(_abi.Result), C.c_int, C.c_int]
         L.oracle_ivp_solve_ensemble.restype = C.c_int
+        L.oracle_ivp_solve_ensemble_ex.argtypes = [
+            C.POINTER(_abi.Config), C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(_abi.Options),
+            C.POINTER(_abi.Result), C.c_int, C.c_int]
+        L.oracle_ivp_solve_ensemble_ex.restype = C.c_int
         L.oracle_roots_secant.argtypes = [C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
                                           C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong)]
         L.oracle_roots_secant.restype = C.c_int
@@ -83,8 +87,11 @@ def rhs_info(name):
 
 def solve_ensemble(method, rhs, y0, params=None, *, dt_min, dt_max, tol, t_start, t_end,
                    semantics=_abi.SEM_CORRECTED, shared_params=False, params_aos=False, history_capacity=0,
-                   max_attempts=0, pow_mode=0, n_threads=0, bdf_newton=False):
+                   max_attempts=0, pow_mode=0, n_threads=0, bdf_newton=False, dt_init=0.0, t_start_each=None,
+                   dt_start_each=None, event=None):
     """Run the oracle on an ensemble.  y0: (dim, n) float64; params: (n_params, n) or (n_params,).
+    Optional inputs as in bacon_ivp_options: dt_init, per-trajectory t_start_each / dt_start_each (restart record),
+    event = (w, c, direction) terminal event.
 
     Returns a dict of numpy arrays with the same names/layouts as bacon_ivp_result.
     """
@@ -108,7 +115,24 @@ def solve_ensemble(method, rhs, y0, params=None, *, dt_min, dt_max, tol, t_start
         pptr = params.ctypes.data
     cfg = _abi.Config(method=method, dim=dim, n_params=npar, semantics=semantics, flags=flags,
                       history_capacity=history_capacity, dt_min=dt_min, dt_max=dt_max, tol=tol,
-                      t_start=t_start, t_end=t_end, max_attempts=max_attempts)
+                      t_start=t_start, t_end=t_end, max_attempts=max_attempts, dt_init=dt_init)
+    opts = _abi.Options()
+    keep = []
+    if t_start_each is not None:
+        keep.append(np.ascontiguousarray(t_start_each, dtype=np.float64))
+        assert keep[-1].shape == (n,)
+        opts.t_start_each = keep[-1].ctypes.data
+    if dt_start_each is not None:
+        keep.append(np.ascontiguousarray(dt_start_each, dtype=np.float64))
+        assert keep[-1].shape == (n,)
+        opts.dt_start_each = keep[-1].ctypes.data
+    if event is not None:
+        w, c, direction = event
+        keep.append(np.ascontiguousarray(w, dtype=np.float64).reshape(-1))
+        assert keep[-1].size == dim
+        opts.event_w = keep[-1].ctypes.data
+        opts.event_c = float(c)
+        opts.event_direction = int(direction)
     out = {
         "y_end": np.zeros((dim, n)), "t_end": np.zeros(n), "dt_end": np.zeros(n),
         "status": np.zeros(n, dtype=np.int32), "n_accept": np.zeros(n, dtype=np.uint32),
@@ -121,14 +145,16 @@ def solve_ensemble(method, rhs, y0, params=None, *, dt_min, dt_max, tol, t_start
     if history_capacity > 0:  # the two columns of the record array, as views
         out["hist_t"] = out["hist"][:, :, 0]
         out["hist_y"] = out["hist"][:, :, 1:]
-    rc = L.oracle_ivp_solve_ensemble(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(res),
-                                     pow_mode, n_threads)
+    rc = L.oracle_ivp_solve_ensemble_ex(C.byref(cfg), rid, n, y0.ctypes.data, pptr, C.byref(opts), C.byref(res),
+                                        pow_mode, n_threads)
     if rc != 0:
         raise RuntimeError(f"oracle_ivp_solve_ensemble rc={rc}")
     return out
 
 
 def _path_query_args(rhs, y0, params, solved, t_start, shared_params, params_aos):
+    """solved: dict with hist, hist_len and optionally t_end + y_end (closing knot), n_accept / status (a path cut
+    short by its capacity has no closing knot), t_start (per-trajectory start times of a resumed leg)."""
     rid, dim, npar = rhs_info(rhs)
     y0 = np.ascontiguousarray(y0, dtype=np.float64)
     hist = np.ascontiguousarray(solved["hist"], dtype=np.float64)
@@ -140,6 +166,15 @@ def _path_query_args(rhs, y0, params, solved, t_start, shared_params, params_aos
     if solved.get("t_end") is not None and solved.get("y_end") is not None:
         keep += [np.ascontiguousarray(solved["t_end"], dtype=np.float64), np.ascontiguousarray(solved["y_end"], dtype=np.float64)]
         res.t_end, res.y_end = keep[3].ctypes.data, keep[4].ctypes.data
+    if solved.get("n_accept") is not None:
+        keep.append(np.ascontiguousarray(solved["n_accept"], dtype=np.uint32))
+        res.n_accept = keep[-1].ctypes.data
+    if solved.get("status") is not None:
+        keep.append(np.ascontiguousarray(solved["status"], dtype=np.int32))
+        res.status = keep[-1].ctypes.data
+    if solved.get("t_start") is not None:
+        keep.append(np.ascontiguousarray(solved["t_start"], dtype=np.float64))
+        res.t_start = keep[-1].ctypes.data
     pptr = None
     if npar > 0:
         keep.append(np.ascontiguousarray(params, dtype=np.float64))

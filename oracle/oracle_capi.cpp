@@ -122,6 +122,7 @@ struct RunArgs {
     const double* y0;
     const double* params;
     const bacon_ivp_result* out;
+    const bacon_ivp_options* opts;  // optional inputs (restart record, terminal event); may be NULL
 };
 
 template <int D>
@@ -163,34 +164,46 @@ template <class Rhs> static void run_one(const RunArgs& a, size_t i) {
     const bo::Mode mode = c.semantics == BACON_SEM_LITERAL ? bo::Mode::Literal : bo::Mode::Corrected;
     const bool keep = c.history_capacity > 0;
     const bool newton = (c.flags & BACON_FLAG_BDF_NEWTON) != 0;
+    // optional inputs: cfg.dt_init / per-trajectory start time and first dt / terminal event
+    double t_start = c.t_start;
+    bo::DriveOpts dopt;
+    if (c.dt_init > 0.0) { dopt.set_dt = true; dopt.dt = c.dt_init; }
+    if (a.opts) {
+        if (a.opts->t_start_each) t_start = a.opts->t_start_each[i];
+        if (a.opts->dt_start_each) { dopt.set_dt = true; dopt.dt = a.opts->dt_start_each[i]; }
+        dopt.ev_w = a.opts->event_w;
+        dopt.ev_c = a.opts->event_c;
+        dopt.ev_dir = a.opts->event_direction;
+    }
+    const bo::DriveOpts* o = (dopt.set_dt || dopt.ev_w) ? &dopt : nullptr;
     bo::Solution<D> s;
     switch (c.method) {
         case BACON_RK45:
-            s = bo::solve_rk<D, 6>(bo::tableau_rkf45(mode), Rhs{}, p.data(), y0, c.t_start, c.t_end,
-                                   c.dt_min, c.dt_max, c.tol, a.pm, c.max_attempts, keep);
+            s = bo::solve_rk<D, 6>(bo::tableau_rkf45(mode), Rhs{}, p.data(), y0, t_start, c.t_end,
+                                   c.dt_min, c.dt_max, c.tol, a.pm, c.max_attempts, keep, o);
             break;
         case BACON_RK23:
-            s = bo::solve_rk<D, 4>(bo::tableau_bs23(mode), Rhs{}, p.data(), y0, c.t_start, c.t_end,
-                                   c.dt_min, c.dt_max, c.tol, a.pm, c.max_attempts, keep);
+            s = bo::solve_rk<D, 4>(bo::tableau_bs23(mode), Rhs{}, p.data(), y0, t_start, c.t_end,
+                                   c.dt_min, c.dt_max, c.tol, a.pm, c.max_attempts, keep, o);
             break;
         case BACON_BDF6:
-            s = bo::solve_bdf<D, 7>(bo::coefficients_bdf6(), Rhs{}, p.data(), y0, c.t_start, c.t_end,
-                                    c.dt_min, c.dt_max, c.tol, mode, c.max_attempts, keep, newton);
+            s = bo::solve_bdf<D, 7>(bo::coefficients_bdf6(), Rhs{}, p.data(), y0, t_start, c.t_end,
+                                    c.dt_min, c.dt_max, c.tol, mode, c.max_attempts, keep, newton, o);
             break;
         case BACON_BDF2:
-            s = bo::solve_bdf<D, 3>(bo::coefficients_bdf2(), Rhs{}, p.data(), y0, c.t_start, c.t_end,
-                                    c.dt_min, c.dt_max, c.tol, mode, c.max_attempts, keep, newton);
+            s = bo::solve_bdf<D, 3>(bo::coefficients_bdf2(), Rhs{}, p.data(), y0, t_start, c.t_end,
+                                    c.dt_min, c.dt_max, c.tol, mode, c.max_attempts, keep, newton, o);
             break;
         case BACON_ADAMS5:
-            s = bo::solve_adams<D, 5>(bo::coefficients_adams5(), Rhs{}, p.data(), y0, c.t_start, c.t_end,
-                                      c.dt_min, c.dt_max, c.tol, a.pm, mode, c.max_attempts, keep);
+            s = bo::solve_adams<D, 5>(bo::coefficients_adams5(), Rhs{}, p.data(), y0, t_start, c.t_end,
+                                      c.dt_min, c.dt_max, c.tol, a.pm, mode, c.max_attempts, keep, o);
             break;
         case BACON_ADAMS3:
-            s = bo::solve_adams<D, 3>(bo::coefficients_adams3(), Rhs{}, p.data(), y0, c.t_start, c.t_end,
-                                      c.dt_min, c.dt_max, c.tol, a.pm, mode, c.max_attempts, keep);
+            s = bo::solve_adams<D, 3>(bo::coefficients_adams3(), Rhs{}, p.data(), y0, t_start, c.t_end,
+                                      c.dt_min, c.dt_max, c.tol, a.pm, mode, c.max_attempts, keep, o);
             break;
         default:  // BACON_EULER: config.dt_max carries the builder's dt
-            s = bo::solve_euler<D>(Rhs{}, p.data(), y0, c.t_start, c.t_end, c.dt_max, c.max_attempts, keep);
+            s = bo::solve_euler<D>(Rhs{}, p.data(), y0, t_start, c.t_end, c.dt_max, c.max_attempts, keep, o);
             break;
     }
     store<D>(a, i, s);
@@ -230,10 +243,13 @@ template <int D> struct Knots {
         rec = a.solved->hist + i * (size_t)cap * (1 + D);
         const uint32_t len = a.solved->hist_len[i];
         m = len < cap ? len : cap;
-        t0 = a.cfg->t_start;
+        t0 = a.solved->t_start ? a.solved->t_start[i] : a.cfg->t_start;
         closing = false;
         tc = 0.0;
-        if (a.solved->t_end && a.solved->y_end) {
+        // a path cut short by its capacity ends at its last record (no closing knot across the unrecorded span)
+        const bool cut = a.solved->n_accept ? a.solved->n_accept[i] > cap
+                                            : (a.solved->status ? a.solved->status[i] == BACON_E_HISTORY_OVERFLOW : false);
+        if (a.solved->t_end && a.solved->y_end && !cut) {
             tc = a.solved->t_end[i];
             closing = tc > (m > 0 ? rec[(size_t)(m - 1) * (1 + D)] : t0);
         }
@@ -247,39 +263,8 @@ template <int D> struct Knots {
     }
 };
 
-template <int D>
-static void hermite_eval(double th, double h, const double* ya, const double* yb, const double* fa, const double* fb,
-                         double* out) {
-    const double om = 1.0 - th, tt = th * (th - 1.0), c0 = 1.0 - 2.0 * th, c1 = th - 1.0;
-    for (int d = 0; d < D; ++d) {
-        const double dy = yb[d] - ya[d];
-        const double v = (c0 * dy + c1 * (h * fa[d])) + th * (h * fb[d]);
-        out[d] = (om * ya[d] + th * yb[d]) + tt * v;
-    }
-}
-
-// zero in [0, 1] of the scalar Hermite cubic: safeguarded Newton, as path_query.cuh (hermite_root)
-static double hermite_root(double ga, double gb, double A, double B) {
-    if (gb == 0.0) return 1.0;
-    const double dg = gb - ga, vs = (A + B) - 2.0 * dg;
-    double lo = 0.0, hi = 1.0;
-    double th = ga / (ga - gb);
-    for (int it = 0; it < 60; ++it) {
-        const double tm1 = th - 1.0;
-        const double v = ((1.0 - 2.0 * th) * dg + tm1 * A) + th * B;
-        const double val = ((1.0 - th) * ga + th * gb) + (th * tm1) * v;
-        if (val == 0.0) break;
-        if ((val < 0.0) == (ga < 0.0)) lo = th;
-        else hi = th;
-        const double der = (dg + (2.0 * th - 1.0) * v) + (th * tm1) * vs;
-        double tn = th - val / der;
-        if (!(tn > lo && tn < hi)) tn = 0.5 * (lo + hi);
-        const double moved = std::fabs(tn - th);
-        th = tn;
-        if (moved <= 1e-15) break;
-    }
-    return th;
-}
+using bo::hermite_eval;
+using bo::hermite_root;
 
 template <class Rhs> static void load_params(const PathArgs& a, size_t i, std::vector<double>& p) {
     constexpr int P = Rhs::NPARAM;
@@ -406,16 +391,16 @@ int oracle_max_threads(void) {
 
 // Same contract as bacon_ivp_solve_ensemble (host buffers).  pow_mode: 0 = libm
 // pow (what rk.rs:401 calls), 1 = sqrt(sqrt(x)).  n_threads <= 0: all cores.
-int oracle_ivp_solve_ensemble(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0,
-                              const double* params, const bacon_ivp_result* out, int pow_mode,
-                              int n_threads) {
+int oracle_ivp_solve_ensemble_ex(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0,
+                                 const double* params, const bacon_ivp_options* opts, const bacon_ivp_result* out,
+                                 int pow_mode, int n_threads) {
     if (!cfg || !out || !y0 || !out->y_end || !out->status) return BACON_E_BAD_ARGUMENT;
     if (rhs_id < 0 || rhs_id >= kTableSize) return BACON_E_BAD_ARGUMENT;
     const Entry& e = kTable[rhs_id];
     if (cfg->dim != e.dim || cfg->n_params != e.n_params) return BACON_E_BAD_ARGUMENT;
     if (e.n_params > 0 && !params) return BACON_E_BAD_ARGUMENT;
     if (cfg->method < 0 || cfg->method >= BACON_N_METHODS) return BACON_E_BAD_ARGUMENT;
-    RunArgs a{cfg, pow_mode ? bo::PowMode::SqrtSqrt : bo::PowMode::LibmPow, n, y0, params, out};
+    RunArgs a{cfg, pow_mode ? bo::PowMode::SqrtSqrt : bo::PowMode::LibmPow, n, y0, params, out, opts};
 #ifdef _OPENMP
     const int nt = n_threads > 0 ? n_threads : omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
@@ -423,6 +408,12 @@ int oracle_ivp_solve_ensemble(const bacon_ivp_config* cfg, int rhs_id, size_t n,
     for (long long i = 0; i < (long long)n; ++i) e.run(a, (size_t)i);
     (void)n_threads;
     return 0;
+}
+
+int oracle_ivp_solve_ensemble(const bacon_ivp_config* cfg, int rhs_id, size_t n, const double* y0,
+                              const double* params, const bacon_ivp_result* out, int pow_mode,
+                              int n_threads) {
+    return oracle_ivp_solve_ensemble_ex(cfg, rhs_id, n, y0, params, nullptr, out, pow_mode, n_threads);
 }
 
 // Same contracts as bacon_ivp_sample_paths / bacon_ivp_locate_events (host buffers).

@@ -1,4 +1,4 @@
-//! Raw bindings to `include/bacon_ivp.h` (ABI version 5).  UNVERIFIED: no Rust toolchain in the build image.
+//! Raw bindings to `include/bacon_ivp.h` (ABI version 6).  UNVERIFIED: no Rust toolchain in the build image.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_double, c_int, c_void};
 
@@ -9,6 +9,11 @@ pub const BACON_BDF2: c_int = 3;
 pub const BACON_ADAMS5: c_int = 4;
 pub const BACON_ADAMS3: c_int = 5;
 pub const BACON_EULER: c_int = 6;
+
+/// the `Dyn` type parameter of bacon_solver_new_static / bacon_solver_new_dyn
+pub const BACON_DIM_DYN: c_int = 0;
+/// per-trajectory status, not an error: the integration stopped at a terminal event
+pub const BACON_STOPPED_AT_EVENT: i32 = 19;
 
 pub const BACON_SEM_CORRECTED: i32 = 0;
 pub const BACON_SEM_LITERAL: i32 = 1;
@@ -33,6 +38,7 @@ pub struct bacon_ivp_config {
     pub t_start: c_double,
     pub t_end: c_double,
     pub max_attempts: u64,
+    pub dt_init: c_double,
 }
 
 #[repr(C)]
@@ -47,6 +53,20 @@ pub struct bacon_ivp_result {
     pub n_rhs: *mut u32,
     pub hist: *mut c_double,
     pub hist_len: *mut u32,
+    /// INPUT of the path queries only: per-trajectory start times of a resumed leg (NULL = cfg.t_start)
+    pub t_start: *const c_double,
+}
+
+/// Optional inputs of a solve: restart record (per-trajectory start time and first dt) and terminal event.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct bacon_ivp_options {
+    pub t_start_each: *const c_double,
+    pub dt_start_each: *const c_double,
+    pub event_w: *const c_double,
+    pub event_c: c_double,
+    pub event_direction: i32,
+    pub reserved: i32,
 }
 
 #[repr(C)]
@@ -69,6 +89,9 @@ pub struct bacon_solver {
 extern "C" {
     pub fn bacon_abi_version() -> c_int;
     pub fn bacon_solver_new(method: c_int, dim: c_int) -> *mut bacon_solver;
+    pub fn bacon_solver_new_static(method: c_int, dim_type: c_int, out: *mut *mut bacon_solver) -> c_int;
+    pub fn bacon_solver_new_dyn(method: c_int, dim_type: c_int, size: c_int, out: *mut *mut bacon_solver) -> c_int;
+    pub fn bacon_solver_with_initial_dt(s: *mut bacon_solver, dt: c_double) -> c_int;
     pub fn bacon_solver_free(s: *mut bacon_solver);
     pub fn bacon_solver_with_tolerance(s: *mut bacon_solver, tol: c_double) -> c_int;
     pub fn bacon_solver_with_maximum_dt(s: *mut bacon_solver, max: c_double) -> c_int;
@@ -94,6 +117,13 @@ extern "C" {
                                            stream: *mut c_void) -> c_int;
     pub fn bacon_ivp_solve_ensemble_multi(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, y0: *const c_double,
                                           params: *const c_double, out: *const bacon_ivp_result, n_gpus: c_int) -> c_int;
+    pub fn bacon_ivp_solve_ensemble_ex(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, y0: *const c_double,
+                                       params: *const c_double, options: *const bacon_ivp_options,
+                                       out: *const bacon_ivp_result, n_gpus: c_int) -> c_int;
+    pub fn bacon_ivp_solve_ensemble_device_ex(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize,
+                                              d_y0: *const c_double, d_params: *const c_double,
+                                              options: *const bacon_ivp_options, d_out: *const bacon_ivp_result,
+                                              stream: *mut c_void) -> c_int;
     /// Queries on stored paths (cubic Hermite continuous extension of a dense-output solve; not in bacon 0.16.2).
     pub fn bacon_ivp_sample_paths(cfg: *const bacon_ivp_config, rhs_id: c_int, n: usize, y0: *const c_double,
                                   params: *const c_double, solved: *const bacon_ivp_result, n_times: usize,

@@ -3,7 +3,7 @@
 //! Python mirrors of this file are the tested ones.
 //!
 //! ```ignore
-//! use bacon_ivp::{RK45, IVPSolver};
+//! use bacon_ivp::RK45;
 //! let solver = RK45::new(1)?.with_dt_min(0.01)?.with_dt_max(0.1)?.with_tolerance(1e-4)?
 //!     .with_initial_conditions(&[1.0])?.with_start(0.0)?.with_end(10.0)?.build();
 //! let path = solver.solve_ivp("exp", &[])?;                       // README.md:32-40
@@ -38,6 +38,9 @@ pub enum IVPError {
     #[error("combination not built")] Unsupported = 18,
 }
 
+/// Per-trajectory status of a trajectory that stopped at a terminal event (not an error).
+pub const STOPPED_AT_EVENT: i32 = sys::BACON_STOPPED_AT_EVENT;
+
 fn check(rc: i32) -> Result<(), IVPError> {
     if rc == 0 { Ok(()) } else if (1..=18).contains(&rc) { Err(unsafe { std::mem::transmute::<i32, IVPError>(rc) }) } else { Err(IVPError::Cuda) }
 }
@@ -67,6 +70,15 @@ pub struct EnsembleResult {
     rhs: i32,
     y0: Vec<f64>,
     params: Vec<f64>,
+    t_start: Vec<f64>,     // per-trajectory start times of a resumed leg (empty otherwise)
+}
+
+/// The restart record of a solve: per-trajectory start times and first step sizes (`t_end`, `dt_end` of the previous
+/// leg, whose `y_end` is the next leg's `y0`) — the C-ABI form of the reference's resumable iterator (ivp.rs:220-238).
+#[derive(Clone, Copy, Default)]
+pub struct Restart<'a> {
+    pub t_start_each: Option<&'a [f64]>,
+    pub dt_start_each: Option<&'a [f64]>,
 }
 
 impl EnsembleResult {
@@ -82,8 +94,10 @@ impl EnsembleResult {
     fn solved(&self) -> sys::bacon_ivp_result {
         sys::bacon_ivp_result {
             y_end: self.y_end.as_ptr() as *mut f64, t_end: self.t_end.as_ptr() as *mut f64, dt_end: std::ptr::null_mut(),
-            status: std::ptr::null_mut(), n_accept: std::ptr::null_mut(), n_reject: std::ptr::null_mut(),
+            // (a path cut short by its capacity has no closing knot: the queries read n_accept / status)
+            status: self.status.as_ptr() as *mut i32, n_accept: self.n_accept.as_ptr() as *mut u32, n_reject: std::ptr::null_mut(),
             n_rhs: std::ptr::null_mut(), hist: self.hist.as_ptr() as *mut f64, hist_len: self.hist_len.as_ptr() as *mut u32,
+            t_start: if self.t_start.is_empty() { std::ptr::null() } else { self.t_start.as_ptr() },
         }
     }
 
@@ -118,6 +132,8 @@ pub struct Solver<const METHOD: i32> {
     dim: usize,
     rhs: Option<i32>,
     y0: Option<Vec<f64>>,
+    event: Option<(Vec<f64>, f64, i32)>,
+    n_gpus: i32,
 }
 
 impl<const METHOD: i32> Drop for Solver<METHOD> {
@@ -131,14 +147,44 @@ macro_rules! setter {
 }
 
 impl<const METHOD: i32> Solver<METHOD> {
-    /// `IVPSolver::new` / `new_dyn` (src/ivp.rs:159-163); the dimension is checked against the RHS at solve time.
-    pub fn new(dim: usize) -> Result<Self, IVPError> {
-        let h = unsafe { sys::bacon_solver_new(METHOD, dim as i32) };
-        if h.is_null() { return Err(IVPError::BadArgument); }
-        Ok(Self { h, dim, rhs: None, y0: None })
+    /// `IVPSolver::new` for a `Const<C>` solver (src/ivp.rs:159, src/lib.rs:59-61): `dim` is the static dimension C.
+    /// The dimension is checked against the RHS at solve time.
+    pub fn new(dim: usize) -> Result<Self, IVPError> { Self::new_static(dim as i32) }
+    /// `IVPSolver::new_dyn(size)` for a `Dyn` solver (src/ivp.rs:163, src/lib.rs:73-75).
+    pub fn new_dyn(size: usize) -> Result<Self, IVPError> { Self::new_dyn_typed(sys::BACON_DIM_DYN, size) }
+    /// The two constructors with the solver's type parameter spelled out (`dim_type` = C >= 1 for `Const<C>`,
+    /// `BACON_DIM_DYN` for `Dyn`): `new()` on `Dyn` is `StaticOnDynamic`, `new_dyn` on `Const<C>` `DynamicOnStatic`.
+    pub fn new_static(dim_type: i32) -> Result<Self, IVPError> {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::bacon_solver_new_static(METHOD, dim_type, &mut h) })?;
+        Ok(Self { h, dim: dim_type as usize, rhs: None, y0: None, event: None, n_gpus: 1 })
     }
-    pub fn new_dyn(size: usize) -> Result<Self, IVPError> { Self::new(size) }
+    pub fn new_dyn_typed(dim_type: i32, size: usize) -> Result<Self, IVPError> {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::bacon_solver_new_dyn(METHOD, dim_type, size as i32, &mut h) })?;
+        Ok(Self { h, dim: size, rhs: None, y0: None, event: None, n_gpus: 1 })
+    }
     pub fn dim(&self) -> usize { self.dim }
+    /// Shard every ensemble solve over the first `n` GPUs of the box (trajectory i -> GPU i mod n).
+    pub fn n_gpus(mut self, n: usize) -> Self { self.n_gpus = n as i32; self }
+    /// First step size instead of the reference's (dt_max + dt_min)/2 (rk.rs:315).
+    setter!(with_initial_dt, bacon_solver_with_initial_dt);
+    /// Stop every trajectory at the first zero of `w . y - c` (direction +1 rising, -1 falling, 0 both).
+    pub fn with_terminal_event(mut self, w: &[f64], c: f64, direction: i32) -> Result<Self, IVPError> {
+        if w.len() != self.dim || !(-1..=1).contains(&direction) { return Err(IVPError::BadArgument); }
+        self.event = Some((w.to_vec(), c, direction));
+        Ok(self)
+    }
+    /// `with_derivative(closure)` for a GPU: the functor as CUDA C++ source text (contract: include/bacon_ivp_rhs.cuh),
+    /// compiled by the library with NVRTC and inlined into the kernels.  `UserError` + `last_error()` = the compiler log.
+    pub fn register_source(mut self, name: &str, type_name: &str, source: &str, n_params: usize) -> Result<Self, IVPError> {
+        let (n, t, s) = (CString::new(name).map_err(|_| IVPError::BadArgument)?, CString::new(type_name).map_err(|_| IVPError::BadArgument)?,
+                         CString::new(source).map_err(|_| IVPError::BadArgument)?);
+        let id = unsafe { sys::bacon_rhs_register_source(n.as_ptr(), t.as_ptr(), s.as_ptr(), self.dim as i32, n_params as i32) };
+        if id < 0 { check(-id)?; }
+        self.rhs = Some(id);
+        Ok(self)
+    }
 
     setter!(with_tolerance, bacon_solver_with_tolerance);        // rk.rs:168
     setter!(with_maximum_dt, bacon_solver_with_maximum_dt);      // rk.rs:179
@@ -172,6 +218,11 @@ impl<const METHOD: i32> Solver<METHOD> {
 
     /// N initial conditions x N parameter sets: y0 is [dim][n], params [n_params][n] (or [n_params] when shared).
     pub fn solve_ivp_ensemble(&self, y0: &[f64], params: &[f64], shared_params: bool) -> Result<EnsembleResult, IVPError> {
+        self.solve_ivp_ensemble_from(y0, params, shared_params, Restart::default())
+    }
+
+    /// The same, going on from a restart record (`y0` = the previous leg's `y_end`).
+    pub fn solve_ivp_ensemble_from(&self, y0: &[f64], params: &[f64], shared_params: bool, restart: Restart) -> Result<EnsembleResult, IVPError> {
         let rhs = self.rhs.ok_or(IVPError::MissingParameters)?;
         let mut cfg = sys::bacon_ivp_config::default();
         check(unsafe { sys::bacon_solver_config(self.h, &mut cfg) })?;
@@ -188,16 +239,29 @@ impl<const METHOD: i32> Solver<METHOD> {
             n_accept: vec![0; n], n_reject: vec![0; n], n_rhs: vec![0; n],
             hist: vec![0.0; n * cap * (1 + self.dim)], hist_len: vec![0; n],
             cfg, rhs, y0: if cap > 0 { y0.to_vec() } else { Vec::new() }, params: if cap > 0 { params.to_vec() } else { Vec::new() },
+            t_start: restart.t_start_each.map(|t| t.to_vec()).unwrap_or_default(),
         };
+        if restart.t_start_each.map_or(false, |t| t.len() != n) || restart.dt_start_each.map_or(false, |t| t.len() != n) {
+            return Err(IVPError::BadArgument);
+        }
         let out = sys::bacon_ivp_result {
             y_end: r.y_end.as_mut_ptr(), t_end: r.t_end.as_mut_ptr(), dt_end: r.dt_end.as_mut_ptr(),
             status: r.status.as_mut_ptr(), n_accept: r.n_accept.as_mut_ptr(), n_reject: r.n_reject.as_mut_ptr(),
             n_rhs: r.n_rhs.as_mut_ptr(),
             hist: if cap > 0 { r.hist.as_mut_ptr() } else { std::ptr::null_mut() },
             hist_len: if cap > 0 { r.hist_len.as_mut_ptr() } else { std::ptr::null_mut() },
+            t_start: std::ptr::null(),
         };
         let pptr = if params.is_empty() { std::ptr::null() } else { params.as_ptr() };
-        check(unsafe { sys::bacon_ivp_solve_ensemble(&cfg, rhs, n, y0.as_ptr(), pptr, &out) })?;
+        let opts = sys::bacon_ivp_options {
+            t_start_each: restart.t_start_each.map_or(std::ptr::null(), |t| t.as_ptr()),
+            dt_start_each: restart.dt_start_each.map_or(std::ptr::null(), |t| t.as_ptr()),
+            event_w: self.event.as_ref().map_or(std::ptr::null(), |e| e.0.as_ptr()),
+            event_c: self.event.as_ref().map_or(0.0, |e| e.1),
+            event_direction: self.event.as_ref().map_or(0, |e| e.2),
+            reserved: 0,
+        };
+        check(unsafe { sys::bacon_ivp_solve_ensemble_ex(&cfg, rhs, n, y0.as_ptr(), pptr, &opts, &out, self.n_gpus) })?;
         Ok(r)
     }
 
@@ -205,8 +269,14 @@ impl<const METHOD: i32> Solver<METHOD> {
     pub fn solve(self, data: &[f64]) -> Result<Path, IVPError> {
         let y0 = self.y0.clone().ok_or(IVPError::MissingParameters)?;
         let s = self.with_history(1 << 16)?;
-        let r = s.solve_ivp_ensemble(&y0, data, false)?;
-        check(r.status[0])?;
+        let mut r = s.solve_ivp_ensemble(&y0, data, false)?;
+        let s = if r.n_accept[0] as usize > (1 << 16) {  // collect_vec grows its Vec (ivp.rs:209-211): once more, with the capacity reported
+            let s = s.with_history(r.n_accept[0] as usize)?;
+            r = s.solve_ivp_ensemble(&y0, data, false)?;
+            s
+        } else { s };
+        let _ = s;
+        if r.status[0] != STOPPED_AT_EVENT { check(r.status[0])?; }
         Ok(r.path(0))
     }
     pub fn solve_ivp(self, rhs: &str, data: &[f64]) -> Result<Path, IVPError> { self.with_derivative(rhs)?.solve(data) }   // README.md:40

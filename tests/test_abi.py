@@ -23,6 +23,19 @@ def test_header_and_python_mirror_agree():
     assert declared_functions() == sorted(_abi.EXPORTED_SYMBOLS)
 
 
+def test_rust_sys_bindings_declare_the_same_abi():
+    """rust/bacon-ivp-sys cannot be compiled here (no cargo): at least its extern block names every entry point of the
+    header except the nvcc-side plug-in registration, and its #[repr(C)] structs list the header's fields in order."""
+    rs = open(os.path.join(ROOT, "rust", "bacon-ivp-sys", "src", "lib.rs")).read()
+    assert f"ABI version {_abi.ABI_VERSION}" in rs
+    fns = set(re.findall(r"pub fn (bacon_\w+)", rs))
+    assert fns == set(declared_functions()) - {"bacon_rhs_register"}
+    for struct, mirror in (("bacon_ivp_config", _abi.Config), ("bacon_ivp_result", _abi.Result),
+                           ("bacon_ivp_options", _abi.Options), ("bacon_ivp_launch_info", _abi.LaunchInfo)):
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % struct, rs, flags=re.S).group(1)
+        assert re.findall(r"pub (\w+):", body) == [n for n, _ in mirror._fields_], struct
+
+
 def test_library_exports_every_declared_symbol(engine):
     from bacon_b200._lib import lib
     L = lib()
@@ -30,16 +43,74 @@ def test_library_exports_every_declared_symbol(engine):
         assert hasattr(L, name), f"libbacon_ivp.so does not export {name}"
     assert L.bacon_abi_version() == _abi.ABI_VERSION
     for code, name in _abi.STATUS_NAMES.items():
-        if code <= _abi.E_UNSUPPORTED:
-            assert L.bacon_status_name(code).decode() == name
+        assert L.bacon_status_name(code).decode() == name
 
 
-def test_struct_layouts_match_header():
-    # bacon_ivp_config: 6 x 4-byte fields, 5 doubles, one u64; bacon_ivp_result: 9 pointers
-    assert C.sizeof(_abi.Config) == 6 * 4 + 5 * 8 + 8
-    assert _abi.Config.dt_min.offset == 24 and _abi.Config.max_attempts.offset == 64
-    assert C.sizeof(_abi.Result) == 9 * C.sizeof(C.c_void_p)
-    assert C.sizeof(_abi.LaunchInfo) == 3 * 4 + 4 * 4
+def test_struct_layouts_match_header(tmp_path):
+    """The ctypes mirrors against the header itself: a C program compiled from include/bacon_ivp.h prints the sizes and
+    field offsets gcc gives the structs."""
+    import subprocess
+    fields = {"Config": ("bacon_ivp_config", [n for n, _ in _abi.Config._fields_]),
+              "Result": ("bacon_ivp_result", [n for n, _ in _abi.Result._fields_]),
+              "Options": ("bacon_ivp_options", [n for n, _ in _abi.Options._fields_]),
+              "LaunchInfo": ("bacon_ivp_launch_info", [n for n, _ in _abi.LaunchInfo._fields_])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bacon_ivp.h"', 'int main(void) {']
+    for py, (c, names) in fields.items():
+        lines.append(f'printf("{py} size %zu\\n", sizeof({c}));')
+        for n in names:
+            lines.append(f'printf("{py} {n} %zu\\n", offsetof({c}, {n}));')
+    lines.append('printf("abi %d\\n", BACON_IVP_ABI_VERSION); printf("dyn %d\\n", BACON_DIM_DYN);')
+    lines.append('printf("stopped %d\\n", (int)BACON_STOPPED_AT_EVENT); return 0; }')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for l in out:
+        w = l.split()
+        if len(w) == 3 and w[1] == "size":
+            assert C.sizeof(getattr(_abi, w[0])) == int(w[2]), l
+            seen += 1
+        elif len(w) == 3:
+            assert getattr(getattr(_abi, w[0]), w[1]).offset == int(w[2]), l
+            seen += 1
+        elif len(w) == 2:
+            assert {"abi": _abi.ABI_VERSION, "dyn": _abi.DIM_DYN, "stopped": _abi.STOPPED_AT_EVENT}[w[0]] == int(w[1]), l
+            seen += 1
+    assert seen == 4 + sum(len(n) for _, n in fields.values()) + 3
+
+
+def test_dimension_errors_of_the_constructors(engine):
+    """IVPSolver::new / new_dyn with the reference's `Dimension` (src/lib.rs:53-76, ivp.rs:72-88): new() on a Dyn solver
+    is StaticOnDynamic, new_dyn(size) on a Const<C> solver is DynamicOnStatic; the matching calls build a solver."""
+    E = engine.IVPError
+    for cls in (engine.RungeKutta45, engine.BDF6, engine.Adams5, engine.Euler):
+        assert cls.new(3).dim() == 3                      # RK45::<U3>::new()
+        assert cls.new_dyn(2).dim() == 2                  # RK45::<Dyn>::new_dyn(2)   (ivp.rs:562)
+        with pytest.raises(E) as e:
+            cls.new(dim_type=cls.DYN)                     # RK45::<Dyn>::new()
+        assert e.value.variant == "StaticOnDynamic" and e.value.code == 12
+        with pytest.raises(E) as e:
+            cls.new_dyn(3, dim_type=3)                    # RK45::<U3>::new_dyn(3)
+        assert e.value.variant == "DynamicOnStatic" and e.value.code == 11
+    # the messages are the reference's (lib.rs:47-50)
+    try:
+        engine.RK45.new(dim_type=engine.RK45.DYN)
+    except E as e:
+        assert "static solver with dynamic dimension" in str(e)
+
+
+def test_initial_dt_setter(engine):
+    E = engine.IVPError
+    s = (engine.RK45.new(1).with_maximum_dt(0.1).with_minimum_dt(0.01).with_tolerance(1e-4).with_initial_time(0.0)
+         .with_ending_time(1.0))
+    assert s._config(0).dt_init == 0.0                    # the reference's (dt_max + dt_min)/2
+    assert s.with_initial_dt(0.05)._config(0).dt_init == 0.05
+    for bad in (0.0, -1.0, float("nan")):
+        with pytest.raises(E) as e:
+            s.with_initial_dt(bad)
+        assert e.value.variant == "TimeDeltaOOB"
 
 
 def test_builtin_rhs_registry(engine):

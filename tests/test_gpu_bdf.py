@@ -113,8 +113,12 @@ def test_bdf_dense_output_and_failures(cuda, engine, oracle):
                         tol=1e-8, t_start=0.0, t_end=1.0)
     np.testing.assert_array_equal(gpu.status, ref["status"])
     assert (gpu.status != _abi.OK).all()
-    # REF_LITERAL BDF is CPU-oracle only
-    s = make_solver(engine, "BDF6", 3, rhs="robertson", semantics=_abi.SEM_LITERAL, t_end=0.01, **ROB)
+    # REF_LITERAL BDF (the source as written) runs in the strict Broyden build: the oracle's bits, Robertson included
+    # (tests/test_gpu_options.py replays the reference's own BDF tests in this mode); the Newton variant has no LITERAL form
+    gpu, ref = run_both(engine, oracle, "BDF6", "robertson", y0[:, :64], k[:, :64], semantics=_abi.SEM_LITERAL,
+                        max_attempts=3000, t_end=0.004, **ROB)
+    _bit_exact(gpu, ref)
+    s = make_solver(engine, "BDF6", 3, rhs="robertson", semantics=_abi.SEM_LITERAL, flags=_abi.FLAG_BDF_NEWTON, t_end=0.01, **ROB)
     with pytest.raises(engine.IVPError) as e:
         s.solve_ivp_ensemble(y0, k)
     assert e.value.variant == "Unsupported"
