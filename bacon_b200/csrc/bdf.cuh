@@ -358,7 +358,12 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
     uint32_t cap;
     // one trajectory (bdf.rs:72-122)
     double y[D], p[P > 0 ? P : 1];
-    double hy[O][D], ht[O];  // prev_values: oldest first; `have` = deque non-empty (it holds 0 or O entries)
+    // prev_values, oldest first; `have` = deque non-empty (it holds 0 or O entries).  Only the STATES are kept: the
+    // times of the deque are never used by the formulas, and the one place that reads them — yielding the stored warm-up
+    // points (bdf.rs:500-512) — gets the same bits by repeating the warm-up's own additions t <- t + dt from the time
+    // the block started (`tb`): dt cannot change between the warm-up and those yields.  Seven doubles fewer to hold and
+    // to shift at every accepted step (the shifts were a fifth of this kernel's instructions).
+    double hy[O][D], tb;
     double save[D];
     double oy[D], ot;        // the point of the last Ok(...)
     double t, dt;
@@ -394,8 +399,9 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
 #pragma unroll
         for (int d = 0; d < D; ++d) { save[d] = 0.0; oy[d] = 0.0; }
 #pragma unroll
+        tb = t_start;
+#pragma unroll
         for (int k = 0; k < O; ++k) {
-            ht[k] = 0.0;
 #pragma unroll
             for (int d = 0; d < D; ++d) hy[k][d] = 0.0;
         }
@@ -418,14 +424,12 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
         Rhs{}(tt, x, p, dy);
     }
 
-    __device__ __forceinline__ void push_pop(double tt, const double (&x)[D]) {  // push_back + pop_front
+    __device__ __forceinline__ void push_pop(double, const double (&x)[D]) {  // push_back + pop_front
 #pragma unroll
         for (int k = 0; k + 1 < O; ++k) {
-            ht[k] = ht[k + 1];
 #pragma unroll
             for (int d = 0; d < D; ++d) hy[k][d] = hy[k + 1][d];
         }
-        ht[O - 1] = tt;
 #pragma unroll
         for (int d = 0; d < D; ++d) hy[O - 1][d] = x[d];
     }
@@ -631,13 +635,15 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
             const uint32_t get = (uint32_t)O - ym;
             ym -= 1;
             if (ym == 0) ym = O + 2;
+            ot = tb;  // time of stored point `get` = tb + dt, get + 1 times over, rounded as the warm-up rounded it
 #pragma unroll
-            for (int k = 0; k < O; ++k)
+            for (int k = 0; k < O; ++k) {
+                if ((uint32_t)k <= get) ot = A::add(ot, dt);
                 if (get == (uint32_t)k) {
-                    ot = ht[k];
 #pragma unroll
                     for (int d = 0; d < D; ++d) oy[d] = hy[k][d];
                 }
+            }
             n_acc++;
             yielded = true;
             return -1;
@@ -664,9 +670,10 @@ template <class Rhs, class Coef, bool STRICT, bool NEWTON> struct BdfStepper {
             for (int d = 0; d < D; ++d) save[d] = y[d];
             if (A::madd(dt, order, t) >= t_end) dt = A::div(A::sub(t_end, t), order);
 #pragma unroll
+            tb = t;
+#pragma unroll
             for (int k = 0; k < O; ++k) {
                 rk4_step();
-                ht[k] = t;
 #pragma unroll
                 for (int d = 0; d < D; ++d) hy[k][d] = y[d];
             }

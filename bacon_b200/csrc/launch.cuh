@@ -137,7 +137,10 @@ template <class Rhs, class Tab, bool EVENT = false, int MINB = 1> int launch_rk_
 // cold paths) — the kernel is latency-bound (ncu: 3 warps per sub-partition at 168 registers, 45 % of stalls are
 // fixed-latency waits), measured 7.38e10 steps/s against 7.00e10 at 3 and 7.09e10 at 5.  The reference's Broyden
 // iteration keeps two D x D matrices alive and stays at 2.
-template <class Rhs, class Coef, bool STRICT, bool EVENT = false, int MINB = 2, int MINB_NEWTON = 4> int launch_bdf(bacon_launch_args* a) {
+#ifndef BACON_BDF_NEWTON_MINB
+#define BACON_BDF_NEWTON_MINB 4  // (A/B switch for measurements)
+#endif
+template <class Rhs, class Coef, bool STRICT, bool EVENT = false, int MINB = 2, int MINB_NEWTON = BACON_BDF_NEWTON_MINB> int launch_bdf(bacon_launch_args* a) {
     // REF_LITERAL (bdf.rs:407, :568, :622 as written) is the reference's own Broyden iteration in the strict build
     if (a->cfg.semantics != BACON_SEM_CORRECTED && !(STRICT && !(a->cfg.flags & BACON_FLAG_BDF_NEWTON))) return BACON_E_UNSUPPORTED;
     if (a->cfg.flags & BACON_FLAG_BDF_NEWTON) {

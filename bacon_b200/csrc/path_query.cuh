@@ -25,6 +25,8 @@
 #pragma once
 #ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 #endif
 
 #include "ivp_common.cuh"
@@ -326,6 +328,7 @@ __device__ __noinline__ void locate_event(const bacon_path_args& a, unsigned lon
 
 // how a warp's queue of crossings is located: one crossing per lane (thread-sized states)
 template <class Rhs> struct LaneLocate {
+    static constexpr bool DEFERRED = false;  // crossings are located inside the streaming kernel
     static __device__ __forceinline__ void flush(const bacon_path_args& a, unsigned long long i, uint32_t n_pend, const uint32_t* pk,
                                                  const uint32_t* ps, double* ev, unsigned lane) {
         if (lane < n_pend) locate_event<Rhs>(a, i, pk[lane], ev + (size_t)ps[lane] * (1 + Rhs::DIM));
@@ -468,8 +471,236 @@ __global__ void __launch_bounds__(PATH_BLOCK, ev_minb<Rhs::DIM>()) path_events_k
     if (lane == 0) a.n_events[i] = count;
 }
 
+// ---- events on WIDE records (1 + D > 8; linear32's 264-byte records): the stream staged through shared memory by TMA.
+// What limited the one-lane-per-record kernel above on such paths (config 4: ~122 records, 2.3 TB/s = 36 % of the HBM
+// peak; ncu: 67 % of the stall samples long_scoreboard, 0.27 eligible warps per scheduler, 3.1 of 4 warps resident at
+// 128 registers; profiles/r02z_cfg4_events_full.md) is memory-level parallelism: a lane that sums its own 264-byte
+// record from global memory touches a new 32-byte sector every four terms, and with the registers of a wide kernel only a
+// few of those loads are in flight at once — nine dependent round trips per chunk, ~33 us per path per warp.  Here ONE
+// elected lane asks the TMA unit for whole chunks (32 records = 8448 contiguous bytes, cp.async.bulk into a per-warp ring of
+// EVW_STAGES buffers, completion on an mbarrier), up to EVW_STAGES chunks ahead, so 25 KB per warp are in flight without
+// a single register; the lanes then read their record from shared memory (row stride 33 doubles: conflict-free) and
+// sum g in the oracle's order.  Crossing test and queue are the kernel's above.  Location: a Locate policy with
+// DEFERRED leaves only the knot index of every crossing in its event slot and a second kernel (path_locate_deferred_kernel)
+// locates them all at once — for linear32 a location needs the trajectory's 8 KB matrix and four
+// 32 x 32 matrix-vector products by the whole warp, and done inside the stream, one crossing after the other at the
+// end of each path, it held the streaming kernel at 3.2 ms whatever its staging depth or occupancy (config 4: 0.9
+// crossings per path; A/B in profiles/r03_path_queries.md).
+#ifndef BACON_EVW_STAGES
+#define BACON_EVW_STAGES 2
+#endif
+#ifndef BACON_EVW_MINB
+#define BACON_EVW_MINB 3
+#endif
+constexpr int EVW_STAGES = BACON_EVW_STAGES;
+template <int R> __host__ __device__ constexpr size_t evw_smem_bytes() { return (size_t)(PATH_BLOCK / 32) * EVW_STAGES * 32 * R * sizeof(double); }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+// global -> shared bulk copy by the TMA unit: 16-byte aligned on both sides, a multiple of 16 bytes
+__device__ __forceinline__ void tma_bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class Rhs, bool STRICT, class Locate>
+__global__ void __launch_bounds__(PATH_BLOCK, BACON_EVW_MINB) path_events_wide_kernel(const __grid_constant__ bacon_path_args a) {
+    constexpr int D = Rhs::DIM;
+    constexpr int R = 1 + D;
+    constexpr int NW = PATH_BLOCK / 32;
+    extern __shared__ __align__(128) double evw_ring[];  // [NW][EVW_STAGES][32 * R]
+    __shared__ __align__(8) unsigned long long bars[NW][EVW_STAGES];
+    __shared__ uint32_t pend_k[NW][32], pend_slot[NW][32];
+    const unsigned wid = threadIdx.x >> 5, lane = lane_id();
+    double* ring = evw_ring + (size_t)wid * EVW_STAGES * 32 * R;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < EVW_STAGES; ++s) mbar_init(&bars[wid][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // (the barriers become visible to the async proxy)
+    }
+    __syncwarp();
+    const unsigned long long i = ((unsigned long long)blockIdx.x * PATH_BLOCK + threadIdx.x) >> 5;
+    if (i >= a.n) return;  // (whole warps leave together)
+    const PathView<D> pv(a, i);
+    const uint32_t K = pv.last();
+    const uint32_t n_chunks = (pv.m + 31u) >> 5;
+    auto issue = [&](uint32_t c) {  // lane 0: chunk c on its way into stage c % EVW_STAGES
+        const uint32_t st = c % EVW_STAGES;
+        const uint32_t left = pv.m - 32u * c, nrec = left < 32u ? left : 32u;
+        const uint32_t bytes = (nrec & ~1u) * R * 8u;  // an even number of records is a multiple of 16 bytes
+        if (bytes) {
+            mbar_expect_tx(&bars[wid][st], bytes);
+            tma_bulk_load(ring + (size_t)st * 32 * R, pv.rec + (size_t)32 * c * R, bytes, &bars[wid][st]);
+        } else {
+            mbar_arrive(&bars[wid][st]);  // (a last chunk of one record: nothing for the TMA unit)
+        }
+    };
+    if (lane == 0) {
+        for (uint32_t c = 0; c < n_chunks && c < (uint32_t)EVW_STAGES; ++c) issue(c);
+    }
+    // g of a knot that is not a record (knot 0, the closing knot): straight from memory, oracle order
+    auto knot_g = [&](uint32_t k) -> double {
+        const double* src = k == 0 ? pv.y0 + i : pv.y_end + i;
+        double sum = a.ev_w[0] * src[0];
+#pragma unroll
+        for (int d = 1; d < D; ++d) sum += a.ev_w[d] * src[(size_t)d * pv.n];
+        return sum - a.ev_c;
+    };
+    const double g0 = knot_g(0);
+    unsigned carry_neg = g0 < 0.0 ? 1u : 0u, carry_pos = g0 > 0.0 ? 1u : 0u;
+    uint32_t count = 0, n_pend = 0;  // warp-uniform
+    const uint32_t cap = (uint32_t)a.ev_capacity;
+    double* ev = a.events + (size_t)i * cap * R;
+    auto flush = [&]() {
+        __syncwarp();
+        Locate::flush(a, i, n_pend, pend_k[wid], pend_slot[wid], ev, lane);
+        __syncwarp();
+    };
+    // 32 knots base .. base + 31 (lane l holds knot base + l, `have` = it exists): crossings against the left neighbour
+    auto scan = [&](uint32_t base, bool have, double g) {
+        const unsigned neg = __ballot_sync(FULL_MASK, have && g < 0.0), pos = __ballot_sync(FULL_MASK, have && g > 0.0);
+        const unsigned ord = __ballot_sync(FULL_MASK, have && g == g);  // (a NaN is neither side of the surface)
+        const unsigned rising = ((neg << 1) | carry_neg) & ~neg & ord, falling = ((pos << 1) | carry_pos) & ~pos & ord;
+        carry_neg = neg >> 31;
+        carry_pos = pos >> 31;
+        const unsigned h = a.ev_direction > 0 ? rising : (a.ev_direction < 0 ? falling : (rising | falling));
+        if (h == 0) return;
+        const uint32_t nh = (uint32_t)__popc(h);
+        const uint32_t room = count < cap ? cap - count : 0u;
+        const uint32_t n_enq = nh < room ? nh : room;
+        const uint32_t rank = (uint32_t)__popc(h & lanemask_lt());
+        if constexpr (Locate::DEFERRED) {  // the slot holds the knot index until the second kernel has been there
+            if (((h >> lane) & 1u) && rank < n_enq) ev[(size_t)(count + rank) * R] = __longlong_as_double((long long)(base + lane));
+            count += nh;
+            return;
+        }
+        if (n_pend + n_enq > 32u) {
+            flush();
+            n_pend = 0;
+        }
+        if (((h >> lane) & 1u) && rank < n_enq) {
+            pend_k[wid][n_pend + rank] = base + lane;
+            pend_slot[wid][n_pend + rank] = count + rank;
+        }
+        n_pend += n_enq;
+        count += nh;
+    };
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint32_t st = c % EVW_STAGES;
+        double* buf = ring + (size_t)st * 32 * R;
+        const uint32_t left = pv.m - 32u * c, nrec = left < 32u ? left : 32u;
+        mbar_wait(&bars[wid][st], (c / EVW_STAGES) & 1u);
+        if (nrec & 1u) {  // the odd last record of the path: by the lanes
+            const double* src = pv.rec + ((size_t)32 * c + (nrec - 1)) * R;
+            for (uint32_t e = lane; e < (uint32_t)R; e += 32) buf[(size_t)(nrec - 1) * R + e] = src[e];
+        }
+        __syncwarp();
+        const bool have = lane < nrec;
+        double g = 0.0;
+        if (have) {
+            const double* r = buf + (size_t)lane * R + 1;
+            double sum = a.ev_w[0] * r[0];
+#pragma unroll
+            for (int d = 1; d < D; ++d) sum += a.ev_w[d] * r[d];
+            g = sum - a.ev_c;
+        }
+        scan(1u + 32u * c, have, g);
+        __syncwarp();  // every lane is done with this stage: the next chunk may land in it
+        if (lane == 0 && c + EVW_STAGES < n_chunks) issue(c + EVW_STAGES);
+    }
+    if (K > pv.m) scan(K, lane == 0, knot_g(K));  // the closing knot
+    if (n_pend) flush();
+    if (lane == 0) a.n_events[i] = count;
+}
+
+// second kernel of a DEFERRED location.  A warp takes 32 consecutive event slots (slot = trajectory * capacity + j):
+// lane l reads whether its slot is filled (j < min(n_events, capacity)) and the knot index parked there — coalesced,
+// one round trip for 32 slots — then the warp locates the filled ones trajectory by trajectory through the policy's
+// flush(), so a trajectory's matrix is loaded once for all its crossings.
+#ifndef BACON_LOCATE_MINB
+#define BACON_LOCATE_MINB 4  // (measured on config 4: 3 -> 2.42 ms, 4 -> 2.32, 5 -> 2.33)
+#endif
+template <class Locate>
+__global__ void __launch_bounds__(PATH_BLOCK, BACON_LOCATE_MINB) path_locate_deferred_kernel(const __grid_constant__ bacon_path_args a) {
+    constexpr int R = 1 + Locate::DIM;
+    __shared__ uint32_t pk[PATH_BLOCK / 32][32], ps[PATH_BLOCK / 32][32];
+    const unsigned wid = threadIdx.x >> 5, lane = lane_id();
+    const unsigned long long cap = (unsigned long long)a.ev_capacity, total = a.n * cap;
+    const unsigned long long s = ((((unsigned long long)blockIdx.x * PATH_BLOCK + threadIdx.x) >> 5) << 5) + lane;
+    bool valid = false;
+    uint32_t k = 0, j = 0;
+    unsigned long long i = 0;
+    if (s < total) {
+        i = s / cap;
+        j = (uint32_t)(s - i * cap);
+        const uint32_t found = a.n_events[i];
+        valid = j < (found < (uint32_t)cap ? found : (uint32_t)cap);
+        if (valid) k = (uint32_t)__double_as_longlong(a.events[(size_t)s * R]);
+    }
+    unsigned mask = __ballot_sync(FULL_MASK, valid);
+    while (mask) {
+        const int lead = __ffs(mask) - 1;
+        const unsigned long long i_cur = __shfl_sync(FULL_MASK, i, lead);
+        const bool mine = valid && i == i_cur;
+        const unsigned same = __ballot_sync(FULL_MASK, mine);
+        if (mine) {
+            const unsigned rank = __popc(same & lanemask_lt());
+            pk[wid][rank] = k;
+            ps[wid][rank] = j;
+        }
+        __syncwarp();
+        Locate::flush(a, i_cur, (uint32_t)__popc(same), pk[wid], ps[wid], a.events + (size_t)i_cur * cap * R, lane);
+        __syncwarp();
+        mask &= ~same;
+    }
+}
+
 #ifndef __CUDACC_RTC__  // (runtime-compiled functors are launched through the driver API: rtc.cu)
 // host-side launcher of both queries for one right-hand side and one build flavour
+// the events kernel for this record width: wide records (1 + D > 8) stream through the TMA-staged kernel when every
+// path starts on a 16-byte boundary (an even capacity; hist itself is at least 32-byte aligned)
+template <class Rhs, bool STRICT, class Locate>
+int launch_path_events(bacon_path_args* a, unsigned blocks, cudaStream_t st, cudaFuncAttributes* fa) {
+    constexpr int R = 1 + Rhs::DIM;
+    static const bool no_tma = getenv("BACON_EV_NO_TMA") != nullptr;  // (A/B switch for measurements)
+    if constexpr (R > 8) {
+        const bool aligned = ((size_t)a->cfg.history_capacity * R) % 2 == 0 && (reinterpret_cast<uintptr_t>(a->hist) & 15u) == 0;
+        if (aligned && !no_tma) {
+            auto kernel = path_events_wide_kernel<Rhs, STRICT, Locate>;
+            constexpr size_t smem = evw_smem_bytes<R>();
+            if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return BACON_E_CUDA;
+            if (cudaFuncGetAttributes(fa, kernel) != cudaSuccess) return BACON_E_CUDA;
+            kernel<<<blocks, PATH_BLOCK, smem, st>>>(*a);
+            if constexpr (Locate::DEFERRED) {
+                const unsigned long long slots = (unsigned long long)a->n * (unsigned long long)a->ev_capacity;
+                const unsigned long long b2 = (slots + PATH_BLOCK - 1) / PATH_BLOCK;  // (a warp per 32 slots)
+                if (b2 > 0x7fffffffull) return BACON_E_BAD_ARGUMENT;
+                if (b2 > 0) path_locate_deferred_kernel<Locate><<<(unsigned)b2, PATH_BLOCK, 0, st>>>(*a);
+            }
+            return 0;
+        }
+    }
+    auto kernel = path_events_kernel<Rhs, STRICT, Locate>;
+    if (cudaFuncGetAttributes(fa, kernel) != cudaSuccess) return BACON_E_CUDA;
+    kernel<<<blocks, PATH_BLOCK, 0, st>>>(*a);
+    return 0;
+}
+
 template <class Rhs, bool STRICT> int launch_path_query(bacon_path_args* a) {
     static_assert(Rhs::DIM <= BACON_PATH_MAX_DIM, "event weights are passed by value");
     cudaStream_t st = (cudaStream_t)a->stream;
@@ -482,11 +713,9 @@ template <class Rhs, bool STRICT> int launch_path_query(bacon_path_args* a) {
         if (blocks == 0 || blocks > 0x7fffffffull) return BACON_E_BAD_ARGUMENT;
         kernel<<<(unsigned)blocks, PATH_BLOCK, 0, st>>>(*a);
     } else if (a->op == BACON_PATH_EVENTS) {
-        auto kernel = path_events_kernel<Rhs, STRICT>;
-        if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return BACON_E_CUDA;
         blocks = (a->n * 32 + PATH_BLOCK - 1) / PATH_BLOCK;
         if (blocks == 0 || blocks > 0x7fffffffull) return BACON_E_BAD_ARGUMENT;
-        kernel<<<(unsigned)blocks, PATH_BLOCK, 0, st>>>(*a);
+        if (const int rc = launch_path_events<Rhs, STRICT, LaneLocate<Rhs>>(a, (unsigned)blocks, st, &fa)) return rc;
     } else {
         return BACON_E_BAD_ARGUMENT;
     }

@@ -42,6 +42,48 @@ __device__ __forceinline__ double warp_matvec32(const double (&A)[32], double y_
     return s;
 }
 
+// The same sums for both knots of an interval at once: the two chains are independent, so their shuffles and FMAs
+// interleave and the 32 dependent steps are walked once instead of twice (each sum keeps its own order, so its bits).
+__device__ __forceinline__ void warp_matvec32_pair(const double (&A)[32], double ya, double yb, double& fa, double& fb) {
+    double sa = A[0] * __shfl_sync(FULL_MASK, ya, 0), sb = A[0] * __shfl_sync(FULL_MASK, yb, 0);
+#pragma unroll
+    for (int k = 1; k < 32; ++k) {
+        sa += A[k] * __shfl_sync(FULL_MASK, ya, k);
+        sb += A[k] * __shfl_sync(FULL_MASK, yb, k);
+    }
+    fa = sa;
+    fb = sb;
+}
+// f = A y and w . y for both knots: one broadcast of y_k feeds both sums
+__device__ __forceinline__ void warp_matvec_dot32_pair(const bacon_path_args& a, const double (&A)[32], double ya, double yb,
+                                                       double& fa, double& fb, double& wa, double& wb) {
+    double ya_k = __shfl_sync(FULL_MASK, ya, 0), yb_k = __shfl_sync(FULL_MASK, yb, 0);
+    double sa = A[0] * ya_k, sb = A[0] * yb_k, da = a.ev_w[0] * ya_k, db = a.ev_w[0] * yb_k;
+#pragma unroll
+    for (int k = 1; k < 32; ++k) {
+        ya_k = __shfl_sync(FULL_MASK, ya, k);
+        yb_k = __shfl_sync(FULL_MASK, yb, k);
+        sa += A[k] * ya_k;
+        sb += A[k] * yb_k;
+        da += a.ev_w[k] * ya_k;
+        db += a.ev_w[k] * yb_k;
+    }
+    fa = sa;
+    fb = sb;
+    wa = da;
+    wb = db;
+}
+__device__ __forceinline__ void warp_seqdot32_pair(const bacon_path_args& a, double va, double vb, double& wa, double& wb) {
+    double da = a.ev_w[0] * __shfl_sync(FULL_MASK, va, 0), db = a.ev_w[0] * __shfl_sync(FULL_MASK, vb, 0);
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        da += a.ev_w[d] * __shfl_sync(FULL_MASK, va, d);
+        db += a.ev_w[d] * __shfl_sync(FULL_MASK, vb, d);
+    }
+    wa = da;
+    wb = db;
+}
+
 // w . v over the lanes, sequential in d like event_fn; every lane gets the sum
 __device__ __forceinline__ double warp_seqdot32(const bacon_path_args& a, double v_lane) {
     double s = a.ev_w[0] * __shfl_sync(FULL_MASK, v_lane, 0);
@@ -93,7 +135,8 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __
     }
     double A[32];
     load_matrix_row32(a, i, lane, A);
-    // phase 2: the warp interpolates them one after the other
+    // phase 2: the warp interpolates them one after the other.  (Requesting the knots of sample l + 1 before sample l is
+    // computed was measured slower: 3.90 -> 4.85 ms on config 4, the extra live rows cost more than the overlap gains.)
 #pragma unroll 2
     for (unsigned l = 0; l < n_here; ++l) {
         const double tau = __shfl_sync(FULL_MASK, my_tau, l);
@@ -105,7 +148,8 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __
         }
         const double ta = pv.time(lo - 1), tb = pv.time(lo);
         const double ya[1] = {knot_component32(pv, lo - 1, lane)}, yb[1] = {knot_component32(pv, lo, lane)};
-        const double fa[1] = {warp_matvec32(A, ya[0])}, fb[1] = {warp_matvec32(A, yb[0])};
+        double fa[1], fb[1];
+        warp_matvec32_pair(A, ya[0], yb[0], fa[0], fb[0]);
         const double h = tb - ta;
         const double th = h > 0.0 ? (tau - ta) / h : 0.0;
         double res[1];
@@ -116,6 +160,10 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __
 
 // the queue of crossings of one trajectory, located by the whole warp one after the other
 template <bool STRICT> struct WarpLocateLinear32 {
+    static constexpr int DIM = 32;
+    // with the TMA-staged streaming kernel (path_query.cuh: path_events_wide_kernel) the crossings are located by a
+    // second kernel, one warp per crossing, instead of one after the other at the end of each path
+    static constexpr bool DEFERRED = true;
     static __device__ __noinline__ void flush(const bacon_path_args& a, unsigned long long i, uint32_t n_pend, const uint32_t* pk,
                                               const uint32_t* ps, double* ev, unsigned lane) {
         const PathView<32> pv(a, i);
@@ -127,10 +175,11 @@ template <bool STRICT> struct WarpLocateLinear32 {
             double* dst = ev + (size_t)ps[e] * 33;
             const double ta = pv.time(k - 1), tb = pv.time(k);
             const double ya[1] = {knot_component32(pv, k - 1, lane)}, yb[1] = {knot_component32(pv, k, lane)};
-            const double fa[1] = {warp_matvec32(A, ya[0])}, fb[1] = {warp_matvec32(A, yb[0])};
+            double fa[1], fb[1], wa, wb, da, db;
+            warp_matvec_dot32_pair(a, A, ya[0], yb[0], fa[0], fb[0], wa, wb);
+            warp_seqdot32_pair(a, fa[0], fb[0], da, db);
             const double h = tb - ta;
-            const double ga = warp_seqdot32(a, ya[0]) - a.ev_c, gb = warp_seqdot32(a, yb[0]) - a.ev_c;
-            const double da = warp_seqdot32(a, fa[0]), db = warp_seqdot32(a, fb[0]);
+            const double ga = wa - a.ev_c, gb = wb - a.ev_c;
             const double th = hermite_root(ga, gb, h * da, h * db);
             double ys[1];
             hermite_eval<1>(th, h, ya, yb, fa, fb, ys);
@@ -151,11 +200,9 @@ template <bool STRICT> int launch_path_query_linear32(bacon_path_args* a) {
         if (blocks == 0 || blocks > 0x7fffffffull) return BACON_E_BAD_ARGUMENT;
         kernel<<<(unsigned)blocks, PATH_BLOCK, 0, st>>>(*a);
     } else if (a->op == BACON_PATH_EVENTS) {
-        auto kernel = path_events_kernel<RhsLinear<32>, STRICT, WarpLocateLinear32<STRICT>>;
-        if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return BACON_E_CUDA;
         blocks = (a->n * 32 + PATH_BLOCK - 1) / PATH_BLOCK;
         if (blocks == 0 || blocks > 0x7fffffffull) return BACON_E_BAD_ARGUMENT;
-        kernel<<<(unsigned)blocks, PATH_BLOCK, 0, st>>>(*a);
+        if (const int rc = launch_path_events<RhsLinear<32>, STRICT, WarpLocateLinear32<STRICT>>(a, (unsigned)blocks, st, &fa)) return rc;
     } else {
         return BACON_E_BAD_ARGUMENT;
     }

@@ -125,6 +125,9 @@ def main():
         totals = shard.reduce_stats_device(out["n_accept"], out["n_reject"], out["n_rhs"], out["status"])
         torch.cuda.synchronize()
         dist.barrier()
+    from bench import ClockSampler
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
     for k in range(args.steps):
         flush.fill_(k)
         if world > 1:
@@ -139,6 +142,8 @@ def main():
             totals = shard.reduce_stats_device(out["n_accept"], out["n_reject"], out["n_rhs"], out["status"])
         ev[k][1].record()
     torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
     kms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
     if world > 1:
@@ -174,7 +179,8 @@ def main():
             + (f", dense output capacity {hist}" if hist else "") + (", Newton+LU" if flags & _abi.FLAG_BDF_NEWTON else ""),
             "metric": "accepted f64 trajectory-steps/sec", "unit": "trajectory-steps/s", "n_gpus": world,
             "scaling": "strong", "trajectories_per_gpu": n, "n": n_glob, "dtype": "f64", "data": "synthetic",
-            "grid": launch["grid"], "block": launch["block"], "regs_per_thread": launch["regs_per_thread"]}
+            "grid": launch["grid"], "block": launch["block"], "regs_per_thread": launch["regs_per_thread"],
+            "clocks": sampler.summary()}
     if world > 1:
         tot_acc, tot_rej, tot_rhs = acc_all, rej_all, nrhs_all
         line.update({"value": acc_all / (ms * 1e-3), "ms_per_pass": ms, "kernel_ms_max_over_ranks": kms,
