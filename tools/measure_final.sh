@@ -11,3 +11,5 @@ PY
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_ref.json 2>/dev/null; cut -c1-260 gpurun_out/${T}_bench_ref.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${T}.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu1.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+# one full ncu capture of the headline kernel (read here with profiles/summarize_ncu.py)
+ncu --set full --clock-control none --import-source on -k regex:ensemble_kernel -s 3 -c 1 -o gpurun_out/prof_rk45_${T} -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu2.log 2>&1
