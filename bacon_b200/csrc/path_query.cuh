@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_LOCATE_MINB) path_locate_def
 template <class Rhs, bool STRICT, class Locate>
 int launch_path_events(bacon_path_args* a, unsigned blocks, cudaStream_t st, cudaFuncAttributes* fa) {
     constexpr int R = 1 + Rhs::DIM;
-    static const bool no_tma = getenv("BACON_EV_NO_TMA") != nullptr;  // (A/B switch for measurements)
+    const bool no_tma = getenv("BACON_EV_NO_TMA") != nullptr;  // (A/B switch for measurements and tests; read per call)
     if constexpr (R > 8) {
         const bool aligned = ((size_t)a->cfg.history_capacity * R) % 2 == 0 && (reinterpret_cast<uintptr_t>(a->hist) & 15u) == 0;
         if (aligned && !no_tma) {

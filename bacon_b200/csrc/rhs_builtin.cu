@@ -22,8 +22,9 @@ BACON_REGISTER_RHS(RhsCos, "cos");
 BACON_REGISTER_RHS(RhsHarmonic, "harmonic");
 BACON_REGISTER_RHS(RhsLinear<4>, "linear4");
 
-#if !defined(BACON_SKIP_RK) && !defined(BACON_ONLY_EVENTS)
-// linear32 (BASELINE config 4): warp-per-trajectory kernels (rk_warp_linear.cuh)
+#if !defined(BACON_SKIP_RK)
+// linear32 (BASELINE config 4): warp-per-trajectory kernels (rk_warp_linear.cuh).  The plain kernels and the path
+// queries live in the plain objects, the kernels that watch a terminal event in the event objects (Makefile).
 namespace {
 int register_linear32() {
     bacon_rhs_desc d{};
@@ -31,13 +32,18 @@ int register_linear32() {
     d.dim = 32;
     d.n_params = 32 * 32;
 #ifdef BACON_STRICT_FP
-    d.launch[1][BACON_RK45] = d.launch_event[1][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, true>;
-    d.launch[1][BACON_RK23] = d.launch_event[1][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, true>;
-    d.path_query[1] = &launch_path_query_linear32<true>;
+    constexpr int S = 1;
 #else
-    d.launch[0][BACON_RK45] = d.launch_event[0][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, false>;
-    d.launch[0][BACON_RK23] = d.launch_event[0][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, false>;
-    d.path_query[0] = &launch_path_query_linear32<false>;
+    constexpr int S = 0;
+#endif
+#ifndef BACON_ONLY_EVENTS
+    d.launch[S][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, S != 0>;
+    d.launch[S][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, S != 0>;
+    d.path_query[S] = &launch_path_query_linear32<S != 0>;
+#endif
+#ifndef BACON_SKIP_EVENTS
+    d.launch_event[S][BACON_RK45] = &launch_rk_warp_linear32<TabRKF45, S != 0, true>;
+    d.launch_event[S][BACON_RK23] = &launch_rk_warp_linear32<TabBS23, S != 0, true>;
 #endif
     return bacon_rhs_register(&d);
 }

@@ -13,6 +13,7 @@
 // Same reference statements as rk_fast.cuh / rk_strict.cuh (src/ivp/rk.rs:361-423).
 #pragma once
 #include "ivp_common.cuh"
+#include "path_query.cuh"
 #include "rk_fast.cuh"
 #include "rk_strict.cuh"
 #include "tableaux.cuh"
@@ -21,7 +22,10 @@ namespace bacon {
 
 constexpr int WARP_BLOCK = 128;  // 4 warps = 4 trajectories in flight per CTA
 
-template <class Tab, bool STRICT, bool HIST, int MINB>
+// EVENT: the instantiation that watches a terminal event (bacon_ivp_options::event_w; drive.cuh has the thread-per-
+// trajectory form): g = w . y summed over the lanes in the oracle's order on every accepted point, the crossing located
+// on the Hermite cubic of that step with f = A y at both ends, all of it warp-uniform.
+template <class Tab, bool STRICT, bool HIST, int MINB, bool EVENT = false>
 __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(const __grid_constant__ bacon_launch_args a) {
     constexpr int N = 32;
     constexpr int O = Tab::O;
@@ -106,6 +110,16 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
         double k[O];  // strict: half_steps (k_j = f_j*dt, persistent); fast: unscaled f_j
 #pragma unroll
         for (int j = 0; j < O; ++j) k[j] = 0.0;
+        // terminal event: the last knot (knot 0 = the initial condition)
+        auto g_of = [&](double y_lane) -> double {  // w . y - c, sequential in d like the oracle; every lane gets it
+            double s = a.ev_w[0] * __shfl_sync(FULL_MASK, y_lane, 0);
+#pragma unroll
+            for (int d = 1; d < N; ++d) s += a.ev_w[d] * __shfl_sync(FULL_MASK, y_lane, d);
+            return s - a.ev_c;
+        };
+        [[maybe_unused]] double ev_tp = t, ev_yp = y, ev_gp = 0.0;
+        const bool ev_on = EVENT && a.ev_on != 0;  // (a launch with only a restart record runs these kernels too)
+        if (ev_on) ev_gp = g_of(y);
 
         while (st < 0) {
             if (n_att >= cap) { st = BACON_E_MAX_ATTEMPTS; break; }
@@ -188,6 +202,32 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
                 st = BACON_E_MIN_DT_EXCEEDED;
                 break;
             }
+            if constexpr (EVENT) {
+                if (accepted && ev_on) {
+                    const double gb = g_of(y);
+                    if (event_crossing(ev_gp, gb, a.ev_direction)) {  // rare: the trajectory ends at the crossing
+                        const double fa[1] = {matvec(A, ev_yp)}, fb[1] = {matvec(A, y)};
+                        const double hh = t - ev_tp;
+                        double da = a.ev_w[0] * __shfl_sync(FULL_MASK, fa[0], 0), db = a.ev_w[0] * __shfl_sync(FULL_MASK, fb[0], 0);
+#pragma unroll
+                        for (int d = 1; d < N; ++d) {
+                            da += a.ev_w[d] * __shfl_sync(FULL_MASK, fa[0], d);
+                            db += a.ev_w[d] * __shfl_sync(FULL_MASK, fb[0], d);
+                        }
+                        const double th = hermite_root(ev_gp, gb, hh * da, hh * db);
+                        const double ya[1] = {ev_yp}, yb[1] = {y};
+                        double ye[1];
+                        hermite_eval<1>(th, hh, ya, yb, fa, fb, ye);
+                        y = ye[0];
+                        t = ev_tp + th * hh;
+                        st = BACON_STOPPED_AT_EVENT;  // (the point that crossed is not yielded)
+                        break;
+                    }
+                    ev_gp = gb;
+                    ev_tp = t;
+                    ev_yp = y;
+                }
+            }
             if (accepted) {
                 if (HIST && n_acc < hcap) {  // the yielded point (rk.rs:418-419): one coalesced row
                     const size_t row = (size_t)idx * hcap + n_acc;
@@ -235,8 +275,7 @@ template <class K> inline int launch_persistent_warp(K kernel, bacon_launch_args
     return cudaGetLastError() == cudaSuccess ? 0 : BACON_E_CUDA;
 }
 
-template <class Tab, bool STRICT> int launch_rk_warp_linear32(bacon_launch_args* a) {
-    if (a->ev_on) return BACON_E_UNSUPPORTED;  // (no terminal events in the warp-per-trajectory kernels; restart records: yes)
+template <class Tab, bool STRICT, bool EVENT = false> int launch_rk_warp_linear32(bacon_launch_args* a) {
     if (STRICT) {
         RkTableauRt T;
         fill_runtime_tableau<Tab>(T, a->cfg.semantics == BACON_SEM_LITERAL);
@@ -246,9 +285,16 @@ template <class Tab, bool STRICT> int launch_rk_warp_linear32(bacon_launch_args*
     } else if (a->cfg.semantics != BACON_SEM_CORRECTED) {
         return BACON_E_UNSUPPORTED;
     }
-    if (a->cfg.history_capacity > 0 && a->out.hist)
-        return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, true, 4>, a);
-    return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, false, 4>, a);
+    if constexpr (EVENT) {
+        if (a->cfg.history_capacity > 0 && a->out.hist)
+            return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, true, 4, true>, a);
+        return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, false, 4, true>, a);
+    } else {
+        if (a->ev_on) return BACON_E_UNSUPPORTED;
+        if (a->cfg.history_capacity > 0 && a->out.hist)
+            return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, true, 4>, a);
+        return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, false, 4>, a);
+    }
 }
 
 }  // namespace bacon

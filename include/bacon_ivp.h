@@ -69,7 +69,7 @@ typedef enum bacon_status {
     BACON_E_HISTORY_OVERFLOW = 15,   /* more accepted points than history_capacity */
     BACON_E_CUDA = 16,               /* CUDA runtime error; see bacon_last_error() */
     BACON_E_BAD_ARGUMENT = 17,       /* NULL pointer, unknown rhs/method, dim mismatch */
-    BACON_E_UNSUPPORTED = 18,        /* combination not built (e.g. terminal events for linear32) */
+    BACON_E_UNSUPPORTED = 18,        /* combination not built (e.g. REF_LITERAL with the Newton BDF)  */
     BACON_STOPPED_AT_EVENT = 19      /* per-trajectory, not an error: the integration stopped at a terminal event
                                         (bacon_ivp_options::event_w); t_end / y_end are the event point */
 } bacon_status;

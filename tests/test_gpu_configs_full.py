@@ -129,3 +129,126 @@ def test_nccl_gather_records_matches_single_gpu(cuda, engine, tmp_path, n_global
         st = rec["stats"]
         assert st[0] == full.n_accept.sum() and st[1] == full.n_reject.sum() and st[2] == full.n_rhs.sum()
         assert st[3] == 0 and st[4] == 2.0
+
+
+# ---------------------------------------------------------------- BASELINE.json's full sizes: size-independent properties
+def _device_solve(torch, solver, y0, par, **kw):
+    dev = "cuda:0"
+    d_y0 = torch.from_numpy(np.ascontiguousarray(y0)).to(dev)
+    d_par = torch.from_numpy(np.ascontiguousarray(par)).to(dev)
+    out = solver.solve_ivp_ensemble_device(d_y0, d_par, **kw)
+    torch.cuda.synchronize()
+    return d_y0, d_par, out
+
+
+@pytest.mark.timeout(900, method="thread")
+def test_config3_full_size_properties(cuda, engine, oracle):
+    """Config 3 at its full size (2^22 trajectories): every trajectory reaches t_end, a second run gives the same bits
+    (idempotence: the result does not depend on which lane ran what), and a sample spread over the mu-sweep is inside
+    the band against the oracle."""
+    torch = cuda
+    w = E.VDP
+    n = w["n"]
+    assert n == 1 << 22
+    y0, mu = E.vdp_problem(np.arange(n), n)
+    s = make_solver(engine, "RK23", 2, rhs="vdp", dt_min=w["dt_min"], dt_max=w["dt_max"], tol=w["tol"],
+                    t_start=w["t_start"], t_end=w["t_end"])
+    d_y0, d_mu, a = _device_solve(torch, s, y0, mu)
+    assert int((a["status"] != 0).sum().item()) == 0
+    assert bool((a["t_end"] == w["t_end"]).all().item())
+    ya = a["y_end"].clone()
+    acc = a["n_accept"].clone()
+    b = s.solve_ivp_ensemble_device(d_y0, d_mu)
+    torch.cuda.synchronize()
+    assert torch.equal(ya.view(torch.int64), b["y_end"].view(torch.int64)) and torch.equal(acc, b["n_accept"])
+    sel = np.linspace(0, n - 1, 2048).astype(np.int64)
+    ref = oracle.solve_ensemble(_abi.RK23, "vdp", y0[:, sel], mu[:, sel], dt_min=w["dt_min"], dt_max=w["dt_max"],
+                                tol=w["tol"], t_start=w["t_start"], t_end=w["t_end"])
+    g = ya[:, torch.from_numpy(sel).to(ya.device)].cpu().numpy()
+    assert rel_err(g, ref["y_end"]).max() <= band(w["tol"])
+    a64 = acc.to(torch.int64)
+    assert int(a64.max().item()) > 6 * int(a64.min().item())
+
+
+@pytest.mark.timeout(900, method="thread")
+def test_config5_full_size_properties(cuda, engine, oracle):
+    """Config 5 at its full size (2^20 Robertson trajectories, BDF6 with the batched Newton LU): all reach t_end, mass is
+    conserved (y1 + y2 + y3 = 1 is an invariant of the kinetics and of every linear multistep method up to rounding),
+    bitwise idempotent, sample inside the band."""
+    torch = cuda
+    w = E.ROBERTSON
+    n = w["n"]
+    assert n == 1 << 20
+    y0, k = E.robertson_problem(np.arange(n))
+    s = make_solver(engine, "BDF6", 3, rhs="robertson", flags=_abi.FLAG_BDF_NEWTON, dt_min=w["dt_min"], dt_max=w["dt_max"],
+                    tol=w["tol"], t_start=w["t_start"], t_end=w["t_end"])
+    d_y0, d_k, a = _device_solve(torch, s, y0, k)
+    assert int((a["status"] != 0).sum().item()) == 0
+    assert float((a["t_end"] - w["t_end"]).abs().max().item()) <= 1e-12
+    mass = a["y_end"].sum(dim=0)
+    assert float((mass - 1.0).abs().max().item()) < 1e-9
+    ya = a["y_end"].clone()
+    b = s.solve_ivp_ensemble_device(d_y0, d_k)
+    torch.cuda.synchronize()
+    assert torch.equal(ya.view(torch.int64), b["y_end"].view(torch.int64))
+    sel = np.linspace(0, n - 1, 1024).astype(np.int64)
+    ref = oracle.solve_ensemble(_abi.BDF6, "robertson", y0[:, sel], k[:, sel], bdf_newton=True, dt_min=w["dt_min"],
+                                dt_max=w["dt_max"], tol=w["tol"], t_start=w["t_start"], t_end=w["t_end"])
+    g = ya[:, torch.from_numpy(sel).to(ya.device)].cpu().numpy()
+    assert rel_err(g, ref["y_end"]).max() <= band(w["tol"])
+
+
+@pytest.mark.timeout(900, method="thread")
+def test_config4_full_size_properties(cuda, engine, oracle):
+    """Config 4 at its full size (2^18 trajectories, 2 GiB of per-trajectory matrices, dense output of capacity 256): all
+    reach t_end, every stored path is as long as its step count and strictly increasing in time up to t_end, the end of
+    the path is the final state, a sample agrees with the matrix exponential, and the events query over the 8.5 GB of
+    264-byte records (TMA-staged kernel + deferred location) agrees with the one-lane-per-record kernel bit for bit."""
+    from scipy.linalg import expm
+    torch = cuda
+    w = E.LINEAR32
+    n = w["n"]
+    assert n == 1 << 18
+    chunks = [E.linear32_problem(np.arange(c, min(c + (1 << 15), n))) for c in range(0, n, 1 << 15)]
+    y0 = np.concatenate([c[0] for c in chunks], axis=1)
+    A = np.concatenate([c[1] for c in chunks], axis=0).reshape(n, 1024)
+    del chunks
+    cap = w["history_capacity"]
+    s = make_solver(engine, "RK45", 32, rhs="linear32", dt_min=w["dt_min"], dt_max=w["dt_max"], tol=w["tol"],
+                    t_start=w["t_start"], t_end=w["t_end"], history=cap)
+    d_y0, d_A, a = _device_solve(torch, s, y0, A, params_aos=True)
+    assert int((a["status"] != 0).sum().item()) == 0 and bool((a["t_end"] == w["t_end"]).all().item())
+    acc = a["n_accept"].to(torch.int64)
+    assert torch.equal(a["hist_len"].to(torch.int64), acc) and int(acc.max().item()) <= cap
+    ht = a["hist_t"]
+    idx = torch.arange(cap, device=ht.device)[None, :]
+    valid = idx < acc[:, None]
+    inc = (ht[:, 1:] > ht[:, :-1]) | ~valid[:, 1:]
+    assert bool(inc.all().item())
+    last = torch.gather(a["hist"], 1, (acc - 1).clamp(min=0)[:, None, None].expand(-1, 1, 33))[:, 0]
+    assert bool((last[:, 0] == w["t_end"]).all().item())
+    assert torch.equal(last[:, 1:].t().contiguous().view(torch.int64), a["y_end"].view(torch.int64))
+    sel = np.linspace(0, n - 1, 48).astype(np.int64)
+    ye = a["y_end"][:, torch.from_numpy(sel).to(ht.device)].cpu().numpy()
+    for j, i in enumerate(sel):
+        want = expm(A[i].reshape(32, 32) * (w["t_end"] - w["t_start"])) @ y0[:, i]
+        assert np.linalg.norm(ye[:, j] - want) <= 1e-6 * max(np.linalg.norm(want), 1e-3), (i, np.linalg.norm(ye[:, j] - want))
+    wv = np.zeros(32)
+    wv[0] = 1.0
+    ev1, c1 = s.locate_events_device(d_y0, d_A, a, wv, 0.0, 0, 4, params_aos=True)
+    torch.cuda.synchronize()
+    os.environ["BACON_EV_NO_TMA"] = "1"  # the round-1 kernel (one lane per record, located inside the stream)
+    try:
+        ev2, c2 = s.locate_events_device(d_y0, d_A, a, wv, 0.0, 0, 4, params_aos=True)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["BACON_EV_NO_TMA"]
+    assert torch.equal(c1, c2) and torch.equal(ev1.view(torch.int64), ev2.view(torch.int64))
+    assert int(c1.sum().item()) > n // 2
+    k = torch.minimum(c1.to(torch.int64), torch.tensor(4, device=c1.device))
+    t_ev = ev1[:, :, 0]
+    ok = (torch.arange(4, device=c1.device)[None, :] >= k[:, None]) | ((t_ev > w["t_start"]) & (t_ev <= w["t_end"]))
+    assert bool(ok.all().item())
+    g_ev = ev1[:, :, 1]  # y[0] at the event: on the surface
+    on = (torch.arange(4, device=c1.device)[None, :] >= k[:, None]) | (g_ev.abs() < 1e-9)
+    assert bool(on.all().item())

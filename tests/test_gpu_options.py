@@ -246,14 +246,37 @@ def test_terminal_event_closed_form_and_fast_kernels(cuda, engine, oracle):
     assert (g.status == _abi.STOPPED_AT_EVENT).sum() > n // 3
 
 
-def test_terminal_event_unsupported_for_linear32_and_bad_direction(cuda, engine):
-    z0, A = E.linear32_problem(np.arange(4))
-    A = A.reshape(4, 1024)
-    s = make_solver(engine, "RK45", 32, rhs="linear32", dt_min=1e-6, dt_max=0.05, tol=1e-8, t_start=0.0, t_end=0.1) \
-        .with_terminal_event(np.ones(32), 0.0, 0)
-    with pytest.raises(engine.IVPError) as e:
-        s.solve_ivp_ensemble(z0, A, params_aos=True)
-    assert e.value.variant == "Unsupported"
+def test_terminal_event_linear32_warp_kernels(cuda, engine, oracle):
+    """The warp-per-trajectory kernels of config 4 watch the event too: strict build bit-exact with the oracle's
+    statement (event point, counters, the path before it), the fast build inside the band; y[0] = 0, every direction."""
+    m = 96
+    z0, A = E.linear32_problem(np.arange(m))
+    A = A.reshape(m, 1024)
+    lin = dict(dt_min=1e-7, dt_max=0.05, tol=1e-8, t_start=0.0, t_end=4.0)
+    w = np.zeros(32)
+    w[0], w[5] = 1.0, -0.5
+    for direction in (0, 1, -1):
+        s = make_solver(engine, "RK45", 32, rhs="linear32", flags=_abi.FLAG_STRICT_FP, history=300, **lin) \
+            .with_terminal_event(w, 0.01, direction)
+        gpu = s.solve_ivp_ensemble(z0, A, params_aos=True)
+        ref = oracle.solve_ensemble(_abi.RK45, "linear32", z0, A, params_aos=True, pow_mode=1, history_capacity=300,
+                                    event=(w, 0.01, direction), **lin)
+        _bit_exact(gpu, ref)
+        np.testing.assert_array_equal(gpu.hist_len, ref["hist_len"])
+        stopped = gpu.status == _abi.STOPPED_AT_EVENT
+        assert stopped.sum() > m // 3 and set(np.unique(gpu.status)) <= {_abi.OK, _abi.STOPPED_AT_EVENT}
+        assert np.abs(w @ gpu.y_end[:, stopped] - 0.01).max() < 1e-10
+        for i in np.flatnonzero(stopped)[:4]:
+            k = int(gpu.hist_len[i])
+            _same_bits(gpu.hist[i, :k], ref["hist"][i, :k], f"path {i}")
+        fast = make_solver(engine, "RK45", 32, rhs="linear32", **lin).with_terminal_event(w, 0.01, direction) \
+            .solve_ivp_ensemble(z0, A, params_aos=True)
+        ref_f = oracle.solve_ensemble(_abi.RK45, "linear32", z0, A, params_aos=True, event=(w, 0.01, direction), **lin)
+        np.testing.assert_array_equal(fast.status, ref_f["status"])
+        assert rel_err(fast.y_end, ref_f["y_end"]).max() <= band(1e-8) and np.abs(fast.t_end - ref_f["t_end"]).max() < 1e-7
+
+
+def test_terminal_event_bad_direction(cuda, engine):
     with pytest.raises(engine.IVPError):
         make_solver(engine, "RK45", 3, rhs="lorenz", t_end=1.0, **LOR).with_terminal_event([0, 0, 1.0], 0.0, 2)
 
