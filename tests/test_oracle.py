@@ -321,3 +321,16 @@ def test_path_queries_against_scipy_dense_output_and_events(oracle):
         assert cnt[i] == want.size
         assert np.abs(ev[i, :want.size, 0] - want).max() < 1e-9  # (measured 9e-12)
         assert np.abs(ev[i, :want.size, 3] - 27.0).max() < 1e-10
+
+
+def test_oracle_is_clean_under_sanitizers():
+    """the reference is safe Rust; its C++ restatement is at least clean under AddressSanitizer and
+    UndefinedBehaviorSanitizer on every stepper family, both semantics, dense output below and above the capacity, the
+    optional inputs and the path queries (oracle/selftest.cpp)."""
+    import os
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    subprocess.run(["make", "-C", here, "_selftest"], check=True, capture_output=True)
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", OMP_NUM_THREADS="2")
+    r = subprocess.run([os.path.join(here, "_selftest")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "selftest ok" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
