@@ -8,8 +8,9 @@
 // Divergent trajectory lengths: what diverges is the END of a trajectory.  A lane
 // whose trajectory retired (Done / Failure) stores its record and re-arms itself
 // with the next trajectory index from the global work counter, so a warp only
-// idles lanes once the whole ensemble has been handed out.  What is left of the
-// tail is suspended and re-dealt by a second kernel (below).
+// idles lanes once the whole ensemble has been handed out.  What is left then is
+// regrouped inside the kernel: the CTA's trajectories change lanes through shared
+// memory so that half-empty warps fold away (ensemble_kernel, below).
 #pragma once
 #include "hist_stage.cuh"
 #include "ivp_common.cuh"

@@ -314,7 +314,7 @@ template <class Rhs, class Tab> struct RkFastStepper {
         return -1;
     }
 
-    // suspend / resume (tail compaction, drive.cuh): everything that belongs to the trajectory
+    // suspend / resume (end-of-ensemble regrouping, drive.cuh): everything that belongs to the trajectory
     static constexpr int STATE_DOUBLES = D + (P > 0 ? P : 0) + 3;
     __device__ __forceinline__ double remaining() const { return t_end - t; }
     __device__ __forceinline__ void save(double (&st)[STATE_DOUBLES + 1]) const {

@@ -137,7 +137,8 @@ def test_fast_vdp_mu_sweep_within_band(cuda, engine, oracle):
 
 
 def test_dense_output_matches_oracle_path(cuda, engine, oracle):
-    """K4: every accepted (t, y) of every trajectory, staged through shared memory."""
+    """K4: every accepted (t, y) of every trajectory, one record per accepted point written straight to the
+    trajectory-major history (one 256-bit store for D = 3; no staging: profiles/r01i_dense_output.md)."""
     n = 3000  # not a multiple of the block size; refill + partial flushes
     y0 = E.lorenz_y0(np.arange(n))
     for strict in (True, False):
