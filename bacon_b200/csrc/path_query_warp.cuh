@@ -122,13 +122,7 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __
     if (lane < n_here) {
         my_tau = a.times[j0 + lane];
         if (K > 0 && my_tau >= pv.t0 && my_tau <= t_last) {
-            uint32_t lo = 1, hi = K;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (pv.time(mid) >= my_tau) hi = mid;
-                else lo = mid + 1;
-            }
-            my_lo = lo;
+            my_lo = pv.first_knot_at_or_after(my_tau, K, t_last);
         } else if (my_tau == pv.t0) {
             my_lo = ~0u;
         }
