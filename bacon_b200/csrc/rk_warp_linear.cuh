@@ -1,10 +1,10 @@
 // rk_warp_linear.cuh — K5: wide-state variant of the RK stepper for y' = A y with a
 // per-trajectory dense A (BASELINE config 4: D = 32, dense output).  7 x 32 doubles of
 // stepper state plus a 32 x 32 matrix cannot live in one thread, so ONE WARP integrates
-// one trajectory: lane i owns row i of A (32 doubles in registers), component i of y and
-// of every stage derivative.  The stage vector is exchanged through a 256-byte shared
-// buffer per warp (one conflict-free STS.64 per lane, then 16 broadcast LDS.128), so a
-// right-hand side costs 32 DFMA per lane = exactly the 2*32*32 algorithmic flops.
+// one trajectory: lane i owns component i of y and of every stage derivative and 32 entries of A in registers (strict
+// build: row i; fast build: half of row i and half of row i ^ 16, see matvec below).  The stage vector is exchanged
+// through a 256-byte shared buffer per warp (one conflict-free STS.64 per lane, then 16 broadcast LDS.128 — 8 per
+// half-warp in the fast build), so a right-hand side costs 32 DFMA per lane = exactly the 2*32*32 algorithmic flops.
 // The controller (error norm, accept, dt) is warp-uniform: every lane holds the same
 // t, dt and counters, the norm is an xor-shuffle tree (fast) or the oracle's sequential
 // sum (strict).  Dense output needs no staging here: an accepted point is one coalesced
@@ -21,6 +21,9 @@
 namespace bacon {
 
 constexpr int WARP_BLOCK = 128;  // 4 warps = 4 trajectories in flight per CTA
+#ifndef LIN32_MINB
+#define LIN32_MINB 4  // resident CTAs per SM the plain kernels are compiled for (128 registers)
+#endif
 
 // EVENT: the instantiation that watches a terminal event (bacon_ivp_options::event_w; drive.cuh has the thread-per-
 // trajectory form): g = w . y summed over the lanes in the oracle's order on every accepted point, the crossing located
@@ -47,13 +50,21 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
     const bool shared = (a.cfg.flags & BACON_FLAG_SHARED_PARAMS) != 0;
     [[maybe_unused]] const RkTableauRt& c_rk_tab = c_rk_tabs[rk_tab_slot(O, a.cfg.semantics)];  // (strict only)
 
-    // y' = A y : dy_i = sum_j A[i][j] Y[j], Y broadcast from shared memory
+    // y' = A y : dy_i = sum_j A[i][j] Y[j], Y broadcast from shared memory.
+    // Strict build: lane i holds row i and sums it in the oracle's order.  Fast build: lane (h, r) = (lane >> 4,
+    // lane & 15) holds the column half h of its own row r + 16 h (A[0..15]) and of its partner's row r + 16 (1 - h)
+    // (A[16..31]), so it needs 16 values of Y instead of 32, and each of them feeds two DFMA.  The kernel is bound by the shared-memory data pipe, not by the FP64 pipe
+    // (ncu: l1tex__data_pipe_lsu_wavefronts 91 % busy with the row layout, profiles/r04d_cfg4_source.md): a broadcast
+    // LDS.128 takes two wavefronts, and it still takes two when each HALF-warp reads its own address
+    // (tools/lds_pattern_probe.cu) — 16 wavefronts per product instead of 32.  The two halves of a row are joined by one
+    // 64-bit shuffle with lane ^ 16; every lane ends up with component `lane` as before.
+    const unsigned half = lane >> 4;
     auto matvec = [&](const double (&A)[N], double Yi) -> double {
         __syncwarp();
         sy[lane] = Yi;
         __syncwarp();
-        const double2* v = reinterpret_cast<const double2*>(sy);
         if constexpr (STRICT) {  // the oracle's order: s = A[i][0]*y[0]; s += A[i][j]*y[j]
+            const double2* v = reinterpret_cast<const double2*>(sy);
             double s = 0.0;
 #pragma unroll
             for (int j2 = 0; j2 < N / 2; ++j2) {
@@ -62,18 +73,25 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
                 s = __dadd_rn(s, __dmul_rn(A[2 * j2 + 1], yy.y));
             }
             return s;
-        } else {  // four independent FMA chains
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        } else {  // two rows x two chains
+            const double2* v = reinterpret_cast<const double2*>(sy + 16 * half);
+            double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
 #pragma unroll
-            for (int j4 = 0; j4 < N / 4; ++j4) {
-                const double2 p0 = v[2 * j4], p1 = v[2 * j4 + 1];
-                s0 = fma(A[4 * j4 + 0], p0.x, s0);
-                s1 = fma(A[4 * j4 + 1], p0.y, s1);
-                s2 = fma(A[4 * j4 + 2], p1.x, s2);
-                s3 = fma(A[4 * j4 + 3], p1.y, s3);
+            for (int j2 = 0; j2 < N / 4; ++j2) {
+                const double2 p = v[j2];
+                c00 = fma(A[2 * j2], p.x, c00);
+                c10 = fma(A[16 + 2 * j2], p.x, c10);
+                c01 = fma(A[2 * j2 + 1], p.y, c01);
+                c11 = fma(A[16 + 2 * j2 + 1], p.y, c11);
             }
-            return (s0 + s1) + (s2 + s3);
+            // (this lane's own row first, the partner's second: nothing to select)
+            return (c00 + c01) + __shfl_xor_sync(FULL_MASK, c10 + c11, 16);
         }
+    };
+    // where A[j] of this lane sits in the row-major 32 x 32 matrix
+    auto a_index = [&](int j) -> unsigned {
+        if constexpr (STRICT) return lane * N + j;
+        else return ((lane & 15u) + 16u * (j < 16 ? half : 1u - half)) * N + 16u * half + (unsigned)(j & 15);
     };
 
     for (;;) {
@@ -88,18 +106,18 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
             const double* P = a.params;
             if (shared) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) A[j] = P[lane * N + j];
-            } else if (aos) {  // [n][N*N] row-major per trajectory: lane i streams its 256-byte row
-                const double2* row = reinterpret_cast<const double2*>(P + (size_t)idx * (N * N) + (size_t)lane * N);
+                for (int j = 0; j < N; ++j) A[j] = P[a_index(j)];
+            } else if (aos) {  // [n][N*N] row-major per trajectory: 128-bit loads along the lane's row(s)
+                const double* M = P + (size_t)idx * (N * N);
 #pragma unroll
                 for (int j2 = 0; j2 < N / 2; ++j2) {
-                    const double2 v = row[j2];
+                    const double2 v = *reinterpret_cast<const double2*>(M + a_index(2 * j2));
                     A[2 * j2] = v.x;
                     A[2 * j2 + 1] = v.y;
                 }
             } else {  // [N*N][n] SoA
 #pragma unroll
-                for (int j = 0; j < N; ++j) A[j] = P[(size_t)(lane * N + j) * n + idx];
+                for (int j = 0; j < N; ++j) A[j] = P[(size_t)a_index(j) * n + idx];
             }
         }
         double y = a.y0[(size_t)lane * n + idx];
@@ -120,6 +138,8 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
         [[maybe_unused]] double ev_tp = t, ev_yp = y, ev_gp = 0.0;
         const bool ev_on = EVENT && a.ev_on != 0;  // (a launch with only a restart record runs these kernels too)
         if (ev_on) ev_gp = g_of(y);
+        // fast build: k[0] = f(y) is carried from attempt to attempt (below); the first one is computed here
+        if constexpr (!STRICT) k[0] = matvec(A, y);
 
         while (st < 0) {
             if (n_att >= cap) { st = BACON_E_MAX_ATTEMPTS; break; }
@@ -160,7 +180,7 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
             } else {
                 double h = dt;
                 if (t + h >= t_end) h = t_end - t;
-                k[0] = matvec(A, y);
+                // (k[0] = A y is already there: computed at the end of the attempt that produced y)
                 static_for<1, O>([&](auto I) {
                     constexpr int i = decltype(I)::value;
                     constexpr int j0 = first_nz_a<Tab, i>();
@@ -179,19 +199,27 @@ __global__ void __launch_bounds__(WARP_BLOCK, MINB) rk_warp_linear32_kernel(cons
                     if constexpr (Tab::e(j) != 0.0) s = fma(Tab::e(j), k[j], s);
                 });
                 double q = s * s;
+                // The point an accepted step lands on and the NEXT attempt's first stage there, before the verdict:
+                // 99 % of the attempts are accepted, the 32 DFMA of this product depend on nothing below, and the
+                // norm's shuffle tree and the step factor are two long dependent chains without FP64 work (ncu,
+                // profiles/r04d_cfg4_source.md: 38 % of a warp's time per attempt) — issued together they overlap.
+                // A rejected attempt keeps y and with it k[0] = A y; the numbers are those of the plain order.
+                constexpr int b0 = first_nz_b<Tab>();
+                double sb = Tab::b(b0) * k[b0];
+                static_for<b0 + 1, O>([&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    if constexpr (Tab::b(j) != 0.0) sb = fma(Tab::b(j), k[j], sb);
+                });
+                const double y_try = fma(h, sb, y);
+                const double k0_try = matvec(A, y_try);
 #pragma unroll
                 for (int m = 16; m >= 1; m >>= 1) q += __shfl_xor_sync(FULL_MASK, q, m);  // identical on every lane
                 if (q != q) { st = BACON_E_NONFINITE; break; }
                 accepted = q <= tol2;
                 if (accepted) {
                     t += h;
-                    constexpr int b0 = first_nz_b<Tab>();
-                    double sb = Tab::b(b0) * k[b0];
-                    static_for<b0 + 1, O>([&](auto J) {
-                        constexpr int j = decltype(J)::value;
-                        if constexpr (Tab::b(j) != 0.0) sb = fma(Tab::b(j), k[j], sb);
-                    });
-                    y = fma(h, sb, y);
+                    y = y_try;
+                    k[0] = k0_try;
                 }
                 const double x = fmax(q * inv_tol2, 1e-6);
                 const double delta = fmin(fmax(Tab::safety * inv_eighth_root(x), 0.1), 4.0);
@@ -292,8 +320,8 @@ template <class Tab, bool STRICT, bool EVENT = false> int launch_rk_warp_linear3
     } else {
         if (a->ev_on) return BACON_E_UNSUPPORTED;
         if (a->cfg.history_capacity > 0 && a->out.hist)
-            return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, true, 4>, a);
-        return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, false, 4>, a);
+            return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, true, LIN32_MINB>, a);
+        return launch_persistent_warp(rk_warp_linear32_kernel<Tab, STRICT, false, LIN32_MINB>, a);
     }
 }
 

@@ -245,8 +245,8 @@ def main():
                        "frac": ev_bytes / 1e9 / (ms_ev * 1e-3) / hp, "regs_per_thread": ev_launch["regs_per_thread"],
                        "traffic_note": "config 2, ncu: dram bytes read = 30.08 GB = the algorithmic bytes (every record once)"},
             "sampling": {"n_times": n_times, "ms": ms_sm, "call_ms": call_sm,
-                         "traffic_note": "config 2, ncu: 9.9 GB of DRAM reads at 5.9 TB/s: the bisection probes 8 of each 64-byte DRAM "
-                                         "burst; DRAM-bound on its actual traffic (profiles/r01o_path_queries.md)", "samples_per_s": float(n) * n_times / (ms_sm * 1e-3),
+                         "traffic_note": "config 2, ncu: 5.1 GB of DRAM reads at 5.2 TB/s (bisection in round 1: 9.9 GB): every probe of a knot's time "
+                                         "moves a 128-byte line for 8 bytes; DRAM-bound on its actual traffic (profiles/r04_sampling_search.md)", "samples_per_s": float(n) * n_times / (ms_sm * 1e-3),
                          "algorithmic_GB": sm_bytes / 1e9, "achieved_GBs": sm_bytes / 1e9 / (ms_sm * 1e-3), "peak_GBs": hp,
                          "frac": sm_bytes / 1e9 / (ms_sm * 1e-3) / hp, "regs_per_thread": sm_launch["regs_per_thread"]},
             "peak_source": src}

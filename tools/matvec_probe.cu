@@ -10,21 +10,26 @@
 
 constexpr int N = 32;
 
-template <int ROWS, int COLS, int CHAINS = 4, int MINB = 4>
+// GROUPED: the LC lanes that share a row are 32/LC lanes apart (column group c = lane / LR: half-warps for 2 x 16,
+// quarter-warps for 4 x 8), so that each LDS.128 of the Y values reads one address per half/quarter warp — two
+// wavefronts like a full broadcast (tools/lds_pattern_probe.cu); the round-2 layouts interleaved them (c = lane % LC),
+// which costs 4 and 8 wavefronts and hid what the blockings save.
+template <int ROWS, int COLS, int CHAINS = 4, int MINB = 4, bool GROUPED = false>
 __global__ void __launch_bounds__(128, MINB) probe(const double* __restrict__ Aglob, double* out, int iters, double h) {
     constexpr int LR = N / ROWS;   // lanes along rows
     constexpr int LC = N / COLS;   // lanes along columns (these lanes reduce)
     static_assert(LR * LC == 32, "one warp");
     __shared__ __align__(16) double s_y[4][N];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = lane / LC, c = lane % LC;
+    const int r = GROUPED ? lane % LR : lane / LC, c = GROUPED ? lane / LR : lane % LC;
+    constexpr int XS = GROUPED ? LR : 1;  // lane distance of neighbouring column groups
     double* sy = s_y[warp];
     const size_t traj = (size_t)blockIdx.x * 4 + warp;
     double A[ROWS][COLS];
 #pragma unroll
     for (int a = 0; a < ROWS; ++a)
 #pragma unroll
-        for (int b = 0; b < COLS; ++b) A[a][b] = Aglob[(traj * N + (ROWS * r + a)) * N + COLS * c + b];
+        for (int b = 0; b < COLS; ++b) A[a][b] = Aglob[(traj * N + (GROUPED ? r + LR * a : ROWS * r + a)) * N + COLS * c + b];
     // the lane's own component of y: component lane (1 x 32), or ROWS * r + (c % ROWS) ... kept simple: component `lane`
     // is owned by lane `lane` in every layout (lane (r, c) -> row index ROWS * r + c when LC == ROWS)
     double y = 1.0 + 1e-3 * lane;
@@ -104,11 +109,11 @@ __global__ void __launch_bounds__(128, MINB) probe(const double* __restrict__ Ag
                         if (a < keep) {
                             const double send = upper ? val[a] : val[a + keep];
                             const double mine = upper ? val[a + keep] : val[a];
-                            val[a] = mine + __shfl_xor_sync(0xffffffffu, send, m);
+                            val[a] = mine + __shfl_xor_sync(0xffffffffu, send, m * XS);
                         }
                     }
                 } else {  // more lanes than rows: plain all-reduce of the one value
-                    val[0] += __shfl_xor_sync(0xffffffffu, val[0], m);
+                    val[0] += __shfl_xor_sync(0xffffffffu, val[0], m * XS);
                 }
             }
             dy = val[0];
@@ -118,16 +123,16 @@ __global__ void __launch_bounds__(128, MINB) probe(const double* __restrict__ Ag
     out[traj * N + lane] = y;
 }
 
-template <int ROWS, int COLS, int CHAINS = 4, int MINB = 4> void run(const double* A, double* out, int sm, int blocks_per_sm) {
+template <int ROWS, int COLS, int CHAINS = 4, int MINB = 4, bool GROUPED = false> void run(const double* A, double* out, int sm, int blocks_per_sm) {
     const int iters = 4096, grid = sm * blocks_per_sm;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    probe<ROWS, COLS, CHAINS, MINB><<<grid, 128>>>(A, out, 64, 1e-9);
+    probe<ROWS, COLS, CHAINS, MINB, GROUPED><<<grid, 128>>>(A, out, 64, 1e-9);
     float best = 1e30f;
     for (int k = 0; k < 3; ++k) {
         cudaEventRecord(e0);
-        probe<ROWS, COLS, CHAINS, MINB><<<grid, 128>>>(A, out, iters, 1e-9);
+        probe<ROWS, COLS, CHAINS, MINB, GROUPED><<<grid, 128>>>(A, out, iters, 1e-9);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
@@ -136,8 +141,8 @@ template <int ROWS, int COLS, int CHAINS = 4, int MINB = 4> void run(const doubl
     }
     const double flops = 2.0 * N * N * (double)iters * grid * 4;
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, probe<ROWS, COLS, CHAINS, MINB>);
-    printf("block %2d x %2d per lane, %d chains, %d CTAs/SM (%d warps/SMSP), %3d regs: %7.3f TFLOP/s = %5.1f %% of 37.2 (%.3f ms)\n", ROWS, COLS, CHAINS,
+    cudaFuncGetAttributes(&fa, probe<ROWS, COLS, CHAINS, MINB, GROUPED>);
+    printf("%s block %2d x %2d per lane, %d chains, %d CTAs/SM (%d warps/SMSP), %3d regs: %7.3f TFLOP/s = %5.1f %% of 37.2 (%.3f ms)\n", GROUPED ? "grouped    " : "interleaved", ROWS, COLS, CHAINS,
            blocks_per_sm, blocks_per_sm, fa.numRegs, flops / (best * 1e-3) / 1e12, 100 * flops / (best * 1e-3) / 37.2e12, best);
 }
 
@@ -149,7 +154,16 @@ int main() {
     cudaMalloc(&A, traj * N * N * 8);
     cudaMalloc(&out, traj * N * 8);
     cudaMemset(A, 0, traj * N * N * 8);
-    for (int bps : {4, 3, 2}) {
+    for (int bps : {4, 3}) {
+        run<2, 16, 2, 4, true>(A, out, sm, bps);
+        run<2, 16, 4, 4, true>(A, out, sm, bps);
+        run<4, 8, 4, 4, true>(A, out, sm, bps);
+        run<8, 4, 4, 4, true>(A, out, sm, bps);
+    }
+    run<2, 16, 4, 5, true>(A, out, sm, 5);
+    run<2, 16, 2, 5, true>(A, out, sm, 5);
+    run<4, 8, 4, 5, true>(A, out, sm, 5);
+    for (int bps : {4}) {
         run<1, 32>(A, out, sm, bps);
         run<1, 32, 8>(A, out, sm, bps);
         run<2, 16, 2>(A, out, sm, bps);
