@@ -1,7 +1,7 @@
 // path_query_warp.cuh — the path queries (path_query.cuh) for the wide-state right-hand side y' = A y, D = 32
 // (`linear32`, BASELINE config 4: the configuration whose dense output the queries read).  As in rk_warp_linear.cuh a
 // state does not fit one thread, so the interpolation is done by a WARP: lane d owns component d of both knots and of
-// both slopes, and row d of the trajectory's matrix; f = A y takes the other components by shuffle, in the oracle's
+// both slopes, and row d of the trajectory's matrix; f = A y takes the other components through shared memory, in the oracle's
 // order (s = A[d][0] y[0]; s += A[d][k] y[k]), so the strict build stays bit-comparable with oracle/oracle_capi.cpp.
 //   path_sample_warp32_kernel   one warp per (trajectory, up to 32 sample times): one bisection per lane, then the warp interpolates;
 //                               both knots come in as coalesced 256-byte rows, the sample leaves as one.
@@ -34,62 +34,94 @@ __device__ __forceinline__ void load_matrix_row32(const bacon_path_args& a, unsi
     }
 }
 
-// (A y)[lane], y spread over the lanes; sequential in k like RhsLinear::operator()
-__device__ __forceinline__ double warp_matvec32(const double (&A)[32], double y_lane) {
-    double s = A[0] * __shfl_sync(FULL_MASK, y_lane, 0);
-#pragma unroll
-    for (int k = 1; k < 32; ++k) s += A[k] * __shfl_sync(FULL_MASK, y_lane, k);
-    return s;
+// The other lanes' components reach a lane through shared memory, two vectors at a time (both knots of an interval):
+// every lane publishes its component of each (one STS.64 per vector), then reads all of them back with broadcast
+// LDS.128.  Round 2's form took them by shuffle; both go through the L1/shared data pipe, where a 64-bit shuffle costs
+// two wavefronts per double and a broadcast LDS.128 two per PAIR of doubles (tools/lds_pattern_probe.cu) — 128 against
+// 68 wavefronts for the two products of a sample, in kernels that issue little else (profiles/r04_linear32.md).  The
+// sums keep the oracle's order (s = A[d][0] y[0]; s += A[d][k] y[k]), so the bits are those of the shuffle form.
+struct WarpPairBuf {
+    double v[2][32];
+};
+__device__ __forceinline__ const double2* warp_pair_publish(WarpPairBuf& buf, unsigned lane, double va, double vb) {
+    __syncwarp();  // (the previous pair has been read by every lane)
+    buf.v[0][lane] = va;
+    buf.v[1][lane] = vb;
+    __syncwarp();
+    return reinterpret_cast<const double2*>(&buf.v[0][0]);
 }
 
-// The same sums for both knots of an interval at once: the two chains are independent, so their shuffles and FMAs
-// interleave and the 32 dependent steps are walked once instead of twice (each sum keeps its own order, so its bits).
-__device__ __forceinline__ void warp_matvec32_pair(const double (&A)[32], double ya, double yb, double& fa, double& fb) {
-    double sa = A[0] * __shfl_sync(FULL_MASK, ya, 0), sb = A[0] * __shfl_sync(FULL_MASK, yb, 0);
+// (A ya)[lane] and (A yb)[lane]: the two chains are independent, so their FMAs interleave and the 32 dependent steps
+// are walked once instead of twice (each sum keeps its own order, so its bits)
+__device__ __forceinline__ void warp_matvec32_pair(WarpPairBuf& buf, unsigned lane, const double (&A)[32], double ya, double yb,
+                                                   double& fa, double& fb) {
+    const double2* v = warp_pair_publish(buf, lane, ya, yb);
+    double sa = 0.0, sb = 0.0;
 #pragma unroll
-    for (int k = 1; k < 32; ++k) {
-        sa += A[k] * __shfl_sync(FULL_MASK, ya, k);
-        sb += A[k] * __shfl_sync(FULL_MASK, yb, k);
+    for (int k2 = 0; k2 < 16; ++k2) {
+        const double2 pa = v[k2], pb = v[16 + k2];
+        if (k2 == 0) {
+            sa = A[0] * pa.x;
+            sb = A[0] * pb.x;
+        } else {
+            sa += A[2 * k2] * pa.x;
+            sb += A[2 * k2] * pb.x;
+        }
+        sa += A[2 * k2 + 1] * pa.y;
+        sb += A[2 * k2 + 1] * pb.y;
     }
     fa = sa;
     fb = sb;
 }
 // f = A y and w . y for both knots: one broadcast of y_k feeds both sums
-__device__ __forceinline__ void warp_matvec_dot32_pair(const bacon_path_args& a, const double (&A)[32], double ya, double yb,
-                                                       double& fa, double& fb, double& wa, double& wb) {
-    double ya_k = __shfl_sync(FULL_MASK, ya, 0), yb_k = __shfl_sync(FULL_MASK, yb, 0);
-    double sa = A[0] * ya_k, sb = A[0] * yb_k, da = a.ev_w[0] * ya_k, db = a.ev_w[0] * yb_k;
+__device__ __forceinline__ void warp_matvec_dot32_pair(WarpPairBuf& buf, unsigned lane, const bacon_path_args& a, const double (&A)[32],
+                                                       double ya, double yb, double& fa, double& fb, double& wa, double& wb) {
+    const double2* v = warp_pair_publish(buf, lane, ya, yb);
+    double sa = 0.0, sb = 0.0, da = 0.0, db = 0.0;
 #pragma unroll
-    for (int k = 1; k < 32; ++k) {
-        ya_k = __shfl_sync(FULL_MASK, ya, k);
-        yb_k = __shfl_sync(FULL_MASK, yb, k);
-        sa += A[k] * ya_k;
-        sb += A[k] * yb_k;
-        da += a.ev_w[k] * ya_k;
-        db += a.ev_w[k] * yb_k;
+    for (int k2 = 0; k2 < 16; ++k2) {
+        const double2 pa = v[k2], pb = v[16 + k2];
+        if (k2 == 0) {
+            sa = A[0] * pa.x;
+            sb = A[0] * pb.x;
+            da = a.ev_w[0] * pa.x;
+            db = a.ev_w[0] * pb.x;
+        } else {
+            sa += A[2 * k2] * pa.x;
+            sb += A[2 * k2] * pb.x;
+            da += a.ev_w[2 * k2] * pa.x;
+            db += a.ev_w[2 * k2] * pb.x;
+        }
+        sa += A[2 * k2 + 1] * pa.y;
+        sb += A[2 * k2 + 1] * pb.y;
+        da += a.ev_w[2 * k2 + 1] * pa.y;
+        db += a.ev_w[2 * k2 + 1] * pb.y;
     }
     fa = sa;
     fb = sb;
     wa = da;
     wb = db;
 }
-__device__ __forceinline__ void warp_seqdot32_pair(const bacon_path_args& a, double va, double vb, double& wa, double& wb) {
-    double da = a.ev_w[0] * __shfl_sync(FULL_MASK, va, 0), db = a.ev_w[0] * __shfl_sync(FULL_MASK, vb, 0);
+// w . va and w . vb over the lanes, sequential in d like event_fn; every lane gets both sums
+__device__ __forceinline__ void warp_seqdot32_pair(WarpPairBuf& buf, unsigned lane, const bacon_path_args& a, double va, double vb,
+                                                   double& wa, double& wb) {
+    const double2* v = warp_pair_publish(buf, lane, va, vb);
+    double da = 0.0, db = 0.0;
 #pragma unroll
-    for (int d = 1; d < 32; ++d) {
-        da += a.ev_w[d] * __shfl_sync(FULL_MASK, va, d);
-        db += a.ev_w[d] * __shfl_sync(FULL_MASK, vb, d);
+    for (int d2 = 0; d2 < 16; ++d2) {
+        const double2 pa = v[d2], pb = v[16 + d2];
+        if (d2 == 0) {
+            da = a.ev_w[0] * pa.x;
+            db = a.ev_w[0] * pb.x;
+        } else {
+            da += a.ev_w[2 * d2] * pa.x;
+            db += a.ev_w[2 * d2] * pb.x;
+        }
+        da += a.ev_w[2 * d2 + 1] * pa.y;
+        db += a.ev_w[2 * d2 + 1] * pb.y;
     }
     wa = da;
     wb = db;
-}
-
-// w . v over the lanes, sequential in d like event_fn; every lane gets the sum
-__device__ __forceinline__ double warp_seqdot32(const bacon_path_args& a, double v_lane) {
-    double s = a.ev_w[0] * __shfl_sync(FULL_MASK, v_lane, 0);
-#pragma unroll
-    for (int d = 1; d < 32; ++d) s += a.ev_w[d] * __shfl_sync(FULL_MASK, v_lane, d);
-    return s;
 }
 
 // component d of knot k
@@ -127,6 +159,8 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __
             my_lo = ~0u;
         }
     }
+    __shared__ __align__(16) WarpPairBuf s_pair[PATH_BLOCK / 32];
+    WarpPairBuf& pair = s_pair[threadIdx.x >> 5];
     double A[32];
     load_matrix_row32(a, i, lane, A);
     // phase 2: the warp interpolates them one after the other.  (Requesting the knots of sample l + 1 before sample l is
@@ -143,7 +177,7 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __
         const double ta = pv.time(lo - 1), tb = pv.time(lo);
         const double ya[1] = {knot_component32(pv, lo - 1, lane)}, yb[1] = {knot_component32(pv, lo, lane)};
         double fa[1], fb[1];
-        warp_matvec32_pair(A, ya[0], yb[0], fa[0], fb[0]);
+        warp_matvec32_pair(pair, lane, A, ya[0], yb[0], fa[0], fb[0]);
         const double h = tb - ta;
         const double th = h > 0.0 ? (tau - ta) / h : 0.0;
         double res[1];
@@ -160,6 +194,8 @@ template <bool STRICT> struct WarpLocateLinear32 {
     static constexpr bool DEFERRED = true;
     static __device__ __noinline__ void flush(const bacon_path_args& a, unsigned long long i, uint32_t n_pend, const uint32_t* pk,
                                               const uint32_t* ps, double* ev, unsigned lane) {
+        __shared__ __align__(16) WarpPairBuf s_pair[PATH_BLOCK / 32];
+        WarpPairBuf& pair = s_pair[threadIdx.x >> 5];
         const PathView<32> pv(a, i);
         double A[32];
         load_matrix_row32(a, i, lane, A);
@@ -170,8 +206,8 @@ template <bool STRICT> struct WarpLocateLinear32 {
             const double ta = pv.time(k - 1), tb = pv.time(k);
             const double ya[1] = {knot_component32(pv, k - 1, lane)}, yb[1] = {knot_component32(pv, k, lane)};
             double fa[1], fb[1], wa, wb, da, db;
-            warp_matvec_dot32_pair(a, A, ya[0], yb[0], fa[0], fb[0], wa, wb);
-            warp_seqdot32_pair(a, fa[0], fb[0], da, db);
+            warp_matvec_dot32_pair(pair, lane, a, A, ya[0], yb[0], fa[0], fb[0], wa, wb);
+            warp_seqdot32_pair(pair, lane, a, fa[0], fb[0], da, db);
             const double h = tb - ta;
             const double ga = wa - a.ev_c, gb = wb - a.ev_c;
             const double th = hermite_root(ga, gb, h * da, h * db);
