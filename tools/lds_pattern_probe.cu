@@ -58,10 +58,11 @@ template <int WIDTH, int MODE> void run(const char* what, double* out, long long
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    long long cyc; cudaMemcpy(&cyc, dcyc, 8, cudaMemcpyDeviceToHost);
-    const double loads_per_sm = 16.0 * iters * 8;  // warp-level loads per SM
-    printf("%-58s %2d B/lane: %6.2f SM cycles per warp load (%5.2f per 8 B per lane), %.3f ms\n", what, WIDTH, cyc / loads_per_sm,
-           cyc / loads_per_sm * 8.0 / WIDTH, ms);
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    const double loads_per_sm = 16.0 * iters * 8;  // warp-level loads per SM (16 resident warps)
+    const double cyc = ms * 1e-3 * khz * 1e3 / loads_per_sm;  // (event time at the boost clock; clock64 of one warp under-reports)
+    printf("%-40s %2d B/lane: %5.2f SM cycles per warp-level load (%4.2f per 8 B per lane), %.3f ms\n", what, WIDTH, cyc, cyc * 8.0 / WIDTH, ms);
 }
 
 int main() {
