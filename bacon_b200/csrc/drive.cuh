@@ -108,6 +108,18 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
 // barrier instructions.  (2) ptxas keeps the tableau in uniform registers across the persistent loop only while the
 // loop's function holds no other loop: with the waiting loop inlined it re-loads all coefficients from the constant
 // bank on every attempt (28 LDCU per pair of attempts, tools/sass_count.py).
+// The two polled flags of RegroupCtl (request, dry) are written and read without a barrier in between ON PURPOSE: every
+// write that races stores the same value, a reader that misses it sees it at its next checkpoint, and what is
+// exchanged afterwards is ordered by the named barrier of the meeting.  They are accessed with morally strong relaxed
+// operations at CTA scope (the PTX memory model's race-free form of exactly this), not `volatile`.
+__device__ __forceinline__ int flag_load(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void flag_store(int* p, int v) {
+    asm volatile("st.relaxed.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
 struct RegroupCtl {  // one per CTA, in shared memory
     int live;        // lanes of the CTA that hold a trajectory (kept by the lanes that run out of work: atomicSub)
     int request;     // != 0: a regrouping is asked for; every running warp comes to the meeting at its next checkpoint
@@ -158,18 +170,18 @@ static __device__ __noinline__ void regroup_count_out(RegroupCtl* ctl, int w_act
     const int left = atomicSub(&ctl->live, 1) - 1;
     const int empty = 32 * w_active - left;
 #ifdef BACON_NO_REGROUP  // (A/B switch for measurements: the warps meet once, when the CTA has nothing left)
-    if (left == 0) *(volatile int*)&ctl->request = 1;
+    if (left == 0) flag_store(&ctl->request, 1);
 #else
-    if (empty >= BACON_REGROUP_AT || (empty >= 32 && w_active <= 4) || left == 0) *(volatile int*)&ctl->request = 1;
+    if (empty >= BACON_REGROUP_AT || (empty >= 32 && w_active <= 4) || left == 0) flag_store(&ctl->request, 1);
 #endif
 }
 
 // Has the launch's work counter handed out everything?  One shared-memory load once somebody in the CTA has seen it.
 // (Not inlined: inlined, the persistent loop carries four more register moves per pair of attempts.)
 static __device__ __noinline__ bool counter_dry(RegroupCtl* ctl, const unsigned long long* counter, unsigned long long n_rest) {
-    if (*(volatile int*)&ctl->dry != 0) return true;
+    if (flag_load(&ctl->dry) != 0) return true;
     if (*(volatile const unsigned long long*)counter < n_rest) return false;
-    *(volatile int*)&ctl->dry = 1;
+    flag_store(&ctl->dry, 1);
     return true;
 }
 
@@ -187,7 +199,7 @@ static __device__ __noinline__ void regroup_plan(RegroupPlan* p, RegroupCtl* ctl
 #endif
     if (lane == 0) {
         cnt[warp] = __popc(live_mask);
-        *(volatile int*)&ctl->request = 1;  // (it is: set again so that a meeting can never be one-sided)
+        flag_store(&ctl->request, 1);  // (it is: set again so that a meeting can never be one-sided)
     }
     named_barrier(1, w_active * 32);
     const int c = lane < w_active ? cnt[lane] : 0;
@@ -231,7 +243,7 @@ static __device__ __noinline__ int regroup_rank(const int* keys, int total, int 
 // Afterwards the lowest ceil(total / 32) warps go on: lane l of warp w owns slot 32 w + l.
 static __device__ __noinline__ void regroup_meet(RegroupPlan* p, RegroupCtl* ctl) {
     if (threadIdx.x == 0) {  // (nobody is stepping: every running warp is between the two meetings)
-        *(volatile int*)&ctl->request = 0;
+        flag_store(&ctl->request, 0);
         *(volatile int*)&ctl->live = p->total;
         if (p->action == RG_EXCHANGE && p->sort) *(volatile int*)&ctl->sorts = *(volatile int*)&ctl->sorts + 1;
     }
@@ -442,7 +454,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) ensemble_kernel(const __grid_cons
                 if constexpr (MIGRATE) {
                     if (HIST ? wq.dry() : counter_dry(&ctl, a.work_counter, n_rest)) {
                         if constexpr (StepperRetimes<Stepper>::value) s.hurry(CHECK_EVERY_DRY);
-                        if (*(volatile int*)&ctl.request != 0) return true;  // the warp goes to the meeting
+                        if (flag_load(&ctl.request) != 0) return true;  // the warp goes to the meeting
                     }
                 }
             } else {
