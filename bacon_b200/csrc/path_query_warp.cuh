@@ -51,15 +51,14 @@ __device__ __forceinline__ const double2* warp_pair_publish(WarpPairBuf& buf, un
     return reinterpret_cast<const double2*>(&buf.v[0][0]);
 }
 
-// (A ya)[lane] and (A yb)[lane]: the two chains are independent, so their FMAs interleave and the 32 dependent steps
-// are walked once instead of twice (each sum keeps its own order, so its bits)
-__device__ __forceinline__ void warp_matvec32_pair(WarpPairBuf& buf, unsigned lane, const double (&A)[32], double ya, double yb,
-                                                   double& fa, double& fb) {
-    const double2* v = warp_pair_publish(buf, lane, ya, yb);
+// (A ya)[lane] and (A yb)[lane] with both vectors in shared memory (16-byte aligned): the two chains are independent,
+// so their FMAs interleave and the 32 dependent steps are walked once instead of twice (each sum keeps its own order,
+// so its bits)
+__device__ __forceinline__ void warp_matvec32_pair_at(const double2* va, const double2* vb, const double (&A)[32], double& fa, double& fb) {
     double sa = 0.0, sb = 0.0;
 #pragma unroll
     for (int k2 = 0; k2 < 16; ++k2) {
-        const double2 pa = v[k2], pb = v[16 + k2];
+        const double2 pa = va[k2], pb = vb[k2];
         if (k2 == 0) {
             sa = A[0] * pa.x;
             sb = A[0] * pb.x;
@@ -73,6 +72,57 @@ __device__ __forceinline__ void warp_matvec32_pair(WarpPairBuf& buf, unsigned la
     fa = sa;
     fb = sb;
 }
+__device__ __forceinline__ void warp_matvec32_pair(WarpPairBuf& buf, unsigned lane, const double (&A)[32], double ya, double yb,
+                                                   double& fa, double& fb) {
+    const double2* v = warp_pair_publish(buf, lane, ya, yb);
+    warp_matvec32_pair_at(v, v + 16, A, fa, fb);
+}
+
+// Asynchronous copies into shared memory (LDGSTS): no register holds the data in flight, so a warp can have all the
+// knots of its samples — or its whole matrix — on the way at once.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One warp's staging area: the 32 x 32 matrix with rows 34 doubles apart, or 32 state vectors of 32 doubles followed by
+// their 32 knot times.
+struct WarpStage {
+    double v[32 * 34];
+};
+// Row `lane` of a row-major (AoS) matrix through the staging area: the warp moves the 8 KB as 16 coalesced 512-byte
+// requests (a row per lane straight from global memory touches 32 lines per request: 512 wavefronts of the L1 data
+// pipe against 192 this way) and every lane reads its own row back with LDS.128 (272 bytes apart: conflict-free).
+// begin() only issues the copies; what the warp does before end() overlaps them.
+__device__ __forceinline__ bool stage_matrix32_begin(const bacon_path_args& a, unsigned long long i, unsigned lane, WarpStage& st) {
+    if ((a.cfg.flags & BACON_FLAG_SHARED_PARAMS) || !(a.cfg.flags & BACON_FLAG_PARAMS_AOS)) return false;
+    const double* M = a.params + (size_t)i * 1024;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) cp_async16(&st.v[(2 * k + (lane >> 4)) * 34 + 2 * (lane & 15)], M + 64 * k + 2 * lane);
+    return true;
+}
+__device__ __forceinline__ void stage_matrix32_end(const bacon_path_args& a, unsigned long long i, unsigned lane, bool staged,
+                                                   WarpStage& st, double (&A)[32]) {
+    if (!staged) {
+        load_matrix_row32(a, i, lane, A);
+        return;
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    const double2* row = reinterpret_cast<const double2*>(&st.v[lane * 34]);
+#pragma unroll
+    for (int j2 = 0; j2 < 16; ++j2) {
+        const double2 v = row[j2];
+        A[2 * j2] = v.x;
+        A[2 * j2 + 1] = v.y;
+    }
+    __syncwarp();  // (the area is free again)
+}
+
 // f = A y and w . y for both knots: one broadcast of y_k feeds both sums
 __device__ __forceinline__ void warp_matvec_dot32_pair(WarpPairBuf& buf, unsigned lane, const bacon_path_args& a, const double (&A)[32],
                                                        double ya, double yb, double& fa, double& fb, double& wa, double& wb) {
@@ -148,6 +198,10 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __
     const PathView<32> pv(a, i);
     const uint32_t K = pv.last();
     const double t_last = pv.time(K);
+    // the matrix is on its way while the lanes search (phase 1)
+    __shared__ __align__(16) WarpStage s_stage[PATH_BLOCK / 32];
+    WarpStage& st = s_stage[threadIdx.x >> 5];
+    const bool staged = stage_matrix32_begin(a, i, lane, st);
     // phase 1: lane l finds the interval of time j0 + l (0 = outside the path, ~0 = exactly t_start on an empty path)
     double my_tau = 0.0;
     uint32_t my_lo = 0;
@@ -159,30 +213,55 @@ __global__ void __launch_bounds__(PATH_BLOCK) path_sample_warp32_kernel(const __
             my_lo = ~0u;
         }
     }
-    __shared__ __align__(16) WarpPairBuf s_pair[PATH_BLOCK / 32];
-    WarpPairBuf& pair = s_pair[threadIdx.x >> 5];
     double A[32];
-    load_matrix_row32(a, i, lane, A);
-    // phase 2: the warp interpolates them one after the other.  (Requesting the knots of sample l + 1 before sample l is
-    // computed was measured slower: 3.90 -> 4.85 ms on config 4, the extra live rows cost more than the overlap gains.)
-#pragma unroll 2
-    for (unsigned l = 0; l < n_here; ++l) {
-        const double tau = __shfl_sync(FULL_MASK, my_tau, l);
-        const uint32_t lo = __shfl_sync(FULL_MASK, my_lo, l);
-        double* out = a.samples + ((size_t)i * a.n_times + j0 + l) * 32;
-        if (lo == 0 || lo == ~0u) {
-            out[lane] = lo ? knot_component32(pv, 0, lane) : path_nan();
-            continue;
+    stage_matrix32_end(a, i, lane, staged, st, A);
+    // phase 2: the knots of up to 16 samples are requested at once (asynchronous copies into the staging area: the
+    // warp pays the memory latency once per group, not once per sample — doing the same through registers was measured
+    // slower in round 1, 3.90 -> 4.85 ms: the extra live rows cost more than the overlap gained), then the warp
+    // interpolates them one after the other, the products reading the knot vectors where they landed.
+    double* const knots = st.v;          // vector q = 2 u + side of sample u: knots[32 q .. 32 q + 31]
+    double* const knot_t = st.v + 1024;  // its time
+    for (unsigned base = 0; base < n_here; base += 16) {
+        const unsigned cnt = n_here - base < 16u ? n_here - base : 16u;
+        __syncwarp();
+        for (unsigned u = 0; u < cnt; ++u) {
+            const uint32_t lo = __shfl_sync(FULL_MASK, my_lo, base + u);
+            if (lo == 0 || lo == ~0u) continue;
+#pragma unroll
+            for (unsigned side = 0; side < 2; ++side) {
+                const uint32_t k = lo - 1 + side, q = 2 * u + side;
+                if (k >= 1 && k <= pv.m) {
+                    const double* r = pv.rec + (size_t)(k - 1) * 33;
+                    cp_async8(&knots[32 * q + lane], r + 1 + lane);
+                    if (lane == 0) cp_async8(&knot_t[q], r);
+                } else {  // the initial condition or the closing knot: other arrays
+                    knots[32 * q + lane] = knot_component32(pv, k, lane);
+                    if (lane == 0) knot_t[q] = pv.time(k);
+                }
+            }
         }
-        const double ta = pv.time(lo - 1), tb = pv.time(lo);
-        const double ya[1] = {knot_component32(pv, lo - 1, lane)}, yb[1] = {knot_component32(pv, lo, lane)};
-        double fa[1], fb[1];
-        warp_matvec32_pair(pair, lane, A, ya[0], yb[0], fa[0], fb[0]);
-        const double h = tb - ta;
-        const double th = h > 0.0 ? (tau - ta) / h : 0.0;
-        double res[1];
-        hermite_eval<1>(th, h, ya, yb, fa, fb, res);
-        out[lane] = res[0];
+        cp_async_wait_all();
+        __syncwarp();
+        for (unsigned u = 0; u < cnt; ++u) {
+            const unsigned l = base + u;
+            const double tau = __shfl_sync(FULL_MASK, my_tau, l);
+            const uint32_t lo = __shfl_sync(FULL_MASK, my_lo, l);
+            double* out = a.samples + ((size_t)i * a.n_times + j0 + l) * 32;
+            if (lo == 0 || lo == ~0u) {
+                out[lane] = lo ? knot_component32(pv, 0, lane) : path_nan();
+                continue;
+            }
+            const double* va = knots + 64 * u;
+            const double ta = knot_t[2 * u], tb = knot_t[2 * u + 1];
+            const double ya[1] = {va[lane]}, yb[1] = {va[32 + lane]};
+            double fa[1], fb[1];
+            warp_matvec32_pair_at(reinterpret_cast<const double2*>(va), reinterpret_cast<const double2*>(va + 32), A, fa[0], fb[0]);
+            const double h = tb - ta;
+            const double th = h > 0.0 ? (tau - ta) / h : 0.0;
+            double res[1];
+            hermite_eval<1>(th, h, ya, yb, fa, fb, res);
+            out[lane] = res[0];
+        }
     }
 }
 
