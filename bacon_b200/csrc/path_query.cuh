@@ -601,9 +601,12 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EVW_MINB) path_events_wide_k
     const uint32_t cap = (uint32_t)a.ev_capacity;
     double* ev = a.events + (size_t)i * cap * R;
     auto flush = [&]() {
-        __syncwarp();
-        Locate::flush(a, i, n_pend, pend_k[wid], pend_slot[wid], ev, lane);
-        __syncwarp();
+        // (a DEFERRED policy never queues anything here, and its flush() must not add its shared memory to this kernel)
+        if constexpr (!Locate::DEFERRED) {
+            __syncwarp();
+            Locate::flush(a, i, n_pend, pend_k[wid], pend_slot[wid], ev, lane);
+            __syncwarp();
+        }
     };
     // 32 knots base .. base + 31 (lane l holds knot base + l, `have` = it exists): crossings against the left neighbour
     auto scan = [&](uint32_t base, bool have, double g) {
@@ -619,7 +622,10 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EVW_MINB) path_events_wide_k
         const uint32_t n_enq = nh < room ? nh : room;
         const uint32_t rank = (uint32_t)__popc(h & lanemask_lt());
         if constexpr (Locate::DEFERRED) {  // the slot holds the knot index until the second kernel has been there
-            if (((h >> lane) & 1u) && rank < n_enq) ev[(size_t)(count + rank) * R] = __longlong_as_double((long long)(base + lane));
+            if (((h >> lane) & 1u) && rank < n_enq) {  // (and, next to it, the number of records: flush_known)
+                ev[(size_t)(count + rank) * R] = __longlong_as_double((long long)(base + lane));
+                ev[(size_t)(count + rank) * R + 1] = __longlong_as_double((long long)pv.m);
+            }
             count += nh;
             return;
         }
@@ -663,28 +669,31 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_EVW_MINB) path_events_wide_k
 }
 
 // second kernel of a DEFERRED location.  A warp takes 32 consecutive event slots (slot = trajectory * capacity + j):
-// lane l reads whether its slot is filled (j < min(n_events, capacity)) and the knot index parked there — coalesced,
-// one round trip for 32 slots — then the warp locates the filled ones trajectory by trajectory through the policy's
-// flush(), so a trajectory's matrix is loaded once for all its crossings.
+// lane l reads whether its slot is filled (j < min(n_events, capacity)) and the knot index and record count parked
+// there — coalesced, one round trip for 32 slots — then the warp locates the filled ones trajectory by trajectory through
+// the policy's flush_known(), so a trajectory's matrix is loaded once for all its crossings.
 #ifndef BACON_LOCATE_MINB
 #define BACON_LOCATE_MINB 4  // (measured on config 4: 3 -> 2.42 ms, 4 -> 2.32, 5 -> 2.33)
 #endif
 template <class Locate>
 __global__ void __launch_bounds__(PATH_BLOCK, BACON_LOCATE_MINB) path_locate_deferred_kernel(const __grid_constant__ bacon_path_args a) {
     constexpr int R = 1 + Locate::DIM;
-    __shared__ uint32_t pk[PATH_BLOCK / 32][32], ps[PATH_BLOCK / 32][32];
+    __shared__ uint32_t pk[PATH_BLOCK / 32][32], ps[PATH_BLOCK / 32][32], pm[PATH_BLOCK / 32][32];
     const unsigned wid = threadIdx.x >> 5, lane = lane_id();
     const unsigned long long cap = (unsigned long long)a.ev_capacity, total = a.n * cap;
     const unsigned long long s = ((((unsigned long long)blockIdx.x * PATH_BLOCK + threadIdx.x) >> 5) << 5) + lane;
     bool valid = false;
-    uint32_t k = 0, j = 0;
+    uint32_t k = 0, j = 0, m = 0;
     unsigned long long i = 0;
     if (s < total) {
         i = s / cap;
         j = (uint32_t)(s - i * cap);
         const uint32_t found = a.n_events[i];
         valid = j < (found < (uint32_t)cap ? found : (uint32_t)cap);
-        if (valid) k = (uint32_t)__double_as_longlong(a.events[(size_t)s * R]);
+        if (valid) {
+            k = (uint32_t)__double_as_longlong(a.events[(size_t)s * R]);
+            m = (uint32_t)__double_as_longlong(a.events[(size_t)s * R + 1]);
+        }
     }
     unsigned mask = __ballot_sync(FULL_MASK, valid);
     while (mask) {
@@ -696,9 +705,10 @@ __global__ void __launch_bounds__(PATH_BLOCK, BACON_LOCATE_MINB) path_locate_def
             const unsigned rank = __popc(same & lanemask_lt());
             pk[wid][rank] = k;
             ps[wid][rank] = j;
+            pm[wid][rank] = m;
         }
         __syncwarp();
-        Locate::flush(a, i_cur, (uint32_t)__popc(same), pk[wid], ps[wid], a.events + (size_t)i_cur * cap * R, lane);
+        Locate::flush_known(a, i_cur, (uint32_t)__popc(same), pk[wid], ps[wid], pm[wid], a.events + (size_t)i_cur * cap * R, lane);
         __syncwarp();
         mask &= ~same;
     }

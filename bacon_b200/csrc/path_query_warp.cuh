@@ -271,19 +271,65 @@ template <bool STRICT> struct WarpLocateLinear32 {
     // with the TMA-staged streaming kernel (path_query.cuh: path_events_wide_kernel) the crossings are located by a
     // second kernel, one warp per crossing, instead of one after the other at the end of each path
     static constexpr bool DEFERRED = true;
-    static __device__ __noinline__ void flush(const bacon_path_args& a, unsigned long long i, uint32_t n_pend, const uint32_t* pk,
-                                              const uint32_t* ps, double* ev, unsigned lane) {
+    static constexpr uint32_t PREFETCH = 4;  // crossings of a trajectory whose knots are requested together with its matrix
+    // pm != nullptr: pm[e] = the number of records of the path (parked next to the knot index by the streaming kernel),
+    // which says where knot k lives without a look at the trajectory's bookkeeping: the two knots of the first PREFETCH
+    // crossings are then requested by asynchronous copies at the same time as the matrix, and the warp waits ONCE per
+    // trajectory instead of once for the matrix and once per crossing (the location kernel is a chain of dependent
+    // round trips: 19 % of the warp slots resident, data pipe 60 % busy).
+    template <bool KNOWN>
+    static __device__ __forceinline__ void locate_all(const bacon_path_args& a, unsigned long long i, uint32_t n_pend, const uint32_t* pk,
+                                                      const uint32_t* ps, const uint32_t* pm, double* ev, unsigned lane) {
         __shared__ __align__(16) WarpPairBuf s_pair[PATH_BLOCK / 32];
-        WarpPairBuf& pair = s_pair[threadIdx.x >> 5];
+        __shared__ __align__(16) WarpStage s_stage[PATH_BLOCK / 32];
+        __shared__ __align__(16) double s_knots[PATH_BLOCK / 32][2 * PREFETCH][32];
+        __shared__ double s_knot_t[PATH_BLOCK / 32][2 * PREFETCH];
+        const unsigned w = threadIdx.x >> 5;
+        WarpPairBuf& pair = s_pair[w];
+        WarpStage& st = s_stage[w];
+        const bool staged = stage_matrix32_begin(a, i, lane, st);
+        const double* rec = a.hist + (size_t)i * (size_t)a.cfg.history_capacity * 33;
+        if constexpr (KNOWN) {
+            for (uint32_t e = 0; e < n_pend && e < PREFETCH; ++e) {
+                const uint32_t k = pk[e], m = pm[e];
+#pragma unroll
+                for (uint32_t side = 0; side < 2; ++side) {
+                    const uint32_t kk = k - 1 + side;
+                    if (kk >= 1 && kk <= m) {
+                        const double* r = rec + (size_t)(kk - 1) * 33;
+                        cp_async8(&s_knots[w][2 * e + side][lane], r + 1 + lane);
+                        if (lane == 0) cp_async8(&s_knot_t[w][2 * e + side], r);
+                    }
+                }
+            }
+        }
         const PathView<32> pv(a, i);
         double A[32];
-        load_matrix_row32(a, i, lane, A);
+        stage_matrix32_end(a, i, lane, staged, st, A);  // (waits for every copy of this lane, then the warp meets)
+        if (!staged) {
+            cp_async_wait_all();
+            __syncwarp();
+        }
 #pragma unroll 1
         for (uint32_t e = 0; e < n_pend; ++e) {
             const uint32_t k = pk[e];
             double* dst = ev + (size_t)ps[e] * 33;
-            const double ta = pv.time(k - 1), tb = pv.time(k);
-            const double ya[1] = {knot_component32(pv, k - 1, lane)}, yb[1] = {knot_component32(pv, k, lane)};
+            double t2[2], y2[2];
+#pragma unroll
+            for (uint32_t side = 0; side < 2; ++side) {
+                const uint32_t kk = k - 1 + side;
+                bool here = false;
+                if constexpr (KNOWN) here = e < PREFETCH && kk >= 1 && kk <= pm[e];
+                if (here) {
+                    t2[side] = s_knot_t[w][2 * e + side];
+                    y2[side] = s_knots[w][2 * e + side][lane];
+                } else {
+                    t2[side] = pv.time(kk);
+                    y2[side] = knot_component32(pv, kk, lane);
+                }
+            }
+            const double ta = t2[0], tb = t2[1];
+            const double ya[1] = {y2[0]}, yb[1] = {y2[1]};
             double fa[1], fb[1], wa, wb, da, db;
             warp_matvec_dot32_pair(pair, lane, a, A, ya[0], yb[0], fa[0], fb[0], wa, wb);
             warp_seqdot32_pair(pair, lane, a, fa[0], fb[0], da, db);
@@ -295,6 +341,15 @@ template <bool STRICT> struct WarpLocateLinear32 {
             if (lane == 0) dst[0] = ta + th * h;
             dst[1 + lane] = ys[0];
         }
+        __syncwarp();  // (the staging areas are free again)
+    }
+    static __device__ __noinline__ void flush(const bacon_path_args& a, unsigned long long i, uint32_t n_pend, const uint32_t* pk,
+                                              const uint32_t* ps, double* ev, unsigned lane) {
+        locate_all<false>(a, i, n_pend, pk, ps, nullptr, ev, lane);
+    }
+    static __device__ __noinline__ void flush_known(const bacon_path_args& a, unsigned long long i, uint32_t n_pend, const uint32_t* pk,
+                                                    const uint32_t* ps, const uint32_t* pm, double* ev, unsigned lane) {
+        locate_all<true>(a, i, n_pend, pk, ps, pm, ev, lane);
     }
 };
 
