@@ -55,6 +55,36 @@ def test_sample_lorenz_matches_oracle(cuda, engine, oracle, strict):
 
 
 @pytest.mark.parametrize("strict", [True, False])
+def test_knot_search_on_geometric_paths(cuda, engine, oracle, strict):
+    """The sampling kernels look a sample's interval up by bisection down to 64 knots and then by interpolation on the
+    bracket's end times (PathView::first_knot_at_or_after), which assumes a step size that varies slowly.  Here it does
+    not: y' = -y from a first step of 1e-9 with dt allowed up to 50 — the steps grow fourfold per attempt, level off
+    where the tolerance bites and grow again as y decays — so the interpolated guesses stagnate at one end of the
+    bracket and the search must fall back to bisection after PATH_INTERP_MAX tries.  Whatever the probe sequence, the
+    knot found is the oracle's (a plain bisection): strict samples bit for bit."""
+    n = 96
+    rng = np.random.default_rng(23)
+    y0 = rng.uniform(0.5, 1.5, size=(1, n)) * 10.0 ** rng.integers(-3, 4, size=(1, n))
+    s = make_solver(engine, "RK45", 1, rhs="decay", dt_min=1e-12, dt_max=50.0, tol=1e-6, t_start=0.0, t_end=200.0,
+                    flags=_abi.FLAG_STRICT_FP if strict else 0, history=2048).with_initial_dt(1e-9)
+    res = s.solve_ivp_ensemble(y0, None)
+    assert (res.status == _abi.OK).all()
+    steps = np.diff(res.hist_t[0, :res.hist_len[0]])
+    assert res.hist_len.min() > 40 and steps.max() / steps.min() > 1e6  # the path really is geometric
+    times = np.concatenate([[0.0, 200.0], np.minimum(np.logspace(-10, np.log10(200.0), 150), 200.0), rng.uniform(0.0, 200.0, 60),
+                            res.hist_t[3, :20], np.nextafter(res.hist_t[7, :20], np.inf)])
+    got = res.sample(times)
+    ref = oracle.sample_paths("decay", y0, None, _solved(res), times, t_start=0.0)
+    assert np.isfinite(got).all()
+    if strict:
+        assert np.array_equal(_bits(got), _bits(ref))
+    else:
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-300)
+    exact = y0.T[:, None, :] * np.exp(-times)[None, :, None]
+    assert np.abs(got - exact).max() <= 1e-4  # (the controller's tolerance is absolute: 1e-6 per unit of time, steps up to 5.8)
+
+
+@pytest.mark.parametrize("strict", [True, False])
 @pytest.mark.parametrize("direction", [0, 1, -1])
 def test_events_lorenz_match_oracle(cuda, engine, oracle, strict, direction):
     """x = 0 crossings of Lorenz trajectories (lobe switches) and the Poincare section z = rho - 1."""
