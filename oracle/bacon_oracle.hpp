@@ -13,11 +13,16 @@
 //    tests replayed through it: rk.rs:682-758 (pins c, b, e and the dt
 //    controller) and src/tests/roots/mod.rs:169-221 (pins the Broyden + LU code
 //    bdf.rs:414-475 shares with roots::secant).
-//  * The reference's RK tests use y-independent right-hand sides, so the stage
-//    matrix (rk.rs:459-502) is NOT pinned by any reference test: "stage-matrix
-//    parity unpinned".  All eight BDF tests (bdf.rs:785-1063) iterate over an
-//    empty path: "BDF parity unpinned".  Both are anchored on closed forms and
-//    SciPy instead (tests/golden/).
+//  * Every coefficient table below (RK stage matrix, nodes, weights, error
+//    weights, safety factor; BDF and Adams coefficients) is held bit for bit
+//    against the numbers parsed out of the reference's own source text
+//    (tests/golden/reference_coefficients.json, tests/test_oracle.py).
+//  * The reference's RK tests use y-independent right-hand sides, so what the
+//    step DOES with the stage matrix (rk.rs:370-384) is NOT pinned by any
+//    reference test: "stage-matrix parity unpinned" beyond its coefficients.
+//    All eight BDF tests (bdf.rs:785-1063) iterate over an empty path: "BDF
+//    parity unpinned".  Both are anchored on closed forms and SciPy instead
+//    (tests/golden/).
 //  * Arithmetic that lives in nalgebra 0.32 (crates.io, un-vendored, patch
 //    level unpinned — no Cargo.lock in the reference): column-major from_vec,
 //    row_iter, norm() = sqrt(sum x^2) accumulated in storage order, partial-

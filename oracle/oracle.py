@@ -60,6 +60,8 @@ def lib():
         L.oracle_nth_root.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_nth_root.restype = None
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_coefficients.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.oracle_coefficients.restype = C.c_int
         L.oracle_sample_paths.argtypes = [C.POINTER(_abi.Config), C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
                                           C.POINTER(_abi.Result), C.c_size_t, C.c_void_p, C.c_void_p]
         L.oracle_sample_paths.restype = C.c_int
@@ -234,3 +236,21 @@ def nth_root(x, n):
     a, b = np.empty_like(x), np.empty_like(x)
     lib().oracle_nth_root(x.ctypes.data, x.size, int(n), a.ctypes.data, b.ctypes.data)
     return a, b
+
+
+def coefficients(method, literal=False):
+    """The method's coefficient tables as the oracle's steppers use them (oracle_coefficients in oracle_capi.cpp)."""
+    n = lib().oracle_coefficients(int(method), int(bool(literal)), None, 0)
+    if n < 0:
+        raise ValueError(f"no coefficient tables for method {method}")
+    v = np.empty(n, dtype=np.float64)
+    lib().oracle_coefficients(int(method), int(bool(literal)), v.ctypes.data, n)
+    if method in (_abi.RK45, _abi.RK23):
+        o = 6 if method == _abi.RK45 else 4
+        return dict(c=v[:o], A=v[o:o + o * o].reshape(o, o), b=v[o + o * o:2 * o + o * o], e=v[2 * o + o * o:3 * o + o * o],
+                    safety=float(v[-1]))
+    if method in (_abi.BDF6, _abi.BDF2):
+        o = n // 2
+        return dict(higher=v[:o], lower=v[o:])
+    o = (n - 1) // 2
+    return dict(predictor=v[:o], corrector=v[o:2 * o], error=float(v[-1]))

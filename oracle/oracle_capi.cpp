@@ -494,6 +494,46 @@ void oracle_nth_root(const double* x, size_t n_values, int n, double* by_pow, do
     }
 }
 
+// The coefficient tables of a method as the steppers use them, flattened (tests/test_oracle.py holds them against the
+// numbers parsed out of the reference's own source text, tests/golden/reference_coefficients.json):
+//   RK45 / RK23 (O stages): c[O], A[O][O] row-major = what the stepper's row_iter() sees, b[O], e[O], safety
+//   BDF6 / BDF2           : higher[O], lower[O]
+//   Adams5 / Adams3       : predictor[O], corrector[O], error
+// Returns how many doubles the method has (and writes them if `cap` is large enough), -1 for an unknown method.
+int oracle_coefficients(int method, int literal, double* out, int cap) {
+    std::vector<double> v;
+    const bo::Mode mode = literal ? bo::Mode::Literal : bo::Mode::Corrected;
+    auto rk = [&](const auto& T, int O) {
+        for (int i = 0; i < O; ++i) v.push_back(T.c[i]);
+        for (int r = 0; r < O; ++r)
+            for (int c = 0; c < O; ++c) v.push_back(T.A[r][c]);
+        for (int i = 0; i < O; ++i) v.push_back(T.b[i]);
+        for (int i = 0; i < O; ++i) v.push_back(T.e[i]);
+        v.push_back(T.safety);
+    };
+    auto bdf = [&](const auto& Cf, int O) {
+        for (int i = 0; i < O; ++i) v.push_back(Cf.higher[i]);
+        for (int i = 0; i < O; ++i) v.push_back(Cf.lower[i]);
+    };
+    auto adams = [&](const auto& Cf, int O) {
+        for (int i = 0; i < O; ++i) v.push_back(Cf.predictor[i]);
+        for (int i = 0; i < O; ++i) v.push_back(Cf.corrector[i]);
+        v.push_back(Cf.error);
+    };
+    switch (method) {
+        case BACON_RK45: rk(bo::tableau_rkf45(mode), 6); break;
+        case BACON_RK23: rk(bo::tableau_bs23(mode), 4); break;
+        case BACON_BDF6: bdf(bo::coefficients_bdf6(), 7); break;
+        case BACON_BDF2: bdf(bo::coefficients_bdf2(), 3); break;
+        case BACON_ADAMS5: adams(bo::coefficients_adams5(), 5); break;
+        case BACON_ADAMS3: adams(bo::coefficients_adams3(), 3); break;
+        default: return -1;
+    }
+    if (out && cap >= (int)v.size())
+        for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+    return (int)v.size();
+}
+
 // x^(1/4) both ways, for the pow-vs-sqrt(sqrt) agreement test.
 void oracle_fourth_root(const double* x, size_t n, double* by_pow, double* by_sqrt) {
     for (size_t i = 0; i < n; ++i) {

@@ -337,3 +337,48 @@ def test_path_query_argument_checks_need_no_gpu():
     # n == 0 is a no-op success
     assert L.bacon_ivp_sample_paths(C.byref(cfg), rid, 0, y0.ctypes.data, p.ctypes.data, C.byref(res), 1, t.ctypes.data,
                                     out.ctypes.data) == 0
+
+
+def test_product_coefficient_tables_are_the_reference_sources():
+    """The PRODUCT's tables — the constexpr tableaux the fast kernels are compiled from and the runtime tableaux the
+    strict kernels' constant memory is filled with (bacon_b200/csrc/tableaux.cuh, adams.cuh), dumped by a host program
+    compiled from those headers (tests/tableau_dump.cu) — against the numbers parsed out of the reference's own source
+    text (tests/golden/reference_coefficients.json), bit for bit, in both semantics.  No GPU: the headers' table code is
+    host code too.  (tests/test_oracle.py holds the oracle's tables against the same file.)"""
+    import json
+    import shutil
+    import subprocess
+    import numpy as np
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = "/tmp/bacon_tableau_dump"
+    subprocess.run([nvcc, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "bacon_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "tableau_dump.cu"), "-o", exe], check=True, capture_output=True)
+    got = {}
+    for line in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.splitlines():
+        key, *words = line.split()
+        got[key] = np.array([int(w, 16) for w in words], dtype=np.uint64)
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_coefficients.json")))
+
+    def bits(x):
+        return np.ascontiguousarray(np.asarray(x, dtype=np.float64)).view(np.uint64).ravel()
+
+    for name, o in (("RK45", 6), ("RK23", 4)):
+        listed = np.array(ref[name]["k_coefficients"]["values"]).reshape(o, o)
+        corrected = listed.copy()
+        if name == "RK45":
+            assert corrected[5, 3] == 1859.0 / 4014.0  # as written (SURVEY.md D2)
+            corrected[5, 3] = 1859.0 / 4104.0
+        for flavour, want_a, safety in (("fast", corrected, 0.84), ("corrected", corrected, 0.84), ("literal", listed.T, 1.0)):
+            assert np.array_equal(got[f"{name}.{flavour}.c"], bits(ref[name]["t_coefficients"]["values"])), (name, flavour)
+            assert np.array_equal(got[f"{name}.{flavour}.b"], bits(ref[name]["avg_coefficients"]["values"])), (name, flavour)
+            assert np.array_equal(got[f"{name}.{flavour}.e"], bits(ref[name]["error_coefficients"]["values"])), (name, flavour)
+            assert np.array_equal(got[f"{name}.{flavour}.A"], bits(want_a)), (name, flavour)
+            assert np.array_equal(got[f"{name}.{flavour}.safety"], bits([84.0 / 100.0 if safety == 0.84 else 1.0])), (name, flavour)
+        assert ref["RK_safety"]["values"] == [1.0]  # what rk.rs:266-268 computes (D3); REF_LITERAL keeps it
+    for name in ("BDF6", "BDF2"):
+        assert np.array_equal(got[f"{name}.higher"], bits(ref[name]["higher_coefficients"]["values"]))
+        assert np.array_equal(got[f"{name}.lower"], bits(ref[name]["lower_coefficients"]["values"]))
+    for name in ("Adams5", "Adams3"):
+        assert np.array_equal(got[f"{name}.predictor"], bits(ref[name]["predictor_coefficients"]["values"]))
+        assert np.array_equal(got[f"{name}.corrector"], bits(ref[name]["corrector_coefficients"]["values"]))
+        assert np.array_equal(got[f"{name}.error"], bits(ref[name]["error_coefficient"]["values"]))

@@ -5,9 +5,12 @@
    vacuous empty-path outcome of the same tests in REF_LITERAL);
  * the known answers of src/tests/roots/mod.rs:169-221 for the Broyden + LU code BDF shares;
  * the predicted-answer table of SURVEY.md §8c;
- * independent anchors: closed forms and SciPy DOP853 / Radau (tests/golden/anchors.json).
-The Rust reference cannot be executed in this image: "parity unpinned" for the RK stage matrix
-and for BDF beyond these anchors (see oracle/bacon_oracle.hpp header).
+ * independent anchors: closed forms and SciPy DOP853 / Radau (tests/golden/anchors.json);
+ * every coefficient table against the numbers parsed out of the reference's source text
+   (tests/golden/reference_coefficients.json + make_reference_coefficients.py).
+The Rust reference cannot be executed in this image: "parity unpinned" for what the RK step does
+with its stage matrix on y-dependent problems and for BDF beyond these anchors (see
+oracle/bacon_oracle.hpp header).
 """
 import json
 import os
@@ -334,3 +337,52 @@ def test_oracle_is_clean_under_sanitizers():
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:abort_on_error=0", OMP_NUM_THREADS="2")
     r = subprocess.run([os.path.join(here, "_selftest")], capture_output=True, text=True, env=env)
     assert r.returncode == 0 and "selftest ok" in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+def test_coefficient_tables_are_the_reference_sources(oracle):
+    """Every coefficient table of the oracle against the numbers PARSED OUT OF THE REFERENCE'S SOURCE TEXT
+    (tests/golden/reference_coefficients.json, made in the build container by make_reference_coefficients.py from
+    /root/reference/src/ivp/{rk,bdf,adams}.rs: the Rust table expressions evaluated in IEEE double, lists in source
+    order) — bit for bit.  This pins the part of the restatement where a transcription slip would be silent: the RK
+    stage matrix, weights and error weights, the BDF and Adams coefficients, and the three defects of the tables that
+    REF_LITERAL keeps and REF_CORRECTED repairs (SURVEY.md D1 column-major fill of the row-listed matrix, D2
+    1859/4014 for Fehlberg's 1859/4104, D3 a safety factor built from 100/100)."""
+    import json
+    import os
+    from bacon_b200 import _abi
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_coefficients.json")))
+
+    def bits(x):
+        return np.asarray(x, dtype=np.float64).view(np.uint64)
+
+    for name, method, o in (("RK45", _abi.RK45, 6), ("RK23", _abi.RK23, 4)):
+        listed = np.array(ref[name]["k_coefficients"]["values"]).reshape(o, o)  # listed[i][j] = entry i*O + j of the source
+        for literal in (True, False):
+            t = oracle.coefficients(method, literal)
+            assert np.array_equal(bits(t["c"]), bits(ref[name]["t_coefficients"]["values"]))
+            assert np.array_equal(bits(t["b"]), bits(ref[name]["avg_coefficients"]["values"]))
+            assert np.array_equal(bits(t["e"]), bits(ref[name]["error_coefficients"]["values"]))
+            if literal:
+                # BSMatrix::from_vec fills column by column: M(r, c) = source[c*O + r] (D1), and the stepper reads rows of M
+                assert np.array_equal(bits(t["A"]), bits(listed.T))
+                assert t["safety"] == ref["RK_safety"]["values"][0] == 1.0  # D3
+            else:
+                want = listed.copy()  # the rows as the source's "Row i" comments label them
+                if name == "RK45":
+                    assert want[5, 3] == 1859.0 / 4014.0  # D2 as written ...
+                    want[5, 3] = 1859.0 / 4104.0           # ... and Fehlberg's coefficient
+                assert np.array_equal(bits(t["A"]), bits(want))
+                assert t["safety"] == 84.0 / 100.0
+        # consistency of the CORRECTED tableau (what D1/D2 break): row sums = nodes, weights sum to one, error weights to zero
+        t = oracle.coefficients(method, False)
+        np.testing.assert_allclose(t["A"].sum(axis=1), t["c"], rtol=0, atol=4e-16)
+        assert abs(t["b"].sum() - 1.0) <= 4e-16 and abs(t["e"].sum()) <= 4e-16
+    for name, method in (("BDF6", _abi.BDF6), ("BDF2", _abi.BDF2)):
+        t = oracle.coefficients(method)
+        assert np.array_equal(bits(t["higher"]), bits(ref[name]["higher_coefficients"]["values"]))
+        assert np.array_equal(bits(t["lower"]), bits(ref[name]["lower_coefficients"]["values"]))
+    for name, method in (("Adams5", _abi.ADAMS5), ("Adams3", _abi.ADAMS3)):
+        t = oracle.coefficients(method)
+        assert np.array_equal(bits(t["predictor"]), bits(ref[name]["predictor_coefficients"]["values"]))
+        assert np.array_equal(bits(t["corrector"]), bits(ref[name]["corrector_coefficients"]["values"]))
+        assert t["error"] == ref[name]["error_coefficient"]["values"][0] == 19.0 / 270.0
