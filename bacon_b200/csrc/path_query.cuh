@@ -11,9 +11,10 @@
 // last record (a failed trajectory, or the unyielded last block of SURVEY.md D9; Euler, whose records are the OLD
 // points, ivp.rs:331-337), closes the path.
 //
-//   path_sample_kernel   one thread per (trajectory, sample time): binary search over the trajectory's knots, two
+//   path_sample_kernel   one thread per (trajectory, sample time): a search over the trajectory's knot times
+//                        (bisection down to 64 knots, then interpolation: PathView::first_knot_at_or_after), two
 //                        records in, D doubles out; neighbouring lanes take neighbouring times of ONE trajectory, so
-//                        their probes share sectors and their stores are contiguous.
+//                        their probes share lines and their stores are contiguous.
 //   path_events_kernel   one warp per trajectory: the warp streams the path 32 records at a time (coalesced: a
 //                        record is 8(1 + D) bytes, a D = 3 chunk is 1 KB), each lane tests g(y) = w . y - c for a sign
 //                        change against its left neighbour, and the rare lane that finds one locates the root of the

@@ -3,8 +3,9 @@
 // state does not fit one thread, so the interpolation is done by a WARP: lane d owns component d of both knots and of
 // both slopes, and row d of the trajectory's matrix; f = A y takes the other components through shared memory, in the oracle's
 // order (s = A[d][0] y[0]; s += A[d][k] y[k]), so the strict build stays bit-comparable with oracle/oracle_capi.cpp.
-//   path_sample_warp32_kernel   one warp per (trajectory, up to 32 sample times): one bisection per lane, then the warp interpolates;
-//                               both knots come in as coalesced 256-byte rows, the sample leaves as one.
+//   path_sample_warp32_kernel   one warp per (trajectory, up to 32 sample times): one knot search per lane, then the warp interpolates;
+//                               the knots of 16 samples come in at once as asynchronous copies of coalesced 256-byte
+//                               rows, the sample leaves as one.
 //   events                      the streaming kernel is path_query.cuh's (one lane per record, g accumulated over the
 //                               record's 32 components); queued crossings are located by the whole warp, one at a time.
 #pragma once
@@ -182,7 +183,7 @@ __device__ __forceinline__ double knot_component32(const PathView<32>& pv, uint3
 }
 
 // Sample times one warp takes of its trajectory.  The 8 KB matrix (row d in lane d's registers) is loaded once per warp
-// and serves them all, and the bisections of all its times run side by side, one per lane (one warp per sample re-read
+// and serves them all, and the knot searches of all its times run side by side, one per lane (one warp per sample re-read
 // the matrix per sample and searched with all 32 lanes in lockstep: 14.1 ms for 2^18 x 16 samples; 8 times per warp,
 // searched one after the other: 7.6 ms; profiles/r01o_path_queries.md).
 constexpr int WARP32_TIMES = 32;
