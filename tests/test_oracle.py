@@ -386,3 +386,45 @@ def test_coefficient_tables_are_the_reference_sources(oracle):
         assert np.array_equal(bits(t["predictor"]), bits(ref[name]["predictor_coefficients"]["values"]))
         assert np.array_equal(bits(t["corrector"]), bits(ref[name]["corrector_coefficients"]["values"]))
         assert t["error"] == ref[name]["error_coefficient"]["values"][0] == 19.0 / 270.0
+
+
+@pytest.mark.parametrize("as_written", [True, False])
+def test_rk_second_reading_agrees_bit_for_bit_on_y_dependent_problems(oracle, as_written):
+    """tests/rk_second_reading.py — rk.rs:249-423 and ivp.rs:220-238 read a second time, in plain Python over the
+    coefficient lists parsed out of the reference's source — against the oracle on the problems no reference test
+    covers: y-DEPENDENT right-hand sides (Lorenz, Van der Pol with per-trajectory mu), both pairs, both semantics.
+    Every yielded (time, state), the step counts and the exit dt, bit for bit."""
+    import rk_second_reading as R2
+    sem = _abi.SEM_LITERAL if as_written else _abi.SEM_CORRECTED
+    cases = []
+    y0 = E.lorenz_y0(np.arange(6))
+    P = np.array(E.LORENZ["params"])
+    cases.append(("RK45", _abi.RK45, "lorenz", R2.lorenz, y0, np.tile(P[:, None], (1, 6)), dict(dt_min=1e-9, dt_max=0.1, tol=1e-8, t_start=0.0, t_end=0.4)))
+    cases.append(("RK23", _abi.RK23, "lorenz", R2.lorenz, y0, np.tile(P[:, None], (1, 6)),
+                  dict(dt_min=1e-9, dt_max=0.1, tol=1e-5, t_start=0.0, t_end=0.05)))
+    yv, mu = E.vdp_problem(np.arange(6) * (E.VDP["n"] // 6), E.VDP["n"])
+    cases.append(("RK23", _abi.RK23, "vdp", R2.vdp, yv, mu, dict(dt_min=1e-12, dt_max=0.1, tol=1e-8, t_start=0.0, t_end=0.05)))
+    cases.append(("RK45", _abi.RK45, "vdp", R2.vdp, yv, mu, dict(dt_min=1e-12, dt_max=0.1, tol=1e-9, t_start=0.0, t_end=0.3)))
+    for name, method, rhs, f, y, p, cfg in cases:
+        cap = 4096
+        # (as written, the tables can make a path crawl at dt ~ 1e-9 for 1e8 attempts: both readings are cut short there —
+        # the oracle by its attempt cap, the second reading after 600 points — and the common prefix is compared)
+        ref = oracle.solve_ensemble(method, rhs, y, p, semantics=sem, history_capacity=cap, pow_mode=0,
+                                    max_attempts=4000 if as_written else 0, **cfg)
+        for i in range(y.shape[1]):
+            path, status, (n_acc, n_rej), (t_fin, dt_fin, y_fin) = R2.solve(name, f, list(y[:, i]), list(p[:, i]), as_written=as_written,
+                                                                           max_points=600 if as_written else cap, **cfg)
+            m = min(int(ref["hist_len"][i]), len(path))
+            assert m > (0 if as_written else 10), (name, rhs, i)
+            t2 = np.array([q[0] for q in path[:m]])
+            y2 = np.array([q[1] for q in path[:m]], dtype=np.float64)
+            assert np.array_equal(t2.view(np.uint64), ref["hist_t"][i, :m].view(np.uint64)), (name, rhs, i)
+            assert np.array_equal(y2.view(np.uint64), np.ascontiguousarray(ref["hist_y"][i, :m]).view(np.uint64)), (name, rhs, i)
+            if as_written and (status == "Truncated" or ref["status"][i] == _abi.E_MAX_ATTEMPTS):
+                continue
+            assert status != "Truncated", (name, rhs, i, len(path))
+            assert status == ("Done" if ref["status"][i] == _abi.OK else "MinimumTimeDeltaExceeded"), (name, rhs, i)
+            assert n_acc == ref["n_accept"][i] and n_rej == ref["n_reject"][i], (name, rhs, i, n_acc, n_rej)
+            assert len(path) == int(ref["hist_len"][i])
+            assert np.array_equal(np.array(y_fin, dtype=np.float64).view(np.uint64), np.ascontiguousarray(ref["y_end"][:, i]).view(np.uint64))
+            assert np.float64(dt_fin).view(np.uint64) == ref["dt_end"][i].view(np.uint64) and t_fin == ref["t_end"][i]
