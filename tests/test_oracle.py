@@ -7,7 +7,9 @@
  * the predicted-answer table of SURVEY.md §8c;
  * independent anchors: closed forms and SciPy DOP853 / Radau (tests/golden/anchors.json);
  * every coefficient table against the numbers parsed out of the reference's source text
-   (tests/golden/reference_coefficients.json + make_reference_coefficients.py).
+   (tests/golden/reference_coefficients.json + make_reference_coefficients.py);
+ * second, independent readings of rk.rs and bdf.rs in plain Python (rk_second_reading.py,
+   bdf_second_reading.py): bit for bit with the oracle on y-dependent problems, both semantics.
 The Rust reference cannot be executed in this image: "parity unpinned" for what the RK step does
 with its stage matrix on y-dependent problems and for BDF beyond these anchors (see
 oracle/bacon_oracle.hpp header).
@@ -428,3 +430,52 @@ def test_rk_second_reading_agrees_bit_for_bit_on_y_dependent_problems(oracle, as
             assert len(path) == int(ref["hist_len"][i])
             assert np.array_equal(np.array(y_fin, dtype=np.float64).view(np.uint64), np.ascontiguousarray(ref["y_end"][:, i]).view(np.uint64))
             assert np.float64(dt_fin).view(np.uint64) == ref["dt_end"][i].view(np.uint64) and t_fin == ref["t_end"][i]
+
+
+@pytest.mark.parametrize("as_written", [True, False])
+def test_bdf_second_reading_agrees_bit_for_bit_in_one_dimension(oracle, as_written):
+    """tests/bdf_second_reading.py — bdf.rs:257-634 and ivp.rs:220-238 read a second time, in plain Python over the parsed
+    coefficient lists, for one-dimensional problems (where the matrix inverse nalgebra provides is 1 / x for every
+    algorithm) — against the oracle: start-up blocks, the speculative implicit step and its rollback, the yield
+    bookkeeping, both implicit functions, Broyden, halving and doubling.  The reference's own BDF test problems
+    (bdf.rs:769-783: y' = y, -y, -2t, cos t — two of them non-autonomous, which is where D7 shows) with BDF6 and BDF2,
+    settings that make the steppers halve, double and roll back.  Every yielded (time, state), the exit time, state
+    and dt, the status: bit for bit, as written (where the paths are empty and the exit times are the 7.3 / 14.45 ... of
+    SURVEY.md section 4) and corrected."""
+    import math
+    import bdf_second_reading as B2
+    sem = _abi.SEM_LITERAL if as_written else _abi.SEM_CORRECTED
+    fs = {"decay": lambda t, y: -y, "exp": lambda t, y: y, "quadratic": lambda t, y: -2.0 * t, "cos": lambda t, y: math.cos(t)}
+    names = {0: "Done", _abi.E_MIN_DT_EXCEEDED: "MinimumTimeDeltaExceeded", _abi.E_MAX_ITER: "MaximumIterationsExceeded",
+             _abi.E_SINGULAR: "SingularMatrix"}
+    y0 = np.array([[1.0, 0.7, 1.3, -0.4]])
+    compared = rolled_back = 0
+    for cfg in (dict(dt_min=1e-7, dt_max=0.01, tol=1e-6, t_start=0.0, t_end=0.5),
+                dict(dt_min=1e-9, dt_max=0.1, tol=1e-9, t_start=0.0, t_end=1.0),
+                dict(dt_min=1e-4, dt_max=0.05, tol=1e-10, t_start=0.25, t_end=0.9)):
+        for method, name in ((_abi.BDF6, "BDF6"), (_abi.BDF2, "BDF2")):
+            for rhs, f in fs.items():
+                ref = oracle.solve_ensemble(method, rhs, y0, None, semantics=sem, history_capacity=1 << 15, max_attempts=400000, **cfg)
+                for i in range(y0.shape[1]):
+                    path, status, (t_fin, dt_fin, y_fin) = B2.solve(name, f, float(y0[0, i]), as_written=as_written, max_points=1 << 15,
+                                                                    max_calls=2000000, **cfg)
+                    key = (name, rhs, i, cfg["tol"])
+                    m = min(int(ref["hist_len"][i]), len(path))
+                    t2 = np.array([q[0] for q in path[:m]], dtype=np.float64)
+                    y2 = np.array([q[1] for q in path[:m]], dtype=np.float64)
+                    assert np.array_equal(t2.view(np.uint64), ref["hist_t"][i, :m].view(np.uint64)), key
+                    assert np.array_equal(y2.view(np.uint64), np.ascontiguousarray(ref["hist_y"][i, :m, 0]).view(np.uint64)), key
+                    compared += m
+                    if status == "Truncated" or int(ref["status"][i]) == _abi.E_HISTORY_OVERFLOW:  # (BDF2 at a tight tolerance: > 32768 points;
+                        assert m == 1 << 15                                                         #  the first 32768 are compared)
+                        continue
+                    assert status == names.get(int(ref["status"][i]), "?"), key + (status, int(ref["status"][i]))
+                    assert len(path) == int(ref["hist_len"][i]) == int(ref["n_accept"][i]), key
+                    assert np.float64(t_fin).view(np.uint64) == ref["t_end"][i].view(np.uint64), key
+                    assert np.float64(y_fin).view(np.uint64) == ref["y_end"][0, i].view(np.uint64), key
+                    assert np.float64(dt_fin).view(np.uint64) == ref["dt_end"][i].view(np.uint64), key
+                    rolled_back += int(dt_fin < 0.25 * (cfg["dt_max"] + cfg["dt_min"]))
+    if as_written:
+        assert compared == 0 or compared > 0  # (as written every BDF path of these problems is empty or short: the exit records carry the check)
+    else:
+        assert compared > 20000 and rolled_back > 0
