@@ -24,7 +24,8 @@
 //    parity unpinned".  Both are anchored on closed forms and SciPy instead
 //    (tests/golden/), and on SECOND, independent readings of the same Rust
 //    source in plain Python (tests/rk_second_reading.py,
-//    tests/bdf_second_reading.py) that agree with this file bit for bit.
+//    tests/bdf_second_reading.py, tests/adams_second_reading.py) that agree
+//    with this file bit for bit.
 //  * Arithmetic that lives in nalgebra 0.32 (crates.io, un-vendored, patch
 //    level unpinned — no Cargo.lock in the reference): column-major from_vec,
 //    row_iter, norm() = sqrt(sum x^2) accumulated in storage order, partial-

@@ -8,8 +8,9 @@
  * independent anchors: closed forms and SciPy DOP853 / Radau (tests/golden/anchors.json);
  * every coefficient table against the numbers parsed out of the reference's source text
    (tests/golden/reference_coefficients.json + make_reference_coefficients.py);
- * second, independent readings of rk.rs and bdf.rs in plain Python (rk_second_reading.py,
-   bdf_second_reading.py): bit for bit with the oracle on y-dependent problems, both semantics.
+ * second, independent readings of rk.rs, bdf.rs and adams.rs in plain Python (rk_second_reading.py,
+   bdf_second_reading.py, adams_second_reading.py): bit for bit with the oracle on y-dependent
+   problems, both semantics.
 The Rust reference cannot be executed in this image: "parity unpinned" for what the RK step does
 with its stage matrix on y-dependent problems and for BDF beyond these anchors (see
 oracle/bacon_oracle.hpp header).
@@ -479,3 +480,49 @@ def test_bdf_second_reading_agrees_bit_for_bit_in_one_dimension(oracle, as_writt
         assert compared == 0 or compared > 0  # (as written every BDF path of these problems is empty or short: the exit records carry the check)
     else:
         assert compared > 20000 and rolled_back > 0
+
+
+@pytest.mark.parametrize("as_written", [True, False])
+def test_adams_second_reading_agrees_bit_for_bit(oracle, as_written):
+    """tests/adams_second_reading.py — adams.rs:249-561 and ivp.rs:220-238 read a second time, in plain Python over the
+    parsed coefficient lists — against the oracle on y-dependent problems in two and three dimensions (the harmonic
+    oscillator with per-trajectory frequency, Lorenz), Adams5 and Adams3: every yielded (time, state), the exit time,
+    state and dt, the status, bit for bit; as written (where D10 makes every start-up block end in a reject and the
+    paths grow like 1/tol: the first 4096 points are compared) and with D10 repaired."""
+    import adams_second_reading as A2
+    import rk_second_reading as R2
+    sem = _abi.SEM_LITERAL if as_written else _abi.SEM_CORRECTED
+    cap = 4096
+
+    def harmonic(_t, y, p):
+        return [y[1], -(p[0] * p[0]) * y[0]]
+
+    cases = [("harmonic", harmonic, np.array([[1.0, 0.5, -0.8], [0.0, 0.3, 1.1]]), np.array([[2.0, 3.0, 0.7]]),
+              dict(dt_min=1e-6, dt_max=0.1, tol=1e-6, t_start=0.0, t_end=1.0)),
+             ("lorenz", R2.lorenz, E.lorenz_y0(np.arange(3)), np.tile(np.array(E.LORENZ["params"])[:, None], (1, 3)),
+              dict(dt_min=1e-9, dt_max=0.01, tol=1e-4, t_start=0.0, t_end=0.2))]
+    compared = 0
+    for method, name in ((_abi.ADAMS5, "Adams5"), (_abi.ADAMS3, "Adams3")):
+        for rhs, f, y0, p, cfg in cases:
+            ref = oracle.solve_ensemble(method, rhs, y0, p, semantics=sem, history_capacity=cap, pow_mode=0,
+                                        max_attempts=60000 if as_written else 0, **cfg)
+            for i in range(y0.shape[1]):
+                path, status, (t_fin, dt_fin, y_fin) = A2.solve(name, f, list(y0[:, i]), list(p[:, i]), as_written=as_written,
+                                                                max_points=cap, **cfg)
+                key = (name, rhs, i)
+                m = min(len(path), int(ref["hist_len"][i]))
+                assert m > 10, key
+                t2 = np.array([q[0] for q in path[:m]], dtype=np.float64)
+                y2 = np.array([q[1] for q in path[:m]], dtype=np.float64)
+                assert np.array_equal(t2.view(np.uint64), ref["hist_t"][i, :m].view(np.uint64)), key
+                assert np.array_equal(y2.view(np.uint64), np.ascontiguousarray(ref["hist_y"][i, :m]).view(np.uint64)), key
+                compared += m
+                if status == "Truncated" or int(ref["status"][i]) in (_abi.E_HISTORY_OVERFLOW, _abi.E_MAX_ATTEMPTS):
+                    assert as_written, key  # (only the as-written paths are that long)
+                    continue
+                assert status == "Done" and int(ref["status"][i]) == _abi.OK, key
+                assert len(path) == int(ref["hist_len"][i]) == int(ref["n_accept"][i]), key
+                assert np.float64(t_fin).view(np.uint64) == ref["t_end"][i].view(np.uint64), key
+                assert np.array_equal(np.array(y_fin, dtype=np.float64).view(np.uint64), np.ascontiguousarray(ref["y_end"][:, i]).view(np.uint64)), key
+                assert np.float64(dt_fin).view(np.uint64) == ref["dt_end"][i].view(np.uint64), key
+    assert compared > 5000
